@@ -1,0 +1,74 @@
+"""Pin the oracle: every golden vector produced by RUNNING THE REFERENCE
+(oracle/make_golden.py) must be reproduced by the CPU restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_files
+from oracle import ann as oann
+from oracle import infonce as oinf
+
+
+@pytest.mark.parametrize("path", golden_files("loss_"), ids=os.path.basename)
+def test_loss_closed_form_matches_reference_fp64(path):
+    g = np.load(path)
+    out = oinf.clip_loss_closed_form(g["image"], g["profile"], float(g["logit_scale"]), int(g["buckets"]))
+    assert out["loss"] == pytest.approx(float(g["loss_f64"]), rel=1e-12)
+    for k_o, k_g in (("d_image", "d_image_f64"), ("d_profile", "d_profile_f64")):
+        ref = g[k_g]
+        err = np.abs(out[k_o] - ref).max() / max(np.abs(ref).max(), 1e-300)
+        assert err < 1e-10, (k_o, err)
+    assert out["d_logit_scale"] == pytest.approx(float(g["d_logit_scale_f64"]), rel=1e-9, abs=1e-14)
+
+
+@pytest.mark.parametrize("path", golden_files("loss_"), ids=os.path.basename)
+def test_loss_torch_port_matches_reference_fp32(path):
+    import torch
+    g = np.load(path)
+    x = torch.tensor(g["image"], requires_grad=True)
+    y = torch.tensor(g["profile"], requires_grad=True)
+    ls = torch.tensor(float(g["logit_scale"]), dtype=torch.float32, requires_grad=True)
+    loss = oinf.clip_loss_materialised(x, y, ls, int(g["buckets"]))
+    loss.backward()
+    # same op sequence as the reference => bitwise or last-ulp agreement in fp32
+    assert float(loss) == pytest.approx(float(g["loss_f32"]), rel=2e-6)
+    np.testing.assert_allclose(x.grad.numpy(), g["d_image_f32"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(y.grad.numpy(), g["d_profile_f32"], rtol=1e-4, atol=1e-7)
+    assert float(ls.grad) == pytest.approx(float(g["d_logit_scale_f32"]), rel=1e-3, abs=1e-6)
+
+
+@pytest.mark.parametrize("path", golden_files("ann_"), ids=os.path.basename)
+def test_ann_restatement_matches_reference(path):
+    g = np.load(path)
+    k = int(g["k"])
+    clf = oann.OracleANNClassifier(g["gallery"], g["labels"], n_neighbors=32, metric="euclidean")
+    qs = [g[f"query{m}"] for m in range(2) if f"query{m}" in g]
+    nb = clf.kneighbors(*qs, k=k, epsilon=.3)
+    for m, (i, dd) in enumerate(nb):
+        assert i.dtype == np.int32 and dd.dtype == np.float32
+        np.testing.assert_array_equal(i, g[f"idx{m}"])
+        np.testing.assert_array_equal(dd, g[f"dist{m}"])
+    np.testing.assert_array_equal(clf.predict(*qs, k=k, epsilon=.3), g["pred"])
+
+
+def test_weighted_vote_matches_sklearn():
+    from sklearn.utils.extmath import weighted_mode
+    r = np.random.default_rng(0)
+    cls = r.integers(0, 5, (200, 9))
+    w = r.random((200, 9)).astype(np.float32)
+    w[:20] = 1.0  # exact ties -> lowest class id must win
+    ref, _ = weighted_mode(cls, w, axis=1)
+    np.testing.assert_array_equal(oann.weighted_vote(cls, w), ref.astype(int).ravel())
+
+
+def test_zero_distance_weights():
+    d = np.array([[0.0, 0.5, 0.0], [0.25, 0.5, 1.0]], dtype=np.float32)
+    w = oann.inverse_distance_weights(d)
+    np.testing.assert_array_equal(w[0], [1, 0, 1])
+    np.testing.assert_allclose(w[1], [4, 2, 1])
+
+
+def test_bucket_divisibility_assert():
+    with pytest.raises(AssertionError, match="divisible"):
+        oinf.clip_loss_closed_form(np.ones((6, 4)), np.ones((6, 4)), buckets=4)
