@@ -1,0 +1,172 @@
+/*
+ * plk.h -- C ABI of libplk.so: the B200-native (sm_100a) cross-modal similarity
+ * hot path of imveikka/multimodal_plankton_recognition.
+ *
+ * The path is S = normalize(I) . normalize(P)^T consumed by
+ *   (1) the symmetric CLIP-style InfoNCE coordination loss, forward + backward
+ *       (reference src/coordination.py:17-47, autograd backward of the same graph), and
+ *   (2) euclidean / cosine top-k retrieval + inverse-distance weighted k-NN vote
+ *       (reference src/ann.py:6-34, driven by reference scripts/benchmark_cross.py:24-96).
+ *
+ * Conventions (all entry points)
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - the caller allocates every input, output and workspace; the library never
+ *     frees or retains a pointer past the call and never synchronises: all work
+ *     is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 = PLK_OK, negative = error (see enum); the message is
+ *     available from plk_last_error() (thread-local).  No exceptions cross the ABI.
+ *   - shapes are row-major; `ld*` arguments are leading dimensions in ELEMENTS.
+ *   - operand dtype `op_dtype` selects the arithmetic path:
+ *       PLK_F32  : fp32 CUDA-core path (parity mode, <=1e-5 rel vs the reference)
+ *       PLK_BF16 : tcgen05 bf16 MMA, fp32 TMEM accumulators (<=2e-3 rel)
+ *     There is no CPU fallback.
+ */
+#ifndef PLK_H_
+#define PLK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum plk_status {
+  PLK_OK = 0,
+  PLK_ERR_INVALID = -1,     /* bad shape / dtype / null pointer / alignment       */
+  PLK_ERR_UNSUPPORTED = -2, /* valid request this build cannot serve (e.g. d>512 bf16) */
+  PLK_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed                */
+  PLK_ERR_ARCH = -4         /* device is not sm_100 (tcgen05 path needs it)       */
+};
+
+enum plk_dtype { PLK_F32 = 0, PLK_BF16 = 1, PLK_F16 = 2 };
+
+int plk_version(void);
+const char* plk_last_error(void);
+/* 1 if the current device can run the tcgen05 (PLK_BF16) kernels. */
+int plk_device_supports_tc(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t plk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a2. L2 normalisation   u = x / max(||x||_2, 1e-12)            reference src/coordination.py:33-34
+ *   x        [n, d]      x_dtype in {F32, BF16, F16}, leading dim ldx
+ *   u        [n, ldu]    u_dtype in {F32, BF16}; columns d..ldu-1 are written as zero (the
+ *                        tcgen05 path wants ldu = d rounded up to 64)
+ *   inv_den  [n]  fp32   1 / max(||x||, eps)
+ *   nrm      [n]  fp32   ||x||           (needed by the backward to detect the eps clamp)
+ *   sqn      [n]  fp32   ||u||^2 of the values actually WRITTEN to u (after rounding);
+ *                        nullable.  Retrieval uses it for |g|^2 - 2 q.g ranking.
+ * ------------------------------------------------------------------------------------------ */
+int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx,
+                   void* u, int u_dtype, int64_t ldu, float* inv_den, float* nrm, float* sqn,
+                   int normalise /* 0: plain cast/copy (retrieval on pre-normalised data) */,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3-a7. Fused similarity + temperature + online row/column sum-exp + diagonal.
+ *        replaces: bmm, *exp(logit_scale), 2x cross_entropy       reference src/coordination.py:36-44
+ *
+ *   u [n_rows, ld]   normalised rows OWNED by this call (global row index = row_offset + i)
+ *   v [n_cols, ld]   normalised rows of the other modality for the WHOLE (global) batch
+ *   S_ij = exp(*logit_scale) * u_i . v_j, restricted to j in the bucket of global row i
+ *          (bucket b = global_i / bucket_size, columns [b*bs, (b+1)*bs)).
+ *   Fixed shift: because |u.v| <= 1, E_ij = exp(S_ij - s) never overflows, so ONE exp
+ *   serves the row and the column sums (valid for s = exp(logit_scale) <= 64).
+ *
+ *   row_sumexp [n_rows]  OUT  sum_j E_ij                (complete)
+ *   col_sumexp [n_cols]  OUT  sum_{i owned} E_ij        (partial when rows are sharded)
+ *   diag       [n_rows]  OUT  S_ii (global diagonal)
+ *   logit_scale          device pointer to the 0-dim fp32 parameter (no host sync).
+ * ------------------------------------------------------------------------------------------ */
+int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld,
+                    int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
+                    int64_t bucket_size, const float* logit_scale,
+                    float* row_sumexp, float* col_sumexp, float* diag, void* stream);
+
+/* a8. loss partial over owned rows:
+ *   *loss_out = (1/(2*B_global)) * sum_i [ 2 s + log R_i + log C_i - 2 S_ii ]      reference src/coordination.py:45
+ *   col_sumexp_own points at the n_rows entries of the (all-reduced) column sums that
+ *   belong to the owned rows.  Also writes sum_i S_ii to *diag_sum_out (used by d logit_scale). */
+int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const float* diag,
+                     const float* logit_scale, int64_t n_rows, int64_t batch_global,
+                     float* loss_out, float* diag_sum_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9. Recompute backward, one direction (flash-style: logits are never materialised).
+ *   acc_i = sum_j  E_ij (1/rs_i + 1/cs_j) * b_j            for the owned rows i
+ *   a [n_rows, ld] owned normalised rows, b [n_cols, ld] all normalised rows of the other
+ *   modality, rs [n_rows] the sum-exp along a's rows, cs [n_cols] the sum-exp along b's rows.
+ *   Direction image:   (a,b,rs,cs) = (u, v, row_sumexp, col_sumexp)
+ *   Direction profile: (a,b,rs,cs) = (v, u, col_sumexp, row_sumexp)   (S is symmetric in roles)
+ *   acc  [parts, n_rows, d] fp32 OUT: `parts` partial sums (column sweep split across CTAs to fill
+ *        the 148 SMs; parts = plk_infonce_grad_parts(...)); plk_infonce_grad_finish adds them.
+ *   gs   nullable; OUT scalar  sum_ij E_ij (1/rs_i + 1/cs_j) S_ij   (for d logit_scale)
+ * ------------------------------------------------------------------------------------------ */
+int plk_infonce_grad_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
+                           int64_t bucket_size);
+int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld,
+                     int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
+                     int64_t bucket_size, const float* logit_scale,
+                     const float* rs, const float* cs, float* acc, float* gs, void* stream);
+
+/* a9 (tail). Adds the -2*delta_ij term, applies g*s/(2B) and the normalisation backward:
+ *   acc_i = sum over the `parts` slabs of acc;
+ *   dU_i = coef * (acc_i - 2 p_i / den_p_i),  coef = (*grad_out) * s / (2 B_global)
+ *   dx_i = (dU_i - u_i (u_i . dU_i)) / den_i      if ||x_i|| > eps,   else dU_i / eps
+ *   x, partner: RAW embeddings [n, d] of this modality / the other one (same rows).
+ *   dx [n, d] written in dx_dtype. */
+int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const void* partner, int x_dtype,
+                            int64_t n, int64_t d, int64_t ldx,
+                            const float* inv_den_x, const float* nrm_x, const float* inv_den_p,
+                            const float* logit_scale, const float* grad_out, int64_t batch_global,
+                            void* dx, int dx_dtype, void* stream);
+
+/* d logit_scale partial:  *dls_out = (*grad_out) / (2 B_global) * (*gs - 2 * *diag_sum) */
+int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_out,
+                    int64_t batch_global, float* dls_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a12. k-nearest candidates by euclidean distance (ranking key |g|^2 - 2 q.g).
+ *      replaces pynndescent NNDescent.query                        reference src/ann.py:15-16
+ *   q [nq, ld], g [ng, ld] in op_dtype; g_sqn [ng] = ||g_j||^2 (from plk_l2norm_fwd).
+ *   Writes the kc best gallery indices per query (unordered quality: sorted by the
+ *   op_dtype key, ascending), global index = gallery_offset + local row.
+ *   cand_idx [nq, kc] int32 (-1 pads when ng < kc), cand_key [nq, kc] fp32.
+ *   workspace: plk_topk_workspace_bytes() bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t plk_topk_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int kc, int op_dtype);
+int plk_topk_candidates(const void* q, const void* g, int op_dtype, int64_t ld,
+                        const float* g_sqn, int64_t nq, int64_t ng, int64_t d, int kc,
+                        int64_t gallery_offset, int32_t* cand_idx, float* cand_key,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact re-score of candidates: dist = sqrt(sum (q-g)^2) accumulated in fp64 from the fp32
+ * vectors, rounded to fp32, sorted ascending by (dist, index); keeps the k best.
+ *   q32 [nq, d], g32 [ng, d] fp32; cand_idx [nq, m] global indices, -1 = empty;
+ *   local gallery row = cand_idx - gallery_offset.
+ *   out_idx [nq, k] int32, out_dist [nq, k] fp32 (+inf / -1 pads). */
+int plk_topk_rescore(const float* q32, const float* g32, int64_t nq, int64_t ng, int64_t d,
+                     const int32_t* cand_idx, int m, int64_t gallery_offset, int k,
+                     float* scratch /* [nq, m] fp32 */, int32_t* out_idx, float* out_dist,
+                     void* stream);
+
+/* Merge per-shard results: cand [nq, m] (idx, dist) -> k best by (dist, idx).  -1 = empty. */
+int plk_topk_merge(const int32_t* cand_idx, const float* cand_dist, int64_t nq, int m, int k,
+                   int32_t* out_idx, float* out_dist, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a13/a14. inverse-distance weighted vote                          reference src/ann.py:19-34
+ *   idx/dist [nq, m] neighbour lists (already h-stacked over query modalities),
+ *   labels [ng] int64 class of each gallery row.  w = 1/dist (fp32); a row containing a
+ *   zero distance votes only with its zero-distance neighbours (weight 1).  Per-class sums
+ *   in fp64, ties -> lowest class id.   pred [nq] int64.
+ * ------------------------------------------------------------------------------------------ */
+int plk_knn_vote(const int32_t* idx, const float* dist, int64_t nq, int m,
+                 const int64_t* labels, int64_t ng, int64_t* pred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLK_H_ */

@@ -1,0 +1,11 @@
+"""B200-native (sm_100a) cross-modal similarity hot path of
+imveikka/multimodal_plankton_recognition: the fused similarity + InfoNCE coordination loss
+(``CLIPLoss``, drop-in for reference src/coordination.py:17-47) and euclidean/cosine top-k retrieval
+with the inverse-distance k-NN vote (``ANNClassifier``, drop-in for reference src/ann.py:6-34).
+
+All arithmetic runs in ``libplk.so`` (hand-written CUDA, C ABI in ``include/plk.h``).
+"""
+from .coordination import CLIPLoss  # noqa: F401
+from .ann import ANNClassifier  # noqa: F401
+
+__all__ = ["CLIPLoss", "ANNClassifier"]

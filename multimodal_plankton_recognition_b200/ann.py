@@ -1,0 +1,142 @@
+"""Drop-in for reference src/ann.py: ``ANNClassifier`` -- k-nearest-neighbour retrieval in the shared
+embedding space + inverse-distance weighted vote, on the GPU.
+
+Same surface as the reference class: ``ANNClassifier(X, y, **nndescent_args)`` stores ``y_`` and an
+``index`` exposing ``query(x, k=, epsilon=) -> (int32 [Nq,k], float32 [Nq,k])``;
+``kneighbors(*X, **query_args)`` returns one (idx, dist) pair per positional query modality;
+``predict(*X, **query_args)`` h-stacks the neighbour lists and returns int labels ``[Nq]``
+(reference src/ann.py:9-25); ``_get_weights(dist)`` keeps the reference semantics (reference src/ann.py:28-34).
+Inputs and outputs are numpy arrays on the host, as in scripts/benchmark_cross.py:57-86.
+
+The reference delegates the search to pynndescent's approximate NN-descent graph configured
+"to mimic deterministic NN-search"; here the search is EXACT: candidates from the fused
+similarity kernel (tcgen05 bf16 or fp32 CUDA cores), then an exact re-score
+sqrt(sum((q-g)^2)) accumulated in fp64 and rounded to fp32, ordered by (distance, index).
+pynndescent's constructor / query keywords (n_neighbors, metric, diversify_prob,
+pruning_degree_multiplier, low_memory, random_state, epsilon) are accepted and ignored, except
+that a metric other than 'euclidean' raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import PLK_BF16, PLK_F32
+
+
+class GpuExactIndex:
+    """Gallery resident in HBM: fp32 rows (exact re-score) + operand copy (bf16 padded or fp32)
+    + squared norms.  ``gallery_offset`` makes returned indices global when the gallery is a shard."""
+
+    def __init__(self, X, precision: str = "bf16", device=None, gallery_offset: int = 0, slack: int = 6):
+        if precision not in ops.MODES:
+            raise ValueError(f"precision must be one of {sorted(ops.MODES)}, got {precision!r}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("ANNClassifier needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.mode = ops.MODES[precision]
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        if X.ndim != 2 or X.shape[0] == 0:
+            raise ValueError(f"gallery must be a non-empty [N, d] array, got shape {X.shape}")
+        self.n, self.d = X.shape
+        self.gallery_offset = int(gallery_offset)
+        self.slack = int(slack)
+        self.g32 = torch.from_numpy(X).to(self.device)
+        self.g_op, _, _, self.g_sqn = ops.l2norm(self.g32, self.mode, normalise=False)
+
+    def prepare(self):  # pynndescent API parity (reference src/ann.py:12)
+        return None
+
+    # -- device-level search: q32 [nq, d] fp32 on device -> (idx int32 [nq,k], dist fp32 [nq,k]) --
+    def search_device(self, q32: torch.Tensor, k: int):
+        lib = self.lib
+        nq = q32.shape[0]
+        kmax = 32 if self.mode == PLK_BF16 else 64
+        if k < 1 or k > kmax:
+            raise ValueError(f"k must be in [1, {kmax}] for this precision, got {k}")
+        kc = min(kmax, max(k + self.slack, 16 if self.mode == PLK_BF16 else k + self.slack))
+        q_op, _, _, _ = ops.l2norm(q32, self.mode, normalise=False)
+        dev = self.device
+        cand_idx = torch.empty((nq, kc), device=dev, dtype=torch.int32)
+        cand_key = torch.empty((nq, kc), device=dev, dtype=torch.float32)
+        ws_bytes = lib.plk_topk_workspace_bytes(nq, self.n, self.d, kc, self.mode)
+        ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
+        out_idx = torch.empty((nq, k), device=dev, dtype=torch.int32)
+        out_dist = torch.empty((nq, k), device=dev, dtype=torch.float32)
+        scratch = torch.empty((nq, kc), device=dev, dtype=torch.float32)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            lib.check(lib.plk_topk_candidates(q_op.data_ptr(), self.g_op.data_ptr(), self.mode, q_op.stride(0),
+                                              self.g_sqn.data_ptr(), nq, self.n, self.d, kc,
+                                              self.gallery_offset, cand_idx.data_ptr(), cand_key.data_ptr(),
+                                              ws.data_ptr(), ws_bytes, st), "plk_topk_candidates")
+            lib.check(lib.plk_topk_rescore(q32.data_ptr(), self.g32.data_ptr(), nq, self.n, self.d,
+                                           cand_idx.data_ptr(), kc, self.gallery_offset, k,
+                                           scratch.data_ptr(), out_idx.data_ptr(), out_dist.data_ptr(), st),
+                      "plk_topk_rescore")
+        return out_idx, out_dist
+
+    def query(self, x, k: int = 10, epsilon: float = 0.1, **_ignored):
+        """pynndescent call shape: -> (indices int32 [Nq,k], distances float32 [Nq,k]) ascending."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise ValueError(f"queries must be [Nq, {self.d}], got {x.shape}")
+        k_eff = min(int(k), self.n)
+        q32 = torch.from_numpy(x).to(self.device)
+        idx, dist = self.search_device(q32, k_eff)
+        return idx.cpu().numpy(), dist.cpu().numpy()
+
+
+def knn_vote_device(idx: torch.Tensor, dist: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """idx/dist [nq, m] on device, labels int64 [ng] on device -> int64 [nq]   (plk_knn_vote)"""
+    lib = _lib.load()
+    nq, m = idx.shape
+    pred = torch.empty(nq, device=idx.device, dtype=torch.int64)
+    with torch.cuda.device(idx.device):
+        lib.check(lib.plk_knn_vote(idx.data_ptr(), dist.data_ptr(), nq, m, labels.data_ptr(), labels.shape[0],
+                                   pred.data_ptr(), torch.cuda.current_stream(idx.device).cuda_stream),
+                  "plk_knn_vote")
+    return pred
+
+
+class ANNClassifier:
+
+    def __init__(self, X, y, **nndescent_args):
+        metric = nndescent_args.get("metric", "euclidean")
+        if metric != "euclidean":
+            raise ValueError(f"only metric='euclidean' is supported (the reference's setting), got {metric!r}")
+        precision = nndescent_args.pop("plk_precision", "bf16")
+        device = nndescent_args.pop("plk_device", None)
+        self.y_ = np.asarray(y).copy()
+        self.index = GpuExactIndex(X, precision=precision, device=device)
+        self.index.prepare()
+        self._labels_dev = torch.from_numpy(self.y_.astype(np.int64)).to(self.index.device)
+
+    def kneighbors(self, *X, **query_args):
+        return tuple(self.index.query(x, **query_args) for x in X)
+
+    def predict(self, *X, **query_args):
+        k = int(query_args.get("k", 10))
+        k_eff = min(k, self.index.n)
+        dev = self.index.device
+        lists = []
+        for x in X:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            lists.append(self.index.search_device(torch.from_numpy(x).to(dev), k_eff))
+        idx = torch.cat([p[0] for p in lists], dim=1).contiguous()
+        dist = torch.cat([p[1] for p in lists], dim=1).contiguous()
+        pred = knn_vote_device(idx, dist, self._labels_dev)
+        return pred.cpu().numpy().astype(int).ravel()
+
+    def _get_weights(self, dist):
+        """Host-side statement of the vote weights (reference src/ann.py:28-34); `predict` applies the same
+        rule on the device in plk_knn_vote."""
+        dist = np.asarray(dist)
+        zero = dist == 0
+        with np.errstate(divide="ignore"):
+            w = (1.0 / dist).astype(dist.dtype, copy=False)
+        rows = zero.any(axis=1)
+        w[rows] = zero[rows]
+        return w

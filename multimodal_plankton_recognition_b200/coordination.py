@@ -1,0 +1,56 @@
+"""Drop-in for the hot-path class of reference src/coordination.py: ``CLIPLoss``.
+
+Same constructor, parameter name/shape (``logit_scale``: 0-dim fp32, init 1.0, so reference
+checkpoints load: key ``loss.logit_scale``), keyword call signature
+``loss(image_emb=..., profile_emb=..., buckets=...)`` (reference src/model.py:95-98) and error
+behaviour (AssertionError with the reference's message when the batch is not divisible by
+``buckets``).  The arithmetic runs on the fused CUDA path (`ops.clip_loss`): the B x B logits are
+never materialised, gradients flow to both raw embeddings and to ``logit_scale``.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch import Tensor
+from torch.nn import Module, Parameter
+
+from . import ops
+
+
+class CLIPLoss(Module):
+    """Symmetric CLIP-style InfoNCE (https://arxiv.org/abs/2103.00020), reference src/coordination.py:17-47.
+
+    ``precision``: "bf16" (tcgen05 tensor-core path, <=2e-3 relative vs the reference) or
+    "fp32" (CUDA-core parity path, <=1e-5 relative).  Default: env ``PLK_PRECISION`` or "bf16".
+    ``process_group``: if given (or ``sharded=True`` with the default group), the batch seen by
+    ``forward`` is this rank's slice of a global batch and the loss is the global-batch loss
+    (`dist.sharded_clip_loss`); the reference has no multi-GPU path, this is new functionality.
+    """
+
+    def __init__(self, bias: bool = False, *, precision: str | None = None, sharded: bool = False,
+                 process_group=None) -> None:
+        super().__init__()
+        self.logit_scale = Parameter(torch.ones([]))
+        precision = precision or os.environ.get("PLK_PRECISION", "bf16")
+        if precision not in ops.MODES:
+            raise ValueError(f"precision must be one of {sorted(ops.MODES)}, got {precision!r}")
+        self.precision = precision
+        self.sharded = sharded or process_group is not None
+        self.process_group = process_group
+
+    def forward(self, image_emb: Tensor, profile_emb: Tensor, buckets: int = 1) -> Tensor:
+        assert image_emb.size(0) % buckets == 0, \
+            "Batch size must be divisible by number of buckets!"
+        if image_emb.dim() != 2 or image_emb.shape != profile_emb.shape:
+            raise ValueError(f"expected two [B, d] embeddings of equal shape, got "
+                             f"{tuple(image_emb.shape)} and {tuple(profile_emb.shape)}")
+        mode = ops.MODES[self.precision]
+        if self.sharded:
+            from . import dist
+            return dist.sharded_clip_loss(image_emb, profile_emb, self.logit_scale, int(buckets), mode,
+                                          self.process_group)
+        return ops.clip_loss(image_emb, profile_emb, self.logit_scale, int(buckets), mode)
+
+    def extra_repr(self) -> str:
+        return f"precision={self.precision}, sharded={self.sharded}"

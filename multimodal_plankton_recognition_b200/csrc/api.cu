@@ -1,0 +1,113 @@
+// extern "C" surface of libplk.so: argument validation + dispatch on the operand dtype.
+// Declarations and the reference lines each entry point replaces: include/plk.h.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+
+namespace plk {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace plk
+
+using namespace plk;
+
+extern "C" {
+
+int plk_version(void) { return 100; }
+const char* plk_last_error(void) { return g_err; }
+int64_t plk_launch_count(void) { return g_launches.load(); }
+
+int plk_device_supports_tc(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+static int check_common(const void* a, const void* b, int op_dtype, int64_t ld, int64_t n_rows,
+                        int64_t n_cols, int64_t d, int64_t bs) {
+  PLK_REQUIRE(a && b, PLK_ERR_INVALID, "null operand pointer");
+  PLK_REQUIRE(op_dtype == PLK_F32 || op_dtype == PLK_BF16, PLK_ERR_INVALID,
+              "op_dtype must be PLK_F32 or PLK_BF16 (got %d)", op_dtype);
+  PLK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0 && ld >= d, PLK_ERR_INVALID,
+              "bad shape n_rows=%lld n_cols=%lld d=%lld ld=%lld", (long long)n_rows,
+              (long long)n_cols, (long long)d, (long long)ld);
+  PLK_REQUIRE(bs > 0, PLK_ERR_INVALID, "bucket_size must be positive");
+  return PLK_OK;
+}
+
+int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld, int64_t n_rows,
+                    int64_t row_offset, int64_t n_cols, int64_t d, int64_t bucket_size,
+                    const float* logit_scale, float* row_sumexp, float* col_sumexp, float* diag,
+                    void* stream) {
+  int rc = check_common(u, v, op_dtype, ld, n_rows, n_cols, d, bucket_size);
+  if (rc) return rc;
+  PLK_REQUIRE(logit_scale && row_sumexp && col_sumexp && diag, PLK_ERR_INVALID, "null output pointer");
+  PLK_REQUIRE(row_offset >= 0 && row_offset + n_rows <= n_cols, PLK_ERR_INVALID,
+              "owned rows [%lld,%lld) outside the global batch %lld", (long long)row_offset,
+              (long long)(row_offset + n_rows), (long long)n_cols);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op_dtype == PLK_F32)
+    return infonce_fwd_f32((const float*)u, (const float*)v, ld, n_rows, row_offset, n_cols, d,
+                           bucket_size, logit_scale, row_sumexp, col_sumexp, diag, st);
+  return infonce_fwd_bf16((const __nv_bfloat16*)u, (const __nv_bfloat16*)v, ld, n_rows, row_offset,
+                          n_cols, d, bucket_size, logit_scale, row_sumexp, col_sumexp, diag, st);
+}
+
+int plk_infonce_grad_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
+                           int64_t bucket_size) {
+  if (op_dtype != PLK_BF16 || n_rows <= 0 || n_cols <= 0 || d <= 0 || bucket_size <= 0) return 1;
+  return grad_parts_bf16(n_rows, n_cols, d, bucket_size);
+}
+
+int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld, int64_t n_rows,
+                     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bucket_size,
+                     const float* logit_scale, const float* rs, const float* cs, float* acc,
+                     float* gs, void* stream) {
+  int rc = check_common(a, b, op_dtype, ld, n_rows, n_cols, d, bucket_size);
+  if (rc) return rc;
+  PLK_REQUIRE(logit_scale && rs && cs && acc, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(row_offset >= 0 && row_offset + n_rows <= n_cols, PLK_ERR_INVALID,
+              "owned rows outside the global batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op_dtype == PLK_F32)
+    return infonce_grad_f32((const float*)a, (const float*)b, ld, n_rows, row_offset, n_cols, d,
+                            bucket_size, logit_scale, rs, cs, acc, gs, st);
+  return infonce_grad_bf16((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, ld, n_rows, row_offset,
+                           n_cols, d, bucket_size, logit_scale, rs, cs, acc, gs, st);
+}
+
+size_t plk_topk_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int kc, int op_dtype) {
+  return op_dtype == PLK_BF16 ? topk_ws_bf16(nq, ng, d, kc) : topk_ws_f32(nq, ng, d, kc);
+}
+
+int plk_topk_candidates(const void* q, const void* g, int op_dtype, int64_t ld, const float* g_sqn,
+                        int64_t nq, int64_t ng, int64_t d, int kc, int64_t gallery_offset,
+                        int32_t* cand_idx, float* cand_key, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  PLK_REQUIRE(q && g && g_sqn && cand_idx && cand_key, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(op_dtype == PLK_F32 || op_dtype == PLK_BF16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
+  PLK_REQUIRE(nq > 0 && ng > 0 && d > 0 && ld >= d, PLK_ERR_INVALID, "bad shape");
+  PLK_REQUIRE(kc >= 1 && kc <= 64, PLK_ERR_INVALID, "kc must be in [1,64] (got %d)", kc);
+  PLK_REQUIRE(gallery_offset >= 0 && gallery_offset + ng < (int64_t)1 << 31, PLK_ERR_INVALID,
+              "gallery indices must fit int32");
+  size_t need = plk_topk_workspace_bytes(nq, ng, d, kc, op_dtype);
+  PLK_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), PLK_ERR_INVALID,
+              "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op_dtype == PLK_F32)
+    return topk_candidates_f32((const float*)q, (const float*)g, ld, g_sqn, nq, ng, d, kc,
+                               gallery_offset, cand_idx, cand_key, workspace, workspace_bytes, st);
+  return topk_candidates_bf16((const __nv_bfloat16*)q, (const __nv_bfloat16*)g, ld, g_sqn, nq, ng, d,
+                              kc, gallery_offset, cand_idx, cand_key, workspace, workspace_bytes, st);
+}
+
+}  // extern "C"

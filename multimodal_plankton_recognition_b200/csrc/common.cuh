@@ -1,0 +1,81 @@
+// Shared host-side helpers for libplk.so (error reporting, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/plk.h"
+
+namespace plk {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+constexpr float kNormEps = 1e-12f;   // F.normalize eps, reference src/coordination.py:33-34
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMaxScale = 64.0f;   // fixed-shift validity bound on s = exp(logit_scale)
+
+#define PLK_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      ::plk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                       __LINE__);                                                        \
+      return PLK_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define PLK_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::plk::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define PLK_LAUNCHED(n)                     \
+  do {                                      \
+    ::plk::count_launch(n);                 \
+    PLK_CUDA(cudaGetLastError());           \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- entry points implemented per translation unit (dispatched from api.cu) ----
+int infonce_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset,
+                    int64_t n_cols, int64_t d, int64_t bs, const float* ls, float* row_sumexp,
+                    float* col_sumexp, float* diag, cudaStream_t st);
+int infonce_grad_f32(const float* a, const float* b, int64_t ld, int64_t n_rows, int64_t row_offset,
+                     int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs,
+                     const float* cs, float* acc, float* gs, cudaStream_t st);
+int topk_candidates_f32(const float* q, const float* g, int64_t ld, const float* g_sqn, int64_t nq,
+                        int64_t ng, int64_t d, int kc, int64_t goff, int32_t* cand_idx,
+                        float* cand_key, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t topk_ws_f32(int64_t nq, int64_t ng, int64_t d, int kc);
+
+int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld, int64_t n_rows,
+                     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
+                     float* row_sumexp, float* col_sumexp, float* diag, cudaStream_t st);
+int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
+                      int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
+                      const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st);
+int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs);
+int topk_candidates_bf16(const __nv_bfloat16* q, const __nv_bfloat16* g, int64_t ld,
+                         const float* g_sqn, int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff,
+                         int32_t* cand_idx, float* cand_key, void* ws, size_t ws_bytes,
+                         cudaStream_t st);
+size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc);
+int select_candidates(const int32_t* in_idx, const float* in_key, int64_t nq, int m, int kc,
+                      int32_t* out_idx, float* out_key, cudaStream_t st);
+
+// Bucket column range of a global row (block-diagonal InfoNCE, reference src/coordination.py:29-37).
+__host__ __device__ inline void bucket_range(int64_t gi, int64_t bs, int64_t n_cols, int64_t& lo,
+                                             int64_t& hi) {
+  int64_t b = gi / bs;
+  lo = b * bs;
+  hi = lo + bs;
+  if (hi > n_cols) hi = n_cols;
+}
+
+}  // namespace plk

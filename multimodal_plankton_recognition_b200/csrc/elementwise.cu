@@ -1,0 +1,389 @@
+// HBM-bound row-wise kernels around the similarity GEMMs: L2 normalisation, loss reduction,
+// gradient tail (diag term + normalisation backward), candidate re-score / merge, k-NN vote.
+// One warp per row, coalesced 32-lane sweeps along d; grids are sized from the row count.
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace plk {
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float ld_as_float<__half>(const __half* p) { return __half2float(*p); }
+
+template <typename T>
+__device__ __forceinline__ void st_from_float(T* p, float v);
+template <>
+__device__ __forceinline__ void st_from_float<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ void st_from_float<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a2: u = x / max(||x||, eps)                                    reference src/coordination.py:33-34
+// ---------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) l2norm_kernel(const TI* __restrict__ x, int64_t n, int64_t d,
+                                                     int64_t ldx, TO* __restrict__ u, int64_t ldu,
+                                                     float* __restrict__ inv_den,
+                                                     float* __restrict__ nrm_out,
+                                                     float* __restrict__ sqn_out, int normalise) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const TI* xr = x + row * ldx;
+  float ss = 0.f;
+  for (int64_t k = lane; k < d; k += 32) {
+    float v = ld_as_float(xr + k);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float den = fmaxf(nrm, kNormEps);
+  const float scale = normalise ? 1.0f / den : 1.0f;
+  TO* ur = u + row * ldu;
+  float sq = 0.f;
+  for (int64_t k = lane; k < ldu; k += 32) {
+    float v = 0.f;
+    if (k < d) v = normalise ? ld_as_float(xr + k) / den : ld_as_float(xr + k);
+    st_from_float(ur + k, v);
+    float w = ld_as_float(ur + k);  // value as stored (after rounding)
+    sq = fmaf(w, w, sq);
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) {
+    if (inv_den) inv_den[row] = scale;
+    if (nrm_out) nrm_out[row] = nrm;
+    if (sqn_out) sqn_out[row] = sq;
+  }
+}
+
+template <typename TI>
+static int l2norm_dispatch_out(const TI* x, int64_t n, int64_t d, int64_t ldx, void* u, int u_dtype,
+                               int64_t ldu, float* inv_den, float* nrm, float* sqn, int normalise,
+                               cudaStream_t st) {
+  dim3 block(256), grid((unsigned)ceil_div(n, 8));
+  if (u_dtype == PLK_F32)
+    l2norm_kernel<TI, float><<<grid, block, 0, st>>>(x, n, d, ldx, (float*)u, ldu, inv_den, nrm, sqn, normalise);
+  else
+    l2norm_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(x, n, d, ldx, (__nv_bfloat16*)u, ldu, inv_den, nrm, sqn, normalise);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8: loss partial over the owned rows                              reference src/coordination.py:45
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ rs,
+                                                    const float* __restrict__ cs,
+                                                    const float* __restrict__ diag,
+                                                    const float* __restrict__ ls, int64_t n,
+                                                    int64_t batch, float* __restrict__ loss_out,
+                                                    float* __restrict__ diag_sum_out) {
+  __shared__ double sh[2][32];
+  const double s = (double)expf(*ls);
+  double a = 0.0, dsum = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double dg = (double)diag[i];
+    a += 2.0 * s + (double)logf(rs[i]) + (double)logf(cs[i]) - 2.0 * dg;
+    dsum += dg;
+  }
+  a = warp_sum(a);
+  dsum = warp_sum(dsum);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = dsum; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = threadIdx.x < (blockDim.x >> 5) ? sh[0][threadIdx.x] : 0.0;
+    dsum = threadIdx.x < (blockDim.x >> 5) ? sh[1][threadIdx.x] : 0.0;
+    a = warp_sum(a);
+    dsum = warp_sum(dsum);
+    if (threadIdx.x == 0) {
+      *loss_out = (float)(a / (2.0 * (double)batch));
+      if (diag_sum_out) *diag_sum_out = (float)dsum;
+    }
+  }
+}
+
+__global__ void dls_kernel(const float* gs, const float* diag_sum, const float* grad_out,
+                           int64_t batch, float* out) {
+  *out = (float)((double)(*grad_out) / (2.0 * (double)batch) * ((double)(*gs) - 2.0 * (double)(*diag_sum)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9 tail: -2*delta term, g*s/(2B) scaling, normalisation backward.
+// ---------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) grad_finish_kernel(
+    const float* __restrict__ acc, int parts, const TI* __restrict__ x,
+    const TI* __restrict__ partner, int64_t n, int64_t d, int64_t ldx, const float* __restrict__ inv_den_x,
+    const float* __restrict__ nrm_x, const float* __restrict__ inv_den_p,
+    const float* __restrict__ ls, const float* __restrict__ grad_out, int64_t batch,
+    TO* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float coef = (*grad_out) * expf(*ls) / (2.0f * (float)batch);
+  const float idx_ = inv_den_x[row], idp = inv_den_p[row];
+  const bool clamped = !(nrm_x[row] > kNormEps);
+  const float* ar = acc + row * d;
+  const TI* xr = x + row * ldx;
+  const TI* pr = partner + row * ldx;
+  const int64_t slab = n * d;
+  float dot = 0.f;
+  for (int64_t k = lane; k < d; k += 32) {
+    float a = ar[k];
+    for (int p = 1; p < parts; ++p) a += ar[k + p * slab];
+    float dU = coef * (a - 2.0f * ld_as_float(pr + k) * idp);
+    dot = fmaf(ld_as_float(xr + k) * idx_, dU, dot);
+  }
+  dot = warp_sum(dot);
+  if (clamped) dot = 0.f;  // below the eps clamp the denominator is constant: dx = dU / eps
+  TO* dr = dx + row * d;
+  for (int64_t k = lane; k < d; k += 32) {
+    float a = ar[k];
+    for (int p = 1; p < parts; ++p) a += ar[k + p * slab];
+    float dU = coef * (a - 2.0f * ld_as_float(pr + k) * idp);
+    float uk = ld_as_float(xr + k) * idx_;
+    st_from_float(dr + k, (dU - uk * dot) * idx_);
+  }
+}
+
+template <typename TI>
+static int grad_finish_dispatch(const float* acc, int parts, const TI* x, const TI* p, int64_t n, int64_t d,
+                                int64_t ldx, const float* idx_, const float* nrm, const float* idp,
+                                const float* ls, const float* go, int64_t batch, void* dx,
+                                int dx_dtype, cudaStream_t st) {
+  dim3 block(256), grid((unsigned)ceil_div(n, 8));
+  if (dx_dtype == PLK_F32)
+    grad_finish_kernel<TI, float><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, ls, go, batch, (float*)dx);
+  else if (dx_dtype == PLK_BF16)
+    grad_finish_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, ls, go, batch, (__nv_bfloat16*)dx);
+  else
+    grad_finish_kernel<TI, __half><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, ls, go, batch, (__half*)dx);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Retrieval tails.  Lists are tiny (<= a few hundred entries per query): one thread per query
+// does an insertion selection ordered by (key, index).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxK = 64;
+
+__device__ __forceinline__ bool pair_less(float ka, int32_t ia, float kb, int32_t ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+
+// keep the k smallest (key, idx) pairs of a stream; best[] sorted ascending.
+__device__ __forceinline__ void topk_insert(float* bk, int32_t* bi, int k, float key, int32_t idx) {
+  if (!pair_less(key, idx, bk[k - 1], bi[k - 1])) return;
+  int p = k - 1;
+  while (p > 0 && pair_less(key, idx, bk[p - 1], bi[p - 1])) {
+    bk[p] = bk[p - 1];
+    bi[p] = bi[p - 1];
+    --p;
+  }
+  bk[p] = key;
+  bi[p] = idx;
+}
+
+__global__ void __launch_bounds__(128) select_kernel(const int32_t* __restrict__ in_idx,
+                                                     const float* __restrict__ in_key, int64_t nq,
+                                                     int m, int k, int32_t* __restrict__ out_idx,
+                                                     float* __restrict__ out_key) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  float bk[kMaxK];
+  int32_t bi[kMaxK];
+  for (int t = 0; t < k; ++t) { bk[t] = CUDART_INF_F; bi[t] = 0x7fffffff; }
+  for (int t = 0; t < m; ++t) {
+    int32_t id = in_idx[q * m + t];
+    if (id < 0) continue;
+    topk_insert(bk, bi, k, in_key[q * m + t], id);
+  }
+  for (int t = 0; t < k; ++t) {
+    const bool empty = bi[t] == 0x7fffffff;
+    out_idx[q * k + t] = empty ? -1 : bi[t];
+    out_key[q * k + t] = bk[t];
+  }
+}
+
+int select_candidates(const int32_t* in_idx, const float* in_key, int64_t nq, int m, int kc,
+                      int32_t* out_idx, float* out_key, cudaStream_t st) {
+  select_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(in_idx, in_key, nq, m, kc, out_idx, out_key);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+// exact distance of each candidate: one warp per (query, candidate), fp64 accumulation.
+__global__ void __launch_bounds__(256) rescore_dist_kernel(const float* __restrict__ q32,
+                                                           const float* __restrict__ g32, int64_t nq,
+                                                           int64_t ng, int64_t d,
+                                                           const int32_t* __restrict__ cand, int m,
+                                                           int64_t goff, float* __restrict__ dist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nq * m) return;
+  const int64_t qi = w / m;
+  const int32_t id = cand[w];
+  const int64_t lr = (int64_t)id - goff;
+  if (id < 0 || lr < 0 || lr >= ng) {
+    if (lane == 0) dist[w] = CUDART_INF_F;
+    return;
+  }
+  const float* qr = q32 + qi * d;
+  const float* gr = g32 + lr * d;
+  double a = 0.0;
+  for (int64_t k = lane; k < d; k += 32) {
+    double t = (double)qr[k] - (double)gr[k];
+    a = fma(t, t, a);
+  }
+  a = warp_sum(a);
+  if (lane == 0) dist[w] = (float)sqrt(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// a13/a14: inverse-distance weighted vote                            reference src/ann.py:19-34
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxVote = 256;
+__global__ void __launch_bounds__(128) vote_kernel(const int32_t* __restrict__ idx,
+                                                   const float* __restrict__ dist, int64_t nq, int m,
+                                                   const int64_t* __restrict__ labels, int64_t ng,
+                                                   int64_t* __restrict__ pred) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int32_t* ir = idx + q * m;
+  const float* dr = dist + q * m;
+  bool any_zero = false;
+  for (int t = 0; t < m; ++t)
+    if (ir[t] >= 0 && dr[t] == 0.0f) any_zero = true;
+  double best_w = 0.0;
+  int64_t best_c = 0;
+  bool have = false;
+  for (int t = 0; t < m; ++t) {
+    if (ir[t] < 0) continue;
+    const int64_t c = labels[ir[t]];
+    bool first = true;  // evaluate each distinct class once (at its first occurrence)
+    for (int r = 0; r < t; ++r)
+      if (ir[r] >= 0 && labels[ir[r]] == c) { first = false; break; }
+    if (!first) continue;
+    double tot = 0.0;
+    for (int r = t; r < m; ++r) {
+      if (ir[r] < 0 || labels[ir[r]] != c) continue;
+      float w = any_zero ? (dr[r] == 0.0f ? 1.0f : 0.0f) : 1.0f / dr[r];
+      tot += (double)w;
+    }
+    // weighted_mode visits classes in ascending order with a strict '>' starting from a zero
+    // count, i.e. the winner is the LOWEST class id among those with the largest positive sum.
+    if (tot > best_w || (have && tot == best_w && c < best_c)) {
+      best_w = tot;
+      best_c = c;
+      have = true;
+    }
+  }
+  pred[q] = have ? best_c : 0;
+}
+
+}  // namespace plk
+
+using namespace plk;
+
+extern "C" {
+
+int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx, void* u,
+                   int u_dtype, int64_t ldu, float* inv_den, float* nrm, float* sqn, int normalise,
+                   void* stream) {
+  PLK_REQUIRE(x && u, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(n > 0 && d > 0 && ldx >= d && ldu >= d, PLK_ERR_INVALID, "bad shape n=%lld d=%lld ldx=%lld ldu=%lld",
+              (long long)n, (long long)d, (long long)ldx, (long long)ldu);
+  PLK_REQUIRE(u_dtype == PLK_F32 || u_dtype == PLK_BF16, PLK_ERR_INVALID, "u_dtype must be F32 or BF16");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (x_dtype) {
+    case PLK_F32: return l2norm_dispatch_out((const float*)x, n, d, ldx, u, u_dtype, ldu, inv_den, nrm, sqn, normalise, st);
+    case PLK_BF16: return l2norm_dispatch_out((const __nv_bfloat16*)x, n, d, ldx, u, u_dtype, ldu, inv_den, nrm, sqn, normalise, st);
+    case PLK_F16: return l2norm_dispatch_out((const __half*)x, n, d, ldx, u, u_dtype, ldu, inv_den, nrm, sqn, normalise, st);
+  }
+  set_error("bad x_dtype %d", x_dtype);
+  return PLK_ERR_INVALID;
+}
+
+int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const float* diag,
+                     const float* logit_scale, int64_t n_rows, int64_t batch_global, float* loss_out,
+                     float* diag_sum_out, void* stream) {
+  PLK_REQUIRE(row_sumexp && col_sumexp_own && diag && logit_scale && loss_out, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(n_rows > 0 && batch_global >= n_rows, PLK_ERR_INVALID, "bad sizes");
+  loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_sumexp, col_sumexp_own, diag, logit_scale, n_rows, batch_global, loss_out, diag_sum_out);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_out,
+                    int64_t batch_global, float* dls_out, void* stream) {
+  PLK_REQUIRE(gs && diag_sum && grad_out && dls_out && batch_global > 0, PLK_ERR_INVALID, "bad args");
+  dls_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(gs, diag_sum, grad_out, batch_global, dls_out);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const void* partner, int x_dtype,
+                            int64_t n, int64_t d, int64_t ldx, const float* inv_den_x,
+                            const float* nrm_x, const float* inv_den_p, const float* logit_scale,
+                            const float* grad_out, int64_t batch_global, void* dx, int dx_dtype,
+                            void* stream) {
+  PLK_REQUIRE(acc && x && partner && inv_den_x && nrm_x && inv_den_p && logit_scale && grad_out && dx,
+              PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(n > 0 && d > 0 && ldx >= d && batch_global >= n && parts >= 1, PLK_ERR_INVALID, "bad sizes");
+  PLK_REQUIRE(dx_dtype >= PLK_F32 && dx_dtype <= PLK_F16, PLK_ERR_INVALID, "bad dx_dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (x_dtype) {
+    case PLK_F32: return grad_finish_dispatch(acc, parts, (const float*)x, (const float*)partner, n, d, ldx, inv_den_x, nrm_x, inv_den_p, logit_scale, grad_out, batch_global, dx, dx_dtype, st);
+    default: break;
+  }
+  set_error("grad_finish: raw embeddings must be fp32 (got dtype %d); cast on the host side", x_dtype);
+  return PLK_ERR_UNSUPPORTED;
+}
+
+int plk_topk_rescore(const float* q32, const float* g32, int64_t nq, int64_t ng, int64_t d,
+                     const int32_t* cand_idx, int m, int64_t gallery_offset, int k, float* scratch,
+                     int32_t* out_idx, float* out_dist, void* stream) {
+  PLK_REQUIRE(q32 && g32 && cand_idx && scratch && out_idx && out_dist, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(nq > 0 && ng > 0 && d > 0 && m >= 1 && k >= 1 && k <= kMaxK, PLK_ERR_INVALID, "bad sizes (k<=64)");
+  cudaStream_t st = (cudaStream_t)stream;
+  rescore_dist_kernel<<<(unsigned)ceil_div(nq * m, 8), 256, 0, st>>>(q32, g32, nq, ng, d, cand_idx, m, gallery_offset, scratch);
+  PLK_LAUNCHED(1);
+  return select_candidates(cand_idx, scratch, nq, m, k, out_idx, out_dist, st);
+}
+
+int plk_topk_merge(const int32_t* cand_idx, const float* cand_dist, int64_t nq, int m, int k,
+                   int32_t* out_idx, float* out_dist, void* stream) {
+  PLK_REQUIRE(cand_idx && cand_dist && out_idx && out_dist, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(nq > 0 && m >= 1 && k >= 1 && k <= kMaxK, PLK_ERR_INVALID, "bad sizes (k<=64)");
+  return select_candidates(cand_idx, cand_dist, nq, m, k, out_idx, out_dist, (cudaStream_t)stream);
+}
+
+int plk_knn_vote(const int32_t* idx, const float* dist, int64_t nq, int m, const int64_t* labels,
+                 int64_t ng, int64_t* pred, void* stream) {
+  PLK_REQUIRE(idx && dist && labels && pred, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(nq > 0 && m >= 1 && m <= kMaxVote && ng > 0, PLK_ERR_INVALID, "bad sizes (m<=256)");
+  vote_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, (cudaStream_t)stream>>>(idx, dist, nq, m, labels, ng, pred);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+}  // extern "C"

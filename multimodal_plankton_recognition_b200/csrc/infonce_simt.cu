@@ -1,0 +1,239 @@
+// fp32 CUDA-core path of the fused similarity + InfoNCE forward / recompute backward
+// ("parity mode": <=1e-5 relative vs the reference's fp32 PyTorch run).  Same algorithm and
+// outputs as the tcgen05 path in infonce_tc.cu -- shared-memory tiled FFMA GEMM with the
+// temperature / exp / row+column sum / diagonal epilogue fused, logits never leave the SM.
+#include "common.cuh"
+
+namespace plk {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+
+// 64x64 tile of A.B^T (K = d) accumulated in a 4x4 register micro-tile per thread.
+// Thread (ty, tx) = (t/16, t%16) owns rows ty*4+r and columns tx + 16*c (bank-conflict free).
+__device__ __forceinline__ void tile_gemm_64x64(const float* __restrict__ A, int64_t a_rows,
+                                                int64_t i0, const float* __restrict__ Bm,
+                                                int64_t b_rows, int64_t j0, int64_t d, int64_t ld,
+                                                float (*As)[BM + 1], float (*Bs)[BN + 1],
+                                                float acc[4][4]) {
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  const int lr = t >> 2;        // 0..63 : tile row loaded by this thread
+  const int lk = (t & 3) * 4;   // 0,4,8,12
+  for (int64_t k0 = 0; k0 < d; k0 += BK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t k = k0 + lk + e;
+      const int64_t ia = i0 + lr, jb = j0 + lr;
+      As[lk + e][lr] = (ia < a_rows && k < d) ? A[ia * ld + k] : 0.f;
+      Bs[lk + e][lr] = (jb < b_rows && k < d) ? Bm[jb * ld + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a[r] = As[kk][ty * 4 + r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = Bs[kk][tx + 16 * c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+}
+
+// Column range a row tile needs: union of the buckets of its rows.
+__device__ __forceinline__ void tile_col_range(int64_t i0, int64_t n_rows, int64_t row_offset,
+                                               int64_t bs, int64_t n_cols, int64_t& jlo,
+                                               int64_t& jhi) {
+  int64_t last = i0 + BM - 1;
+  if (last >= n_rows) last = n_rows - 1;
+  int64_t lo, hi, lo2, hi2;
+  bucket_range(row_offset + i0, bs, n_cols, lo, hi);
+  bucket_range(row_offset + last, bs, n_cols, lo2, hi2);
+  jlo = lo;
+  jhi = hi2;
+}
+
+__global__ void __launch_bounds__(NT) infonce_fwd_simt(
+    const float* __restrict__ u, const float* __restrict__ v, int64_t ld, int64_t n_rows,
+    int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* __restrict__ ls,
+    float* __restrict__ row_sumexp, float* __restrict__ col_sumexp, float* __restrict__ diag) {
+  __shared__ float As[BK][BM + 1];
+  __shared__ float Bs[BK][BN + 1];
+  __shared__ float colsum[BN];
+  const int64_t i0 = (int64_t)blockIdx.y * BM;
+  const int64_t j0 = (int64_t)blockIdx.x * BN;
+  int64_t jlo, jhi;
+  tile_col_range(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  if (j0 + BN <= jlo || j0 >= jhi) return;  // tile outside every bucket of these rows
+
+  float acc[4][4];
+  tile_gemm_64x64(u, n_rows, i0, v, n_cols, j0, d, ld, As, Bs, acc);
+
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  if (t < BN) colsum[t] = 0.f;
+  __syncthreads();
+  const float s = expf(*ls);
+  float cpart[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = i0 + ty * 4 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    if (i < n_rows) bucket_range(gi, bs, n_cols, lo, hi);
+    float rpart = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t j = j0 + tx + 16 * c;
+      const bool valid = i < n_rows && j >= lo && j < hi;
+      const float S = s * acc[r][c];
+      const float E = valid ? expf(S - s) : 0.f;
+      if (valid && j == gi) diag[i] = S;
+      rpart += E;
+      cpart[c] += E;
+    }
+    // reduce over the 16 lanes (tx) that share this row
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) rpart += __shfl_xor_sync(0xffffffffu, rpart, o);
+    if (tx == 0 && i < n_rows) atomicAdd(row_sumexp + i, rpart);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) atomicAdd(&colsum[tx + 16 * c], cpart[c]);
+  __syncthreads();
+  if (t < BN && j0 + t < n_cols && colsum[t] != 0.f) atomicAdd(col_sumexp + j0 + t, colsum[t]);
+}
+
+// One direction of the recompute backward.  CTA = (64 owned rows) x (128 output columns of d);
+// loops over the column tiles of the rows' buckets: S tile -> G tile in shared memory -> G.B.
+constexpr int DC = 128;
+__global__ void __launch_bounds__(NT) infonce_grad_simt(
+    const float* __restrict__ a, const float* __restrict__ b, int64_t ld, int64_t n_rows,
+    int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* __restrict__ ls,
+    const float* __restrict__ rs, const float* __restrict__ cs, float* __restrict__ acc_out,
+    float* __restrict__ gs_out) {
+  __shared__ float As[BK][BM + 1];
+  __shared__ float Bs[BK][BN + 1];
+  __shared__ float Gs[BM][BN + 1];
+  __shared__ float Ys[BK][DC];
+  __shared__ float rcs[BN];
+  __shared__ float red[NT / 32];
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int64_t i0 = (int64_t)blockIdx.y * BM;
+  const int64_t dc0 = (int64_t)blockIdx.x * DC;
+  int64_t jlo, jhi;
+  tile_col_range(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const float s = expf(*ls);
+
+  float rrs[4];
+  int64_t lo[4], hi[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = i0 + ty * 4 + r;
+    lo[r] = hi[r] = 0;
+    rrs[r] = 0.f;
+    if (i < n_rows) {
+      bucket_range(row_offset + i, bs, n_cols, lo[r], hi[r]);
+      rrs[r] = 1.0f / rs[i];
+    }
+  }
+  float out[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[r][c] = 0.f;
+  float gs_local = 0.f;
+
+  for (int64_t j0 = jlo; j0 < jhi; j0 += BN) {
+    float acc[4][4];
+    tile_gemm_64x64(a, n_rows, i0, b, n_cols, j0, d, ld, As, Bs, acc);
+    if (t < BN) rcs[t] = (j0 + t < n_cols) ? 1.0f / cs[j0 + t] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int64_t j = j0 + tx + 16 * c;
+        const bool valid = j >= lo[r] && j < hi[r];
+        const float S = s * acc[r][c];
+        const float G = valid ? expf(S - s) * (rrs[r] + rcs[tx + 16 * c]) : 0.f;
+        gs_local = fmaf(G, S, gs_local);
+        Gs[ty * 4 + r][tx + 16 * c] = G;
+      }
+    __syncthreads();
+    // out[64 x 128] += Gs[64 x 64] . b[j0:j0+64, dc0:dc0+128]
+    for (int jj0 = 0; jj0 < BN; jj0 += BK) {
+      for (int e = t; e < BK * DC; e += NT) {
+        const int jr = e / DC, dcol = e % DC;
+        const int64_t j = j0 + jj0 + jr, k = dc0 + dcol;
+        Ys[jr][dcol] = (j < n_cols && k < d) ? b[j * ld + k] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        float g[4], y[8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) g[r] = Gs[ty * 4 + r][jj0 + kk];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) y[c] = Ys[kk][tx + 16 * c];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) out[r][c] = fmaf(g[r], y[c], out[r][c]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = i0 + ty * 4 + r;
+    if (i >= n_rows) continue;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int64_t k = dc0 + tx + 16 * c;
+      if (k < d) acc_out[i * d + k] = out[r][c];
+    }
+  }
+  if (gs_out != nullptr && blockIdx.x == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+    if ((t & 31) == 0) red[t >> 5] = gs_local;
+    __syncthreads();
+    if (t == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < NT / 32; ++w) tot += red[w];
+      atomicAdd(gs_out, tot);
+    }
+  }
+}
+
+int infonce_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset,
+                    int64_t n_cols, int64_t d, int64_t bs, const float* ls, float* row_sumexp,
+                    float* col_sumexp, float* diag, cudaStream_t st) {
+  PLK_CUDA(cudaMemsetAsync(row_sumexp, 0, sizeof(float) * n_rows, st));
+  PLK_CUDA(cudaMemsetAsync(col_sumexp, 0, sizeof(float) * n_cols, st));
+  PLK_CUDA(cudaMemsetAsync(diag, 0, sizeof(float) * n_rows, st));
+  dim3 grid((unsigned)ceil_div(n_cols, BN), (unsigned)ceil_div(n_rows, BM));
+  infonce_fwd_simt<<<grid, NT, 0, st>>>(u, v, ld, n_rows, row_offset, n_cols, d, bs, ls, row_sumexp,
+                                        col_sumexp, diag);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int infonce_grad_f32(const float* a, const float* b, int64_t ld, int64_t n_rows, int64_t row_offset,
+                     int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs,
+                     const float* cs, float* acc, float* gs, cudaStream_t st) {
+  if (gs) PLK_CUDA(cudaMemsetAsync(gs, 0, sizeof(float), st));
+  dim3 grid((unsigned)ceil_div(d, DC), (unsigned)ceil_div(n_rows, BM));
+  infonce_grad_simt<<<grid, NT, 0, st>>>(a, b, ld, n_rows, row_offset, n_cols, d, bs, ls, rs, cs, acc, gs);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+}  // namespace plk

@@ -1,0 +1,597 @@
+// tcgen05 (sm_100a) path of the fused similarity + InfoNCE forward and recompute backward.
+//
+// Both kernels are warp-specialised:
+//   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor into a 16 KiB-stage ring)
+//   warp 1      MMA issuer     (one elected lane; tcgen05.mma, accumulators in TMEM) + TMEM alloc
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread = one logit row, 32 columns per load)
+// A CTA owns 128 rows of the "a" operand (resident in shared memory, K-major SWIZZLE_128B) and
+// streams [128 x 64] chunks of the "b" operand.  The B x B logits only ever exist as 128x128 fp32
+// tiles in TMEM (double buffered so the epilogue of tile t overlaps the MMAs of tile t+1).
+//
+// Forward epilogue  : E = exp2(acc*s*log2e - s*log2e); row sums in registers, column sums by a
+//                     31-shuffle transpose-reduce per 32 columns, diagonal pick.
+// Backward epilogue : G = E*(1/rs_i + 1/cs_j) -> bf16 -> shared memory (swizzled K-major A operand),
+//                     then a second tcgen05.mma  acc[128 x 64*c] += G . b_chunk  with the streamed
+//                     chunk reused as an MN-major B operand; acc (<= 256 fp32 columns) stays in TMEM
+//                     for the whole column sweep.
+#include "tc_common.cuh"
+
+namespace plk {
+using namespace tc;
+
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kAuxBytes = 8192;  // barriers + tmem pointer (first 512 B), per-tile column scratch
+
+__device__ __forceinline__ void row_block_cols(int64_t i0, int64_t n_rows, int64_t row_offset,
+                                               int64_t bs, int64_t n_cols, int64_t& jlo,
+                                               int64_t& jhi) {
+  int64_t last = i0 + kTileRows - 1;
+  if (last >= n_rows) last = n_rows - 1;
+  int64_t lo, hi, lo2, hi2;
+  bucket_range(row_offset + i0, bs, n_cols, lo, hi);
+  bucket_range(row_offset + last, bs, n_cols, lo2, hi2);
+  jlo = lo;
+  jhi = hi2;
+}
+
+// column sums over the 32 lanes of a warp for 32 columns held one-row-per-lane:
+// on return v[0] of lane l is the sum of column l.
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? v[i + h] : v[i];
+      const float send = up ? v[i] : v[i + h];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int KD>
+struct FwdCfg {
+  static constexpr int kResident = KD * kChunkBytes;
+  static constexpr int kStagesMax = (kMaxSmem - 1024 - kAuxBytes - kResident) / kChunkBytes;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+  static constexpr int kSmem = 1024 + kResident + kStages * kChunkBytes + kAuxBytes;
+  static_assert(kStages >= 2, "not enough shared memory for the ring");
+};
+
+template <int KD>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
+    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+    int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tiles_per_seg,
+    const float* __restrict__ ls, float* __restrict__ row_sumexp, float* __restrict__ col_sumexp,
+    float* __restrict__ diag) {
+  using Cfg = FwdCfg<KD>;
+  constexpr int NST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_a = smem;
+  uint8_t* sm_ring = smem + Cfg::kResident;
+  uint8_t* aux = sm_ring + NST * kChunkBytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);  // [NST]
+  uint64_t* bar_empty = bar_full + NST;                   // [NST]
+  uint64_t* bar_a = bar_empty + NST;                      // [1]
+  uint64_t* bar_sfull = bar_a + 1;                        // [2]
+  uint64_t* bar_sempty = bar_sfull + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sempty + 2);
+  float* colpart = reinterpret_cast<float*>(aux + 512);   // [2][4][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
+  int64_t jlo, jhi;
+  row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
+  const int t_begin = blockIdx.x * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  if (t_begin >= t_end) return;  // uniform across the CTA
+  const int T = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, Cfg::kResident);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &tmap_a, bar_a, c * kChunkK, (int)i0);
+      int st = 0; uint32_t ph = 0;
+      for (int t = 0; t < T; ++t) {
+        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+        for (int c = 0; c < KD; ++c) {
+          mbar_wait(bar_empty + st, ph ^ 1);
+          mbar_expect_tx(bar_full + st, kChunkBytes);
+          tma_load_2d(sm_ring + st * kChunkBytes, &tmap_b, bar_full + st, c * kChunkK, j0);
+          if (++st == NST) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      mbar_wait(bar_a, 0);
+      int st = 0; uint32_t ph = 0;
+      for (int t = 0; t < T; ++t) {
+        const int buf = t & 1;
+        mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 128;
+        for (int c = 0; c < KD; ++c) {
+          mbar_wait(bar_full + st, ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sm_a + c * kChunkBytes);
+          const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+#pragma unroll
+          for (int k = 0; k < kChunkK / kUmmaK; ++k)
+            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16), umma_smem_desc(b_addr + k * 32, 16),
+                      idesc, (c | k) != 0);
+          umma_commit(bar_empty + st);
+          if (++st == NST) { st = 0; ph ^= 1; }
+        }
+        umma_commit(bar_sfull + buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: 4 warps, thread = one logit row ----------------
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;             // row inside the 128-row block
+    const int e_tid = r;                     // 0..127
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    if (i < n_rows) bucket_range(gi, bs, n_cols, lo, hi);
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = -c1;
+    float rsum = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      mbar_wait(bar_sfull + buf, (t >> 1) & 1);
+      tc_fence_after();
+      const bool full = (j0 >= lo) && (j0 + kTileRows <= hi);
+      const bool warp_full = __all_sync(0xffffffffu, full);
+      const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + kTileRows && i < n_rows);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cc * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+        if (warp_full) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int64_t j = j0 + cc * 32 + e;
+            const float E = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
+            v[e] = (j >= lo && j < hi) ? E : 0.f;
+          }
+        }
+        if (has_diag) {
+          const int64_t de = gi - (j0 + cc * 32);
+          if (de >= 0 && de < 32 && i < n_rows) {
+            float dv = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dv = (e == (int)de) ? __uint_as_float(raw[e]) : dv;
+            diag[i] = s * dv;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) rsum += v[e];
+        warp_transpose_reduce(v, lane);
+        colpart[(buf * 4 + q) * 128 + cc * 32 + lane] = v[0];
+      }
+      tc_fence_before();
+      mbar_arrive(bar_sempty + buf);
+      named_barrier_sync(1, kEpiThreads);
+      const float* cp = colpart + buf * 4 * 128;
+      const float cs = cp[e_tid] + cp[128 + e_tid] + cp[256 + e_tid] + cp[384 + e_tid];
+      if (j0 + e_tid < n_cols && cs != 0.f) atomicAdd(col_sumexp + j0 + e_tid, cs);
+    }
+    if (i < n_rows) atomicAdd(row_sumexp + i, rsum);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// =============================================================================================
+// backward (one direction)
+// =============================================================================================
+template <int KD, int DNC>
+struct GradCfg {
+  static constexpr int kResident = KD * kChunkBytes;
+  static constexpr int kGBytes = 2 * kChunkBytes;  // G tile: two [128 x 64] bf16 sub-tiles
+  static constexpr int kStagesMax = (kMaxSmem - 1024 - kAuxBytes - kResident - kGBytes) / kChunkBytes;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+  static constexpr int kSmem = 1024 + kResident + kGBytes + kStages * kChunkBytes + kAuxBytes;
+  static_assert(kStages >= 2, "not enough shared memory for the ring");
+  static_assert(DNC >= 1 && DNC <= 4, "at most 256 accumulator columns per CTA");
+};
+
+template <int KD, int DNC>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
+    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+    int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tiles_per_seg,
+    const float* __restrict__ ls, const float* __restrict__ rs, const float* __restrict__ cs,
+    float* __restrict__ acc_parts /* [nseg][n_rows][d] */, float* __restrict__ gs_out) {
+  using Cfg = GradCfg<KD, DNC>;
+  constexpr int NST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_a = smem;
+  uint8_t* sm_g = smem + Cfg::kResident;
+  uint8_t* sm_ring = sm_g + Cfg::kGBytes;
+  uint8_t* aux = sm_ring + NST * kChunkBytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);  // [NST]
+  uint64_t* bar_empty = bar_full + NST;                   // [NST]
+  uint64_t* bar_a = bar_empty + NST;                      // [1]
+  uint64_t* bar_sfull = bar_a + 1;                        // [2]
+  uint64_t* bar_sempty = bar_sfull + 2;                   // [2]
+  uint64_t* bar_gfull = bar_sempty + 2;                   // [1]
+  uint64_t* bar_gempty = bar_gfull + 1;                   // [1]
+  uint64_t* bar_accfull = bar_gempty + 1;                 // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
+  float* rcs_s = reinterpret_cast<float*>(aux + 512);     // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
+  const int h = blockIdx.z;  // which block of DNC*64 output columns
+  int64_t jlo, jhi;
+  row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
+  const int t_begin = blockIdx.x * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;
+  float* acc_out = acc_parts + (int64_t)blockIdx.x * n_rows * d;
+  if (T == 0) {  // this segment has no tiles: its partial is zero (uniform across the CTA)
+    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DNC * 64; e += kNumThreads) {
+      const int64_t rr = i0 + e / (DNC * 64), col = (int64_t)h * DNC * 64 + e % (DNC * 64);
+      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
+    mbar_init(bar_gfull, kEpiThreads);
+    mbar_init(bar_gempty, 1);
+    mbar_init(bar_accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kAccCol = 256;
+
+  // Chunk order on the ring (producer and MMA agree): S(0), S(1), B2(0), S(2), B2(1), ... , B2(T-1)
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, Cfg::kResident);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &tmap_a, bar_a, c * kChunkK, (int)i0);
+      int st = 0; uint32_t ph = 0;
+      auto push = [&](int col_chunk, int j0) {
+        mbar_wait(bar_empty + st, ph ^ 1);
+        mbar_expect_tx(bar_full + st, kChunkBytes);
+        tma_load_2d(sm_ring + st * kChunkBytes, &tmap_b, bar_full + st, col_chunk * kChunkK, j0);
+        if (++st == NST) { st = 0; ph ^= 1; }
+      };
+      for (int t = 0; t <= T; ++t) {
+        if (t < T) {
+          const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+          for (int c = 0; c < KD; ++c) push(c, j0);
+        }
+        if (t >= 1) {
+          const int j0 = (int)(jlo + (int64_t)(t_begin + t - 1) * kTileRows);
+          for (int dc = 0; dc < DNC; ++dc) push(h * DNC + dc, j0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);  // B = streamed chunk, MN-major
+      mbar_wait(bar_a, 0);
+      int st = 0; uint32_t ph = 0;
+      const uint32_t g_addr = smem_u32(sm_g);
+      for (int t = 0; t <= T; ++t) {
+        if (t < T) {
+          const int buf = t & 1;
+          mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * 128;
+          for (int c = 0; c < KD; ++c) {
+            mbar_wait(bar_full + st, ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sm_a + c * kChunkBytes);
+            const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+#pragma unroll
+            for (int k = 0; k < kChunkK / kUmmaK; ++k)
+              umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16), umma_smem_desc(b_addr + k * 32, 16),
+                        idesc_s, (c | k) != 0);
+            umma_commit(bar_empty + st);
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+          umma_commit(bar_sfull + buf);
+        }
+        if (t >= 1) {
+          const int u = t - 1;
+          mbar_wait(bar_gfull, u & 1);
+          tc_fence_after();
+          for (int dc = 0; dc < DNC; ++dc) {
+            mbar_wait(bar_full + st, ph);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+            const uint32_t d_tmem = tmem_base + kAccCol + dc * 64;
+#pragma unroll
+            for (int k = 0; k < kTileRows / kUmmaK; ++k) {
+              // A = G[128 x 128] K-major: K 0..63 in sub-tile 0, 64..127 in sub-tile 1
+              const uint32_t a_k = g_addr + (k >> 2) * kChunkBytes + (k & 3) * 32;
+              // B = chunk[128 j x 64 cols] read MN-major: 16 K-rows (j) = 2048 bytes per step
+              const uint32_t b_k = b_addr + k * 2048;
+              umma_bf16(d_tmem, umma_smem_desc(a_k, 16), umma_smem_desc(b_k, kChunkBytes), idesc_g,
+                        (u | k) != 0);
+            }
+            umma_commit(bar_empty + st);
+            if (++st == NST) { st = 0; ph ^= 1; }
+          }
+          umma_commit(bar_gempty);
+        }
+      }
+      umma_commit(bar_accfull);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    float rrs = 0.f;
+    if (i < n_rows) {
+      bucket_range(gi, bs, n_cols, lo, hi);
+      rrs = 1.0f / rs[i];
+    }
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = -c1;
+    const bool want_gs = (gs_out != nullptr) && (h == 0);
+    float gs_local = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      rcs_s[buf * 128 + r] = (j0 + r < n_cols) ? 1.0f / cs[j0 + r] : 0.f;
+      named_barrier_sync(1, kEpiThreads);
+      mbar_wait(bar_sfull + buf, (t >> 1) & 1);
+      tc_fence_after();
+      const bool full = (j0 >= lo) && (j0 + kTileRows <= hi);
+      const bool warp_full = __all_sync(0xffffffffu, full);
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, raw);
+        tmem_ld_wait();
+        uint32_t packed[16];
+        const float4* rc4 = reinterpret_cast<const float4*>(rcs_s + buf * 128 + cc * 32);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 rc = rc4[e4];
+          const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
+          float g[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int e = e4 * 4 + x;
+            const float a = __uint_as_float(raw[e]);
+            float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
+            if (!warp_full) {
+              const int64_t j = j0 + cc * 32 + e;
+              G = (j >= lo && j < hi) ? G : 0.f;
+            }
+            if (want_gs) gs_local = fmaf(G, a, gs_local);
+            g[x] = G;
+          }
+          packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
+          packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
+        }
+        if (cc == 0) mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
+        // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
+        uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
+          *reinterpret_cast<uint4*>(grow + chunk * 16) =
+              make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_sempty + buf);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_gfull);
+    }
+    // drain the resident accumulator
+    mbar_wait(bar_accfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < DNC * 2; ++cc) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + kAccCol + cc * 32, raw);
+      tmem_ld_wait();
+      const int64_t col0 = (int64_t)h * DNC * 64 + cc * 32;
+      if (i < n_rows) {
+        float* dst = acc_out + i * d + col0;
+        if (col0 + 32 <= d && (d & 3) == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(dst + e) =
+                make_float4(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]),
+                            __uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (col0 + e < d) dst[e] = __uint_as_float(raw[e]);
+        }
+      }
+    }
+    if (want_gs) {
+      gs_local *= s;  // sum G * S with S = s * (u.v)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+      if (lane == 0) atomicAdd(gs_out, gs_local);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// =============================================================================================
+// host launchers
+// =============================================================================================
+// widest column range [jlo, jhi) a 128-row block can need: the union of the buckets its rows touch
+static int64_t max_col_span(int64_t bs, int64_t n_cols) {
+  int64_t span = (ceil_div(kTileRows - 1, bs) + 1) * bs;
+  return span > n_cols ? n_cols : span;
+}
+
+static int pick_segments(int64_t row_blocks, int64_t max_tiles, int z) {
+  // enough (row block, column segment) work items to cover the 148 SMs once
+  int64_t nseg = 148 / (row_blocks * z);
+  if (nseg < 1) nseg = 1;
+  if (nseg > max_tiles) nseg = max_tiles;
+  return (int)nseg;
+}
+
+static int check_tc_shape(int64_t ld, int64_t d) {
+  PLK_REQUIRE(ld % kChunkK == 0 && ld >= d && ld - d < kChunkK, PLK_ERR_INVALID,
+              "bf16 operands must be zero-padded to ld = ceil(d/64)*64 (d=%lld ld=%lld)", (long long)d,
+              (long long)ld);
+  PLK_REQUIRE(ld <= 512, PLK_ERR_UNSUPPORTED, "bf16 path supports d <= 512 (got %lld)", (long long)d);
+  PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the bf16 path needs an sm_100 device");
+  return PLK_OK;
+}
+
+template <int KD>
+static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, dim3 grid, int64_t n_rows,
+                      int64_t row_offset, int64_t n_cols, int64_t bs, int tps, const float* ls,
+                      float* rsum, float* csum, float* diag, cudaStream_t st) {
+  auto kern = infonce_fwd_tc<KD>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<KD>::kSmem));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, FwdCfg<KD>::kSmem, st>>>(ta, tb, n_rows, row_offset, n_cols, bs, tps, ls, rsum, csum, diag);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld, int64_t n_rows,
+                     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
+                     float* row_sumexp, float* col_sumexp, float* diag, cudaStream_t st) {
+  int rc = check_tc_shape(ld, d);
+  if (rc) return rc;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_bf16(&ta, u, n_rows, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&tb, v, n_cols, ld, ld, kTileRows))) return rc;
+  PLK_CUDA(cudaMemsetAsync(row_sumexp, 0, sizeof(float) * n_rows, st));
+  PLK_CUDA(cudaMemsetAsync(col_sumexp, 0, sizeof(float) * n_cols, st));
+  PLK_CUDA(cudaMemsetAsync(diag, 0, sizeof(float) * n_rows, st));
+  const int64_t row_blocks = ceil_div(n_rows, kTileRows);
+  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
+  const int nseg = pick_segments(row_blocks, max_tiles, 1);
+  const int tps = (int)ceil_div(max_tiles, nseg);
+  dim3 grid((unsigned)nseg, (unsigned)row_blocks, 1);
+  switch (ld / kChunkK) {
+#define PLK_CASE(KD) case KD: return launch_fwd<KD>(ta, tb, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, st);
+    PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
+#undef PLK_CASE
+  }
+  set_error("unsupported padded width %lld", (long long)ld);
+  return PLK_ERR_UNSUPPORTED;
+}
+
+template <int KD, int DNC>
+static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, dim3 grid, int64_t n_rows,
+                       int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tps,
+                       const float* ls, const float* rs, const float* cs, float* acc, float* gs,
+                       cudaStream_t st) {
+  auto kern = infonce_grad_tc<KD, DNC>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GradCfg<KD, DNC>::kSmem));
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, GradCfg<KD, DNC>::kSmem, st>>>(ta, tb, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+// number of partial accumulators plk_infonce_grad writes for this shape (bf16 path)
+int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs) {
+  const int64_t ld = ceil_div(d, kChunkK) * kChunkK;
+  const int z = ld > 256 ? 2 : 1;
+  const int64_t row_blocks = ceil_div(n_rows, kTileRows);
+  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
+  return pick_segments(row_blocks, max_tiles, z);
+}
+
+int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
+                      int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
+                      const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st) {
+  int rc = check_tc_shape(ld, d);
+  if (rc) return rc;
+  CUtensorMap ta, tb;
+  if ((rc = make_tmap_bf16(&ta, a, n_rows, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&tb, b, n_cols, ld, ld, kTileRows))) return rc;
+  if (gs) PLK_CUDA(cudaMemsetAsync(gs, 0, sizeof(float), st));
+  const int kd = (int)(ld / kChunkK);
+  const int z = kd > 4 ? 2 : 1;
+  const int64_t row_blocks = ceil_div(n_rows, kTileRows);
+  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
+  const int nseg = pick_segments(row_blocks, max_tiles, z);
+  const int tps = (int)ceil_div(max_tiles, nseg);
+  dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
+  switch (kd) {
+#define PLK_CASE(KD, DNC) case KD: return launch_grad<KD, DNC>(ta, tb, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs, st);
+    PLK_CASE(1, 1) PLK_CASE(2, 2) PLK_CASE(3, 3) PLK_CASE(4, 4) PLK_CASE(5, 3) PLK_CASE(6, 3) PLK_CASE(7, 4) PLK_CASE(8, 4)
+#undef PLK_CASE
+  }
+  set_error("unsupported padded width %lld", (long long)ld);
+  return PLK_ERR_UNSUPPORTED;
+}
+
+}  // namespace plk

@@ -1,0 +1,266 @@
+// tcgen05 (sm_100a) path of the k-nearest candidate search.
+// Same mainloop as the InfoNCE forward (128 resident query rows, gallery streamed as [128 x 64]
+// bf16 TMA chunks, double-buffered 128x128 fp32 score tiles in TMEM); the epilogue keeps, per
+// thread (= per query row), a sorted register list of the KC smallest keys |g|^2 - 2 q.g.
+// The common case is one FFMA + one compare per score; insertions are rare after the first tiles.
+#include <math_constants.h>
+#include "tc_common.cuh"
+
+namespace plk {
+using namespace tc;
+
+constexpr int kTkThreads = 192;
+constexpr int kTkEpi = 128;
+constexpr int kTkAux = 4096;
+
+template <int KD>
+struct TopkCfg {
+  static constexpr int kResident = KD * kChunkBytes;
+  static constexpr int kStagesMax = (kMaxSmem - 1024 - kTkAux - kResident) / kChunkBytes;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+  static constexpr int kSmem = 1024 + kResident + kStages * kChunkBytes + kTkAux;
+  static_assert(kStages >= 2, "not enough shared memory for the ring");
+};
+
+template <int KC>
+__device__ __forceinline__ void list_insert(float (&bk)[KC], int32_t (&bi)[KC], float key, int32_t id) {
+  // replace the current worst, then bubble towards the front (fully unrolled, registers only)
+  bk[KC - 1] = key;
+  bi[KC - 1] = id;
+#pragma unroll
+  for (int p = KC - 1; p > 0; --p) {
+    const bool sw = bk[p] < bk[p - 1];
+    const float k0 = sw ? bk[p] : bk[p - 1], k1 = sw ? bk[p - 1] : bk[p];
+    const int32_t i0 = sw ? bi[p] : bi[p - 1], i1 = sw ? bi[p - 1] : bi[p];
+    bk[p - 1] = k0; bk[p] = k1;
+    bi[p - 1] = i0; bi[p] = i1;
+  }
+}
+
+template <int KD, int KC>
+__global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
+    const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+    const float* __restrict__ g_sqn, int64_t nq, int64_t ng, int64_t goff, int tiles_per_chunk,
+    int nchunks, int kc_out, int32_t* __restrict__ out_idx, float* __restrict__ out_key) {
+  using Cfg = TopkCfg<KD>;
+  constexpr int NST = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_a = smem;
+  uint8_t* sm_ring = smem + Cfg::kResident;
+  uint8_t* aux = sm_ring + NST * kChunkBytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* bar_empty = bar_full + NST;
+  uint64_t* bar_a = bar_empty + NST;
+  uint64_t* bar_sfull = bar_a + 1;
+  uint64_t* bar_sempty = bar_sfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sempty + 2);
+  float* gsq_s = reinterpret_cast<float*>(aux + 512);  // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q0 = (int64_t)blockIdx.y * kTileRows;
+  const int chunk = blockIdx.x;
+  const int total_tiles = (int)((ng + kTileRows - 1) / kTileRows);
+  const int t_begin = chunk * tiles_per_chunk;
+  int t_end = t_begin + tiles_per_chunk;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;
+  if (T == 0) {  // empty chunk: emit empty lists
+    for (int e = threadIdx.x; e < kTileRows * kc_out; e += kTkThreads) {
+      const int64_t qi = q0 + e / kc_out;
+      if (qi < nq) {
+        const int64_t o = (qi * nchunks + chunk) * kc_out + e % kc_out;
+        out_idx[o] = -1;
+        out_key[o] = CUDART_INF_F;
+      }
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_g);
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kTkEpi); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, Cfg::kResident);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &tmap_q, bar_a, c * kChunkK, (int)q0);
+      int st = 0; uint32_t ph = 0;
+      for (int t = 0; t < T; ++t) {
+        const int j0 = (t_begin + t) * kTileRows;
+        for (int c = 0; c < KD; ++c) {
+          mbar_wait(bar_empty + st, ph ^ 1);
+          mbar_expect_tx(bar_full + st, kChunkBytes);
+          tma_load_2d(sm_ring + st * kChunkBytes, &tmap_g, bar_full + st, c * kChunkK, j0);
+          if (++st == NST) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      mbar_wait(bar_a, 0);
+      int st = 0; uint32_t ph = 0;
+      for (int t = 0; t < T; ++t) {
+        const int buf = t & 1;
+        mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 128;
+        for (int c = 0; c < KD; ++c) {
+          mbar_wait(bar_full + st, ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sm_a + c * kChunkBytes);
+          const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+#pragma unroll
+          for (int k = 0; k < kChunkK / kUmmaK; ++k)
+            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16), umma_smem_desc(b_addr + k * 32, 16),
+                      idesc, (c | k) != 0);
+          umma_commit(bar_empty + st);
+          if (++st == NST) { st = 0; ph ^= 1; }
+        }
+        umma_commit(bar_sfull + buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int64_t qi = q0 + r;
+    float bk[KC];
+    int32_t bi[KC];
+#pragma unroll
+    for (int e = 0; e < KC; ++e) { bk[e] = CUDART_INF_F; bi[e] = -1; }
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = (int64_t)(t_begin + t) * kTileRows;
+      gsq_s[buf * 128 + r] = (j0 + r < ng) ? g_sqn[j0 + r] : CUDART_INF_F;
+      named_barrier_sync(1, kTkEpi);
+      mbar_wait(bar_sfull + buf, (t >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, raw);
+        tmem_ld_wait();
+        const float4* g4 = reinterpret_cast<const float4*>(gsq_s + buf * 128 + cc * 32);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 gq = g4[e4];
+          const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int e = e4 * 4 + x;
+            const float key = fmaf(-2.0f, __uint_as_float(raw[e]), gv[x]);
+            if (key < bk[KC - 1]) list_insert<KC>(bk, bi, key, (int32_t)(goff + j0 + cc * 32 + e));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_sempty + buf);
+    }
+    if (qi < nq) {
+      const int64_t o = (qi * nchunks + chunk) * kc_out;
+      for (int e = 0; e < kc_out; ++e) {
+        // KC >= kc_out; static indexing keeps the lists in registers
+        float kv = CUDART_INF_F;
+        int32_t iv = -1;
+#pragma unroll
+        for (int p = 0; p < KC; ++p) {
+          kv = (p == e) ? bk[p] : kv;
+          iv = (p == e) ? bi[p] : iv;
+        }
+        out_idx[o + e] = iv;
+        out_key[o + e] = kv;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+static int topk_bf16_chunks(int64_t nq, int64_t ng) {
+  const int64_t qblocks = ceil_div(nq, kTileRows);
+  const int64_t tiles = ceil_div(ng, kTileRows);
+  // want (query blocks x chunks) to be many waves of 148 CTAs, but chunks of >= 16 tiles
+  int64_t c = ceil_div(148 * 8, qblocks);
+  const int64_t maxc = tiles / 16 > 0 ? tiles / 16 : 1;
+  if (c > maxc) c = maxc;
+  if (c > 64) c = 64;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc) {
+  const int c = topk_bf16_chunks(nq, ng);
+  if (c == 1) return 0;
+  return (size_t)nq * c * kc * (sizeof(int32_t) + sizeof(float));
+}
+
+template <int KD, int KC>
+static int launch_topk(const CUtensorMap& tq, const CUtensorMap& tg, dim3 grid, const float* g_sqn,
+                       int64_t nq, int64_t ng, int64_t goff, int tpc, int nchunks, int kc,
+                       int32_t* o_idx, float* o_key, cudaStream_t st) {
+  auto kern = topk_tc_kernel<KD, KC>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TopkCfg<KD>::kSmem));
+    configured = true;
+  }
+  kern<<<grid, kTkThreads, TopkCfg<KD>::kSmem, st>>>(tq, tg, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int topk_candidates_bf16(const __nv_bfloat16* q, const __nv_bfloat16* g, int64_t ld,
+                         const float* g_sqn, int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff,
+                         int32_t* cand_idx, float* cand_key, void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+  PLK_REQUIRE(ld % kChunkK == 0 && ld >= d && ld - d < kChunkK, PLK_ERR_INVALID,
+              "bf16 operands must be zero-padded to ld = ceil(d/64)*64 (d=%lld ld=%lld)", (long long)d, (long long)ld);
+  PLK_REQUIRE(ld <= 512, PLK_ERR_UNSUPPORTED, "bf16 path supports d <= 512 (got %lld)", (long long)d);
+  PLK_REQUIRE(kc <= 32, PLK_ERR_UNSUPPORTED, "bf16 path keeps at most 32 candidates per query (got %d)", kc);
+  PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the bf16 path needs an sm_100 device");
+  int rc;
+  CUtensorMap tq, tg;
+  if ((rc = make_tmap_bf16(&tq, q, nq, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&tg, g, ng, ld, ld, kTileRows))) return rc;
+  const int nchunks = topk_bf16_chunks(nq, ng);
+  const int tpc = (int)ceil_div(ceil_div(ng, kTileRows), nchunks);
+  int32_t* o_idx = cand_idx;
+  float* o_key = cand_key;
+  if (nchunks > 1) {
+    o_idx = (int32_t*)ws;
+    o_key = (float*)((char*)ws + (size_t)nq * nchunks * kc * sizeof(int32_t));
+  }
+  dim3 grid((unsigned)nchunks, (unsigned)ceil_div(nq, kTileRows), 1);
+  const int kd = (int)(ld / kChunkK);
+  rc = PLK_ERR_UNSUPPORTED;
+#define PLK_CASE(KD)                                                                                  \
+  case KD:                                                                                            \
+    rc = kc <= 16 ? launch_topk<KD, 16>(tq, tg, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, st) \
+                  : launch_topk<KD, 32>(tq, tg, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, st); \
+    break;
+  switch (kd) { PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8) }
+#undef PLK_CASE
+  if (rc) return rc;
+  if (nchunks > 1) return select_candidates(o_idx, o_key, nq, nchunks * kc, kc, cand_idx, cand_key, st);
+  return PLK_OK;
+}
+
+}  // namespace plk

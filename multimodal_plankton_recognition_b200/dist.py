@@ -1,0 +1,163 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU, ``torch.distributed`` (NCCL over
+NVLink 5 / NVSwitch) for the exchange steps.  New functionality relative to the reference, which
+is single-device; the single-process reference on the concatenated global batch is the oracle.
+
+Loss (row-block sharding).  Rank r owns rows [r*n, (r+1)*n) of BOTH modalities.
+    forward : normalise locally -> all-gather u_hat, v_hat (operand dtype)
+              fused kernel on S[own rows, all columns] -> complete row sums, PARTIAL column sums
+              all-reduce column sums [B];  all-gather row sums [B];  all-reduce scalar loss
+    backward: two recompute passes, both complete locally (no gradient reduce-scatter):
+              d image[own]   from (u_own, V_all, R_own, C_all)
+              d profile[own] from (v_own, U_all, C_own, R_all)
+              all-reduce d logit_scale
+Retrieval (gallery sharding).  Every rank searches its gallery shard for all queries, the
+per-shard (index, exact distance) lists are all-gathered and merged on the device.
+
+All local compute goes through ``ops.*`` / ``ann.*`` (the C ABI); this file only adds collectives.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def _world(group):
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    R, _ = _world(group)
+    out = torch.empty((R * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+class _ShardedClipLoss(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, image_emb, profile_emb, logit_scale, buckets, mode, group, grad_scale):
+        R, r = _world(group)
+        n, d = image_emb.shape
+        B = n * R
+        assert B % buckets == 0, "Batch size must be divisible by number of buckets!"
+        bs = B // buckets
+        off = r * n
+        x, y = ops._as_f32_rows(image_emb), ops._as_f32_rows(profile_emb)
+        ls = logit_scale.detach().float()
+        u, idx, nx, _ = ops.l2norm(x, mode)
+        v, idy, ny, _ = ops.l2norm(y, mode)
+        u_all = _all_gather_rows(u, group)
+        v_all = _all_gather_rows(v, group)
+        rs, cs_all, dg = ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls)
+        dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
+        rs_all = _all_gather_rows(rs, group)
+        out = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
+        loss = out[0].clone()
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        ctx.save_for_backward(x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, out[1:].clone())
+        ctx.meta = (n, d, B, bs, off, mode, group, grad_scale, image_emb.dtype, profile_emb.dtype,
+                    logit_scale.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, diag_sum = ctx.saved_tensors
+        n, d, B, bs, off, mode, group, grad_scale, dt_x, dt_y, dt_ls = ctx.meta
+        R, _ = _world(group)
+        go = g.detach().float().reshape(1).contiguous()
+        rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
+        acc_x, gs = ops.infonce_grad_local(u, v_all, mode, d, off, bs, ls, rs_own, cs_all, True)
+        acc_y, _ = ops.infonce_grad_local(v, u_all, mode, d, off, bs, ls, cs_own, rs_all, False)
+        # grad_scale == "ddp": DistributedDataParallel AVERAGES parameter gradients over ranks, while
+        # each rank holds the exact d(global loss)/d(local rows); pre-multiplying by the world size
+        # makes the averaged encoder gradients equal the true global-batch gradients.
+        go_emb = go * R if grad_scale == "ddp" else go
+        dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, ls, go_emb, B, dt_x)
+        dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, ls, go_emb, B, dt_y)
+        dls = ops.infonce_dls(gs, diag_sum, go, B)
+        dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
+        return dx, dy, dls.to(dt_ls), None, None, None, None
+
+
+def sharded_clip_loss(image_emb, profile_emb, logit_scale, buckets: int = 1, mode: int = ops.PLK_BF16,
+                      group=None, grad_scale: str = "ddp") -> torch.Tensor:
+    """Global-batch symmetric InfoNCE from per-rank row blocks (every rank passes n rows; the
+    global batch is the rank-ordered concatenation).  Returns the global loss on every rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("sharded_clip_loss needs an initialised torch.distributed process group")
+    if grad_scale not in ("ddp", "none"):
+        raise ValueError("grad_scale must be 'ddp' or 'none'")
+    return _ShardedClipLoss.apply(image_emb, profile_emb, logit_scale, int(buckets), int(mode), group, grad_scale)
+
+
+class ShardedANNClassifier:
+    """Gallery-sharded counterpart of ``ANNClassifier``: each rank passes ITS shard (X, y); queries
+    are replicated.  Global gallery index = rank-ordered concatenation of the shards."""
+
+    def __init__(self, X, y, group=None, **nndescent_args):
+        from .ann import GpuExactIndex
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("ShardedANNClassifier needs an initialised torch.distributed process group")
+        self.group = group
+        R, r = _world(group)
+        precision = nndescent_args.pop("plk_precision", "bf16")
+        device = nndescent_args.pop("plk_device", None)
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        counts = torch.zeros(R, dtype=torch.int64, device=dev)
+        counts[r] = len(X)
+        dist.all_reduce(counts, group=group)
+        self.counts = counts.cpu().tolist()
+        self.offset = int(sum(self.counts[:r]))
+        self.total = int(sum(self.counts))
+        self.index = GpuExactIndex(X, precision=precision, device=dev, gallery_offset=self.offset)
+        labels = torch.zeros(self.total, dtype=torch.int64, device=dev)
+        labels[self.offset:self.offset + len(X)] = torch.from_numpy(np.asarray(y).astype(np.int64)).to(dev)
+        dist.all_reduce(labels, group=group)
+        self._labels_dev = labels
+        self.y_ = labels.cpu().numpy()
+
+    def search_device(self, q32: torch.Tensor, k: int):
+        from . import _lib
+        lib = _lib.load()
+        R, _ = _world(self.group)
+        k_loc = min(k, self.index.n)
+        idx, dst = self.index.search_device(q32, k_loc)
+        if k_loc < k:  # pad short shards with empty slots
+            pad_i = torch.full((idx.shape[0], k - k_loc), -1, device=idx.device, dtype=torch.int32)
+            pad_d = torch.full((idx.shape[0], k - k_loc), float("inf"), device=idx.device)
+            idx, dst = torch.cat((idx, pad_i), 1).contiguous(), torch.cat((dst, pad_d), 1).contiguous()
+        nq = idx.shape[0]
+        all_i = torch.empty((R, nq, k), device=idx.device, dtype=torch.int32)
+        all_d = torch.empty((R, nq, k), device=idx.device, dtype=torch.float32)
+        dist.all_gather_into_tensor(all_i, idx, group=self.group)
+        dist.all_gather_into_tensor(all_d, dst, group=self.group)
+        cand_i = all_i.permute(1, 0, 2).reshape(nq, R * k).contiguous()
+        cand_d = all_d.permute(1, 0, 2).reshape(nq, R * k).contiguous()
+        out_i = torch.empty((nq, k), device=idx.device, dtype=torch.int32)
+        out_d = torch.empty((nq, k), device=idx.device, dtype=torch.float32)
+        with torch.cuda.device(idx.device):
+            lib.check(lib.plk_topk_merge(cand_i.data_ptr(), cand_d.data_ptr(), nq, R * k, k, out_i.data_ptr(),
+                                         out_d.data_ptr(), torch.cuda.current_stream(idx.device).cuda_stream),
+                      "plk_topk_merge")
+        return out_i, out_d
+
+    def kneighbors(self, *X, **query_args):
+        k = min(int(query_args.get("k", 10)), self.total)
+        out = []
+        for x in X:
+            q32 = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.index.device)
+            i, d_ = self.search_device(q32, k)
+            out.append((i.cpu().numpy(), d_.cpu().numpy()))
+        return tuple(out)
+
+    def predict(self, *X, **query_args):
+        from .ann import knn_vote_device
+        k = min(int(query_args.get("k", 10)), self.total)
+        lists = [self.search_device(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.index.device), k)
+                 for x in X]
+        idx = torch.cat([p[0] for p in lists], dim=1).contiguous()
+        dst = torch.cat([p[1] for p in lists], dim=1).contiguous()
+        return knn_vote_device(idx, dst, self._labels_dev).cpu().numpy().astype(int).ravel()

@@ -1,0 +1,193 @@
+"""Torch-level plumbing over the C ABI (``include/plk.h``): device buffers, the current CUDA
+stream, and the ``plk::clip_loss_fwd`` / ``plk::clip_loss_bwd`` custom ops with autograd.
+
+PyTorch is used here for device memory, streams and autograd wiring only; every arithmetic
+step of the hot path runs in ``libplk.so``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import PLK_BF16, PLK_F16, PLK_F32
+
+MODES = {"fp32": PLK_F32, "bf16": PLK_BF16}
+_DT = {torch.float32: PLK_F32, torch.bfloat16: PLK_BF16, torch.float16: PLK_F16}
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if not t.is_cuda:
+            raise RuntimeError("multimodal_plankton_recognition_b200 runs on CUDA (sm_100a) only; "
+                               "there is no CPU fallback -- move the tensors to a B200")
+
+
+def padded_width(d: int, mode: int) -> int:
+    return (d + 63) // 64 * 64 if mode == PLK_BF16 else d
+
+
+def l2norm(x: torch.Tensor, mode: int, normalise: bool = True):
+    """-> (u [n, ld] operand dtype, inv_den [n], nrm [n], sqn [n])   (plk_l2norm_fwd)"""
+    lib = _lib.load()
+    n, d = x.shape
+    ld = padded_width(d, mode)
+    u = torch.empty((n, ld), device=x.device, dtype=torch.bfloat16 if mode == PLK_BF16 else torch.float32)
+    stats = torch.empty((3, n), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        lib.check(lib.plk_l2norm_fwd(x.data_ptr(), _DT[x.dtype], n, d, x.stride(0), u.data_ptr(), mode, ld,
+                                     stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                                     1 if normalise else 0, _stream(x)), "plk_l2norm_fwd")
+    return u, stats[0], stats[1], stats[2]
+
+
+def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale):
+    """Fused similarity + sum-exp for the owned rows `u` against all rows `v`.
+    -> (row_sumexp [n_rows], col_sumexp [n_cols] (partial over owned rows), diag [n_rows])"""
+    lib = _lib.load()
+    n_rows, n_cols = u.shape[0], v.shape[0]
+    rs = torch.empty(n_rows, device=u.device, dtype=torch.float32)
+    cs = torch.empty(n_cols, device=u.device, dtype=torch.float32)
+    dg = torch.empty(n_rows, device=u.device, dtype=torch.float32)
+    with torch.cuda.device(u.device):
+        lib.check(lib.plk_infonce_fwd(u.data_ptr(), v.data_ptr(), mode, u.stride(0), n_rows, row_offset, n_cols,
+                                      d, bucket_size, logit_scale.data_ptr(), rs.data_ptr(), cs.data_ptr(),
+                                      dg.data_ptr(), _stream(u)), "plk_infonce_fwd")
+    return rs, cs, dg
+
+
+def infonce_loss_local(rs, cs_own, dg, logit_scale, batch_global):
+    """-> out[2] = (loss partial over the owned rows, sum of the owned diagonal logits)"""
+    lib = _lib.load()
+    out = torch.empty(2, device=rs.device, dtype=torch.float32)
+    with torch.cuda.device(rs.device):
+        lib.check(lib.plk_infonce_loss(rs.data_ptr(), cs_own.data_ptr(), dg.data_ptr(), logit_scale.data_ptr(),
+                                       rs.shape[0], batch_global, out[0:].data_ptr(), out[1:].data_ptr(),
+                                       _stream(rs)), "plk_infonce_loss")
+    return out
+
+
+def infonce_grad_local(a, b, mode, d, row_offset, bucket_size, logit_scale, rs, cs, want_gs):
+    """One direction of the recompute backward -> (acc [parts, n_rows, d], gs [1] or None)"""
+    lib = _lib.load()
+    n_rows, n_cols = a.shape[0], b.shape[0]
+    parts = lib.plk_infonce_grad_parts(mode, n_rows, n_cols, d, bucket_size)
+    acc = torch.empty((parts, n_rows, d), device=a.device, dtype=torch.float32)
+    gs = torch.empty(1, device=a.device, dtype=torch.float32) if want_gs else None
+    with torch.cuda.device(a.device):
+        lib.check(lib.plk_infonce_grad(a.data_ptr(), b.data_ptr(), mode, a.stride(0), n_rows, row_offset, n_cols,
+                                       d, bucket_size, logit_scale.data_ptr(), rs.data_ptr(), cs.data_ptr(),
+                                       acc.data_ptr(), gs.data_ptr() if want_gs else None, _stream(a)),
+                  "plk_infonce_grad")
+    return acc, gs
+
+
+def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, logit_scale, grad_out, batch_global,
+                        out_dtype):
+    lib = _lib.load()
+    n, d = x.shape
+    dx = torch.empty((n, d), device=x.device, dtype=out_dtype)
+    with torch.cuda.device(x.device):
+        lib.check(lib.plk_infonce_grad_finish(acc.data_ptr(), acc.shape[0], x.data_ptr(), partner.data_ptr(),
+                                              PLK_F32, n, d, x.stride(0), inv_den_x.data_ptr(),
+                                              nrm_x.data_ptr(), inv_den_p.data_ptr(), logit_scale.data_ptr(),
+                                              grad_out.data_ptr(), batch_global, dx.data_ptr(),
+                                              _DT[out_dtype], _stream(x)), "plk_infonce_grad_finish")
+    return dx
+
+
+def infonce_dls(gs, diag_sum, grad_out, batch_global):
+    lib = _lib.load()
+    out = torch.empty((), device=gs.device, dtype=torch.float32)
+    with torch.cuda.device(gs.device):
+        lib.check(lib.plk_infonce_dls(gs.data_ptr(), diag_sum.data_ptr(), grad_out.data_ptr(), batch_global,
+                                      out.data_ptr(), _stream(gs)), "plk_infonce_dls")
+    return out
+
+
+def _as_f32_rows(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# single-GPU custom ops (the object bound to MultiModel.loss calls these)
+# ---------------------------------------------------------------------------------------------
+@torch.library.custom_op("plk::clip_loss_fwd", mutates_args=())
+def clip_loss_fwd(image_emb: torch.Tensor, profile_emb: torch.Tensor, logit_scale: torch.Tensor,
+                  buckets: int, mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
+                                                    torch.Tensor]:
+    """-> (loss [], u [B,ld], v [B,ld], stats [6,B] = (1/den_x, |x|, 1/den_y, |y|, row sum-exp,
+    col sum-exp), diag_sum [1])"""
+    _require_cuda(image_emb, profile_emb, logit_scale)
+    B, d = image_emb.shape
+    bs = B // buckets
+    x, y = _as_f32_rows(image_emb), _as_f32_rows(profile_emb)
+    ls = logit_scale.detach().float()
+    u, idx, nx, _ = l2norm(x, mode)
+    v, idy, ny, _ = l2norm(y, mode)
+    rs, cs, dg = infonce_fwd_local(u, v, mode, d, 0, bs, ls)
+    out = infonce_loss_local(rs, cs, dg, ls, B)
+    stats = torch.stack((idx, nx, idy, ny, rs, cs))
+    return out[0].clone(), u, v, stats, out[1:].clone()
+
+
+@clip_loss_fwd.register_fake
+def _(image_emb, profile_emb, logit_scale, buckets, mode):
+    B, d = image_emb.shape
+    ld = padded_width(d, mode)
+    odt = torch.bfloat16 if mode == PLK_BF16 else torch.float32
+    f = image_emb.new_empty
+    return (f((), dtype=torch.float32), f((B, ld), dtype=odt), f((B, ld), dtype=odt),
+            f((6, B), dtype=torch.float32), f((1,), dtype=torch.float32))
+
+
+@torch.library.custom_op("plk::clip_loss_bwd", mutates_args=())
+def clip_loss_bwd(grad_out: torch.Tensor, image_emb: torch.Tensor, profile_emb: torch.Tensor,
+                  logit_scale: torch.Tensor, u: torch.Tensor, v: torch.Tensor, stats: torch.Tensor,
+                  diag_sum: torch.Tensor, buckets: int, mode: int) -> tuple[torch.Tensor, torch.Tensor,
+                                                                           torch.Tensor]:
+    B, d = image_emb.shape
+    bs = B // buckets
+    x, y = _as_f32_rows(image_emb), _as_f32_rows(profile_emb)
+    ls = logit_scale.detach().float()
+    go = grad_out.detach().float().reshape(1).contiguous()
+    idx, nx, idy, ny, rs, cs = stats.unbind(0)
+    acc_x, gs = infonce_grad_local(u, v, mode, d, 0, bs, ls, rs, cs, True)
+    acc_y, _ = infonce_grad_local(v, u, mode, d, 0, bs, ls, cs, rs, False)
+    dx = infonce_grad_finish(acc_x, x, y, idx, nx, idy, ls, go, B, image_emb.dtype)
+    dy = infonce_grad_finish(acc_y, y, x, idy, ny, idx, ls, go, B, profile_emb.dtype)
+    dls = infonce_dls(gs, diag_sum, go, B).to(logit_scale.dtype)
+    return dx, dy, dls
+
+
+@clip_loss_bwd.register_fake
+def _(grad_out, image_emb, profile_emb, logit_scale, u, v, stats, diag_sum, buckets, mode):
+    return torch.empty_like(image_emb), torch.empty_like(profile_emb), torch.empty_like(logit_scale)
+
+
+def _setup_ctx(ctx, inputs, output):
+    image_emb, profile_emb, logit_scale, buckets, mode = inputs
+    _, u, v, stats, diag_sum = output
+    ctx.save_for_backward(image_emb, profile_emb, logit_scale, u, v, stats, diag_sum)
+    ctx.buckets, ctx.mode = buckets, mode
+
+
+def _backward(ctx, g_loss, *_unused):
+    image_emb, profile_emb, logit_scale, u, v, stats, diag_sum = ctx.saved_tensors
+    dx, dy, dls = clip_loss_bwd(g_loss, image_emb, profile_emb, logit_scale, u, v, stats, diag_sum,
+                                ctx.buckets, ctx.mode)
+    return dx, dy, dls, None, None
+
+
+clip_loss_fwd.register_autograd(_backward, setup_context=_setup_ctx)
+
+
+def clip_loss(image_emb, profile_emb, logit_scale, buckets: int = 1, mode: int = PLK_BF16) -> torch.Tensor:
+    """Symmetric InfoNCE of reference src/coordination.py:26-47 on the fused CUDA path."""
+    return clip_loss_fwd(image_emb, profile_emb, logit_scale, int(buckets), int(mode))[0]

@@ -1,0 +1,51 @@
+"""Host-side mirror of the reference interface (no GPU needed)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ann as oann
+
+
+def test_cliploss_surface_matches_reference():
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    mod = CLIPLoss()                      # reference src/coordination.py:21-23
+    assert list(mod.state_dict().keys()) == ["logit_scale"]
+    assert mod.logit_scale.shape == torch.Size([]) and float(mod.logit_scale) == 1.0
+    assert mod.logit_scale.dtype == torch.float32 and mod.logit_scale.requires_grad
+    CLIPLoss(bias=True)                   # ctor argument accepted and unused, as in the reference
+    x = torch.randn(6, 4)
+    with pytest.raises(AssertionError, match="Batch size must be divisible by number of buckets!"):
+        mod(image_emb=x, profile_emb=x, buckets=4)
+    with pytest.raises(ValueError):
+        CLIPLoss(precision="fp8")
+
+
+def test_no_cpu_fallback():
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    x = torch.randn(8, 4, requires_grad=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        CLIPLoss()(image_emb=x, profile_emb=x, buckets=1)
+    if not torch.cuda.is_available():
+        from multimodal_plankton_recognition_b200 import ANNClassifier
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ANNClassifier(np.eye(4, dtype=np.float32), np.arange(4))
+
+
+def test_get_weights_matches_reference_rule():
+    from multimodal_plankton_recognition_b200.ann import ANNClassifier
+    d = np.array([[0.0, 0.5, 0.0], [0.25, 0.5, 1.0]], dtype=np.float32)
+    w = ANNClassifier._get_weights(None, d.copy())
+    np.testing.assert_array_equal(w, oann.inverse_distance_weights(d))
+    assert w.dtype == np.float32
+
+
+def test_product_never_imports_oracle():
+    import os
+    import re
+    from conftest import ROOT
+    pkg = os.path.join(ROOT, "multimodal_plankton_recognition_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
