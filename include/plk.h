@@ -95,14 +95,14 @@ int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const
 
 /* ------------------------------------------------------------------------------------------
  * a9. Recompute backward, one direction (flash-style: logits are never materialised).
- *   acc_i = sum_j  E_ij (1/rs_i + 1/cs_j) * b_j            for the owned rows i
+ *   acc_i = sum_{j != i}  E_ij (1/rs_i + 1/cs_j) * b_j     for the owned rows i (global j != i)
  *   a [n_rows, ld] owned normalised rows, b [n_cols, ld] all normalised rows of the other
  *   modality, rs [n_rows] the sum-exp along a's rows, cs [n_cols] the sum-exp along b's rows.
  *   Direction image:   (a,b,rs,cs) = (u, v, row_sumexp, col_sumexp)
  *   Direction profile: (a,b,rs,cs) = (v, u, col_sumexp, row_sumexp)   (S is symmetric in roles)
  *   acc  [parts, n_rows, d] fp32 OUT: `parts` partial sums (column sweep split across CTAs to fill
  *        the 148 SMs; parts = plk_infonce_grad_parts(...)); plk_infonce_grad_finish adds them.
- *   gs   nullable; OUT scalar  sum_ij E_ij (1/rs_i + 1/cs_j) S_ij   (for d logit_scale)
+ *   gs   nullable; OUT scalar  sum_ij E_ij (1/rs_i + 1/cs_j) S_ij, j == i included (for d logit_scale)
  * ------------------------------------------------------------------------------------------ */
 int plk_infonce_grad_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
                            int64_t bucket_size);
@@ -111,15 +111,18 @@ int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld,
                      int64_t bucket_size, const float* logit_scale,
                      const float* rs, const float* cs, float* acc, float* gs, void* stream);
 
-/* a9 (tail). Adds the -2*delta_ij term, applies g*s/(2B) and the normalisation backward:
- *   acc_i = sum over the `parts` slabs of acc;
- *   dU_i = coef * (acc_i - 2 p_i / den_p_i),  coef = (*grad_out) * s / (2 B_global)
+/* a9 (tail). Adds the j == i term and the -2*delta_ij term in fp32, applies g*s/(2B) and the
+ * normalisation backward:
+ *   acc_i = sum over the `parts` slabs of acc  (plk_infonce_grad leaves the j == i term out);
+ *   dU_i = coef * (acc_i + (E_ii (1/rs_i + 1/cs_i) - 2) p_i / den_p_i),  E_ii = exp(diag_i - s),
+ *          coef = (*grad_out) * s / (2 B_global)
  *   dx_i = (dU_i - u_i (u_i . dU_i)) / den_i      if ||x_i|| > eps,   else dU_i / eps
- *   x, partner: RAW embeddings [n, d] of this modality / the other one (same rows).
- *   dx [n, d] written in dx_dtype. */
-int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const void* partner, int x_dtype,
-                            int64_t n, int64_t d, int64_t ldx,
+ *   x, partner: RAW fp32 embeddings [n, d] of this modality / the other one (same rows);
+ *   diag, rs, cs: S_ii and the two sum-exps of the owned rows.  dx [n, d] written in dx_dtype. */
+int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const void* partner,
+                            int x_dtype, int64_t n, int64_t d, int64_t ldx,
                             const float* inv_den_x, const float* nrm_x, const float* inv_den_p,
+                            const float* diag, const float* rs, const float* cs,
                             const float* logit_scale, const float* grad_out, int64_t batch_global,
                             void* dx, int dx_dtype, void* stream);
 

@@ -30,21 +30,34 @@ class GpuExactIndex:
     + squared norms.  ``gallery_offset`` makes returned indices global when the gallery is a shard."""
 
     def __init__(self, X, precision: str = "bf16", device=None, gallery_offset: int = 0, slack: int = 6):
-        if precision not in ops.MODES:
-            raise ValueError(f"precision must be one of {sorted(ops.MODES)}, got {precision!r}")
         if not torch.cuda.is_available():
             raise RuntimeError("ANNClassifier needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.lib = _lib.load()
-        self.mode = ops.MODES[precision]
-        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         X = np.ascontiguousarray(X, dtype=np.float32)
         if X.ndim != 2 or X.shape[0] == 0:
             raise ValueError(f"gallery must be a non-empty [N, d] array, got shape {X.shape}")
-        self.n, self.d = X.shape
+        self._setup(torch.from_numpy(X).to(device), precision, gallery_offset, slack)
+
+    @classmethod
+    def from_device(cls, g32: torch.Tensor, precision: str = "bf16", gallery_offset: int = 0, slack: int = 6):
+        """Build over a gallery that already lives in HBM (fp32 [N, d], contiguous)."""
+        self = cls.__new__(cls)
+        if not g32.is_cuda or g32.dtype != torch.float32 or g32.dim() != 2:
+            raise ValueError("from_device expects a CUDA fp32 [N, d] tensor")
+        self._setup(g32.contiguous(), precision, gallery_offset, slack)
+        return self
+
+    def _setup(self, g32, precision, gallery_offset, slack):
+        if precision not in ops.MODES:
+            raise ValueError(f"precision must be one of {sorted(ops.MODES)}, got {precision!r}")
+        self.lib = _lib.load()
+        self.mode = ops.MODES[precision]
+        self.device = g32.device
+        self.n, self.d = g32.shape
         self.gallery_offset = int(gallery_offset)
         self.slack = int(slack)
-        self.g32 = torch.from_numpy(X).to(self.device)
-        self.g_op, _, _, self.g_sqn = ops.l2norm(self.g32, self.mode, normalise=False)
+        self.g32 = g32
+        self.g_op, _, _, self.g_sqn = ops.l2norm(self.g32, self.mode, normalise=False, want_sqn=True)
 
     def prepare(self):  # pynndescent API parity (reference src/ann.py:12)
         return None

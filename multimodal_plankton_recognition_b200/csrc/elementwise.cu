@@ -133,12 +133,16 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(
     const float* __restrict__ acc, int parts, const TI* __restrict__ x,
     const TI* __restrict__ partner, int64_t n, int64_t d, int64_t ldx, const float* __restrict__ inv_den_x,
     const float* __restrict__ nrm_x, const float* __restrict__ inv_den_p,
+    const float* __restrict__ diag, const float* __restrict__ rs, const float* __restrict__ cs,
     const float* __restrict__ ls, const float* __restrict__ grad_out, int64_t batch,
     TO* __restrict__ dx) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
-  const float coef = (*grad_out) * expf(*ls) / (2.0f * (float)batch);
+  const float s = expf(*ls);
+  const float coef = (*grad_out) * s / (2.0f * (float)batch);
+  // fp32 diagonal term: G_ii - 2 = E_ii (1/rs_i + 1/cs_i) - 2
+  const float dterm = expf(diag[row] - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
   const float idx_ = inv_den_x[row], idp = inv_den_p[row];
   const bool clamped = !(nrm_x[row] > kNormEps);
   const float* ar = acc + row * d;
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(
   for (int64_t k = lane; k < d; k += 32) {
     float a = ar[k];
     for (int p = 1; p < parts; ++p) a += ar[k + p * slab];
-    float dU = coef * (a - 2.0f * ld_as_float(pr + k) * idp);
+    float dU = coef * fmaf(dterm, ld_as_float(pr + k) * idp, a);
     dot = fmaf(ld_as_float(xr + k) * idx_, dU, dot);
   }
   dot = warp_sum(dot);
@@ -158,7 +162,7 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(
   for (int64_t k = lane; k < d; k += 32) {
     float a = ar[k];
     for (int p = 1; p < parts; ++p) a += ar[k + p * slab];
-    float dU = coef * (a - 2.0f * ld_as_float(pr + k) * idp);
+    float dU = coef * fmaf(dterm, ld_as_float(pr + k) * idp, a);
     float uk = ld_as_float(xr + k) * idx_;
     st_from_float(dr + k, (dU - uk * dot) * idx_);
   }
@@ -167,15 +171,15 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(
 template <typename TI>
 static int grad_finish_dispatch(const float* acc, int parts, const TI* x, const TI* p, int64_t n, int64_t d,
                                 int64_t ldx, const float* idx_, const float* nrm, const float* idp,
-                                const float* ls, const float* go, int64_t batch, void* dx,
+                                const float* diag, const float* rs, const float* cs, const float* ls, const float* go, int64_t batch, void* dx,
                                 int dx_dtype, cudaStream_t st) {
   dim3 block(256), grid((unsigned)ceil_div(n, 8));
   if (dx_dtype == PLK_F32)
-    grad_finish_kernel<TI, float><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, ls, go, batch, (float*)dx);
+    grad_finish_kernel<TI, float><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (float*)dx);
   else if (dx_dtype == PLK_BF16)
-    grad_finish_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, ls, go, batch, (__nv_bfloat16*)dx);
+    grad_finish_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (__nv_bfloat16*)dx);
   else
-    grad_finish_kernel<TI, __half><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, ls, go, batch, (__half*)dx);
+    grad_finish_kernel<TI, __half><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (__half*)dx);
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
@@ -343,16 +347,17 @@ int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_ou
 
 int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const void* partner, int x_dtype,
                             int64_t n, int64_t d, int64_t ldx, const float* inv_den_x,
-                            const float* nrm_x, const float* inv_den_p, const float* logit_scale,
+                            const float* nrm_x, const float* inv_den_p, const float* diag,
+                            const float* rs, const float* cs, const float* logit_scale,
                             const float* grad_out, int64_t batch_global, void* dx, int dx_dtype,
                             void* stream) {
-  PLK_REQUIRE(acc && x && partner && inv_den_x && nrm_x && inv_den_p && logit_scale && grad_out && dx,
+  PLK_REQUIRE(acc && x && partner && inv_den_x && nrm_x && inv_den_p && diag && rs && cs && logit_scale && grad_out && dx,
               PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(n > 0 && d > 0 && ldx >= d && batch_global >= n && parts >= 1, PLK_ERR_INVALID, "bad sizes");
   PLK_REQUIRE(dx_dtype >= PLK_F32 && dx_dtype <= PLK_F16, PLK_ERR_INVALID, "bad dx_dtype");
   cudaStream_t st = (cudaStream_t)stream;
   switch (x_dtype) {
-    case PLK_F32: return grad_finish_dispatch(acc, parts, (const float*)x, (const float*)partner, n, d, ldx, inv_den_x, nrm_x, inv_den_p, logit_scale, grad_out, batch_global, dx, dx_dtype, st);
+    case PLK_F32: return grad_finish_dispatch(acc, parts, (const float*)x, (const float*)partner, n, d, ldx, inv_den_x, nrm_x, inv_den_p, diag, rs, cs, logit_scale, grad_out, batch_global, dx, dx_dtype, st);
     default: break;
   }
   set_error("grad_finish: raw embeddings must be fp32 (got dtype %d); cast on the host side", x_dtype);

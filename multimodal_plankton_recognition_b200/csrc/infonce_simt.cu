@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
         const float S = s * acc[r][c];
         const float G = valid ? expf(S - s) * (rrs[r] + rcs[tx + 16 * c]) : 0.f;
         gs_local = fmaf(G, S, gs_local);
-        Gs[ty * 4 + r][tx + 16 * c] = G;
+        // the j == i term is added (in fp32, together with -2*delta) by plk_infonce_grad_finish
+        Gs[ty * 4 + r][tx + 16 * c] = (j == row_offset + i0 + ty * 4 + r) ? 0.f : G;
       }
     __syncthreads();
     // out[64 x 128] += Gs[64 x 64] . b[j0:j0+64, dc0:dc0+128]

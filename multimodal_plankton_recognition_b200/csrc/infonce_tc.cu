@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       tc_fence_after();
       const bool full = (j0 >= lo) && (j0 + kTileRows <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full);
+      const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + kTileRows && i < n_rows);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         uint32_t raw[32];
@@ -423,6 +424,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
           }
           packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
           packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
+        }
+        if (has_diag) {
+          // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked
+          // softmax and nearly cancels against the -2*delta term): drop it from the bf16 operand
+          const int64_t de = gi - (j0 + cc * 32);
+          if (de >= 0 && de < 32) {
+#pragma unroll
+            for (int p = 0; p < 16; ++p)
+              if (p == (int)(de >> 1)) packed[p] &= (de & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+          }
         }
         if (cc == 0) mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
         // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle

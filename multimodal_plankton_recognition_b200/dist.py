@@ -49,22 +49,30 @@ class _ShardedClipLoss(torch.autograd.Function):
         ls = logit_scale.detach().float()
         u, idx, nx, _ = ops.l2norm(x, mode)
         v, idy, ny, _ = ops.l2norm(y, mode)
-        u_all = _all_gather_rows(u, group)
-        v_all = _all_gather_rows(v, group)
-        rs, cs_all, dg = ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls)
-        dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
-        rs_all = _all_gather_rows(rs, group)
-        out = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
-        loss = out[0].clone()
+        if n % bs == 0:
+            # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange,
+            # the local problem is complete; only the scalars are reduced.
+            u_all, v_all, loc_off = u, v, 0
+            rs, cs_all, dg = ops.infonce_fwd_local(u, v, mode, d, 0, bs, ls)
+            rs_all = rs
+        else:
+            loc_off = off
+            u_all = _all_gather_rows(u, group)
+            v_all = _all_gather_rows(v, group)
+            rs, cs_all, dg = ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls)
+            dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
+            rs_all = _all_gather_rows(rs, group)
+        off = loc_off
+        loss, diag_sum = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-        ctx.save_for_backward(x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, out[1:].clone())
+        ctx.save_for_backward(x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, diag_sum)
         ctx.meta = (n, d, B, bs, off, mode, group, grad_scale, image_emb.dtype, profile_emb.dtype,
                     logit_scale.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, diag_sum = ctx.saved_tensors
+        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, diag_sum = ctx.saved_tensors
         n, d, B, bs, off, mode, group, grad_scale, dt_x, dt_y, dt_ls = ctx.meta
         R, _ = _world(group)
         go = g.detach().float().reshape(1).contiguous()
@@ -75,8 +83,8 @@ class _ShardedClipLoss(torch.autograd.Function):
         # each rank holds the exact d(global loss)/d(local rows); pre-multiplying by the world size
         # makes the averaged encoder gradients equal the true global-batch gradients.
         go_emb = go * R if grad_scale == "ddp" else go
-        dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, ls, go_emb, B, dt_x)
-        dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, ls, go_emb, B, dt_y)
+        dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs_own, cs_own, ls, go_emb, B, dt_x)
+        dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs_own, cs_own, ls, go_emb, B, dt_y)
         dls = ops.infonce_dls(gs, diag_sum, go, B)
         dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
         return dx, dy, dls.to(dt_ls), None, None, None, None
@@ -91,6 +99,28 @@ def sharded_clip_loss(image_emb, profile_emb, logit_scale, buckets: int = 1, mod
     if grad_scale not in ("ddp", "none"):
         raise ValueError("grad_scale must be 'ddp' or 'none'")
     return _ShardedClipLoss.apply(image_emb, profile_emb, logit_scale, int(buckets), int(mode), group, grad_scale)
+
+
+def merge_shard_results(idx: torch.Tensor, dst: torch.Tensor, k: int, group=None):
+    """All-gather the per-shard (global index, exact distance) lists [nq, k] and keep the k best per
+    query by (distance, index) on the device (plk_topk_merge)."""
+    from . import _lib
+    lib = _lib.load()
+    R, _ = _world(group)
+    nq = idx.shape[0]
+    all_i = torch.empty((R, nq, k), device=idx.device, dtype=torch.int32)
+    all_d = torch.empty((R, nq, k), device=idx.device, dtype=torch.float32)
+    dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_d, dst.contiguous(), group=group)
+    cand_i = all_i.permute(1, 0, 2).reshape(nq, R * k).contiguous()
+    cand_d = all_d.permute(1, 0, 2).reshape(nq, R * k).contiguous()
+    out_i = torch.empty((nq, k), device=idx.device, dtype=torch.int32)
+    out_d = torch.empty((nq, k), device=idx.device, dtype=torch.float32)
+    with torch.cuda.device(idx.device):
+        lib.check(lib.plk_topk_merge(cand_i.data_ptr(), cand_d.data_ptr(), nq, R * k, k, out_i.data_ptr(),
+                                     out_d.data_ptr(), torch.cuda.current_stream(idx.device).cuda_stream),
+                  "plk_topk_merge")
+    return out_i, out_d
 
 
 class ShardedANNClassifier:
@@ -120,29 +150,13 @@ class ShardedANNClassifier:
         self.y_ = labels.cpu().numpy()
 
     def search_device(self, q32: torch.Tensor, k: int):
-        from . import _lib
-        lib = _lib.load()
-        R, _ = _world(self.group)
         k_loc = min(k, self.index.n)
         idx, dst = self.index.search_device(q32, k_loc)
         if k_loc < k:  # pad short shards with empty slots
             pad_i = torch.full((idx.shape[0], k - k_loc), -1, device=idx.device, dtype=torch.int32)
             pad_d = torch.full((idx.shape[0], k - k_loc), float("inf"), device=idx.device)
             idx, dst = torch.cat((idx, pad_i), 1).contiguous(), torch.cat((dst, pad_d), 1).contiguous()
-        nq = idx.shape[0]
-        all_i = torch.empty((R, nq, k), device=idx.device, dtype=torch.int32)
-        all_d = torch.empty((R, nq, k), device=idx.device, dtype=torch.float32)
-        dist.all_gather_into_tensor(all_i, idx, group=self.group)
-        dist.all_gather_into_tensor(all_d, dst, group=self.group)
-        cand_i = all_i.permute(1, 0, 2).reshape(nq, R * k).contiguous()
-        cand_d = all_d.permute(1, 0, 2).reshape(nq, R * k).contiguous()
-        out_i = torch.empty((nq, k), device=idx.device, dtype=torch.int32)
-        out_d = torch.empty((nq, k), device=idx.device, dtype=torch.float32)
-        with torch.cuda.device(idx.device):
-            lib.check(lib.plk_topk_merge(cand_i.data_ptr(), cand_d.data_ptr(), nq, R * k, k, out_i.data_ptr(),
-                                         out_d.data_ptr(), torch.cuda.current_stream(idx.device).cuda_stream),
-                      "plk_topk_merge")
-        return out_i, out_d
+        return merge_shard_results(idx, dst, k, self.group)
 
     def kneighbors(self, *X, **query_args):
         k = min(int(query_args.get("k", 10)), self.total)

@@ -30,28 +30,33 @@ def padded_width(d: int, mode: int) -> int:
     return (d + 63) // 64 * 64 if mode == PLK_BF16 else d
 
 
-def l2norm(x: torch.Tensor, mode: int, normalise: bool = True):
-    """-> (u [n, ld] operand dtype, inv_den [n], nrm [n], sqn [n])   (plk_l2norm_fwd)"""
+def l2norm(x: torch.Tensor, mode: int, normalise: bool = True, inv_den=None, nrm=None, want_sqn=False):
+    """-> (u [n, ld] operand dtype, inv_den [n], nrm [n], sqn [n] or None)   (plk_l2norm_fwd)
+    `inv_den` / `nrm` may be caller-provided fp32 [n] rows (e.g. slices of a stats buffer)."""
     lib = _lib.load()
     n, d = x.shape
     ld = padded_width(d, mode)
     u = torch.empty((n, ld), device=x.device, dtype=torch.bfloat16 if mode == PLK_BF16 else torch.float32)
-    stats = torch.empty((3, n), device=x.device, dtype=torch.float32)
+    if inv_den is None:
+        inv_den = torch.empty(n, device=x.device, dtype=torch.float32)
+    if nrm is None:
+        nrm = torch.empty(n, device=x.device, dtype=torch.float32)
+    sqn = torch.empty(n, device=x.device, dtype=torch.float32) if want_sqn else None
     with torch.cuda.device(x.device):
         lib.check(lib.plk_l2norm_fwd(x.data_ptr(), _DT[x.dtype], n, d, x.stride(0), u.data_ptr(), mode, ld,
-                                     stats[0].data_ptr(), stats[1].data_ptr(), stats[2].data_ptr(),
+                                     inv_den.data_ptr(), nrm.data_ptr(), sqn.data_ptr() if want_sqn else None,
                                      1 if normalise else 0, _stream(x)), "plk_l2norm_fwd")
-    return u, stats[0], stats[1], stats[2]
+    return u, inv_den, nrm, sqn
 
 
-def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale):
+def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale, rs=None, cs=None, dg=None):
     """Fused similarity + sum-exp for the owned rows `u` against all rows `v`.
     -> (row_sumexp [n_rows], col_sumexp [n_cols] (partial over owned rows), diag [n_rows])"""
     lib = _lib.load()
     n_rows, n_cols = u.shape[0], v.shape[0]
-    rs = torch.empty(n_rows, device=u.device, dtype=torch.float32)
-    cs = torch.empty(n_cols, device=u.device, dtype=torch.float32)
-    dg = torch.empty(n_rows, device=u.device, dtype=torch.float32)
+    rs = torch.empty(n_rows, device=u.device, dtype=torch.float32) if rs is None else rs
+    cs = torch.empty(n_cols, device=u.device, dtype=torch.float32) if cs is None else cs
+    dg = torch.empty(n_rows, device=u.device, dtype=torch.float32) if dg is None else dg
     with torch.cuda.device(u.device):
         lib.check(lib.plk_infonce_fwd(u.data_ptr(), v.data_ptr(), mode, u.stride(0), n_rows, row_offset, n_cols,
                                       d, bucket_size, logit_scale.data_ptr(), rs.data_ptr(), cs.data_ptr(),
@@ -60,14 +65,15 @@ def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale):
 
 
 def infonce_loss_local(rs, cs_own, dg, logit_scale, batch_global):
-    """-> out[2] = (loss partial over the owned rows, sum of the owned diagonal logits)"""
+    """-> (loss partial over the owned rows [] , sum of the owned diagonal logits [1])"""
     lib = _lib.load()
-    out = torch.empty(2, device=rs.device, dtype=torch.float32)
+    loss = torch.empty((), device=rs.device, dtype=torch.float32)
+    diag_sum = torch.empty(1, device=rs.device, dtype=torch.float32)
     with torch.cuda.device(rs.device):
         lib.check(lib.plk_infonce_loss(rs.data_ptr(), cs_own.data_ptr(), dg.data_ptr(), logit_scale.data_ptr(),
-                                       rs.shape[0], batch_global, out[0:].data_ptr(), out[1:].data_ptr(),
+                                       rs.shape[0], batch_global, loss.data_ptr(), diag_sum.data_ptr(),
                                        _stream(rs)), "plk_infonce_loss")
-    return out
+    return loss, diag_sum
 
 
 def infonce_grad_local(a, b, mode, d, row_offset, bucket_size, logit_scale, rs, cs, want_gs):
@@ -85,15 +91,16 @@ def infonce_grad_local(a, b, mode, d, row_offset, bucket_size, logit_scale, rs, 
     return acc, gs
 
 
-def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, logit_scale, grad_out, batch_global,
-                        out_dtype):
+def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own, cs_own, logit_scale, grad_out,
+                        batch_global, out_dtype):
     lib = _lib.load()
     n, d = x.shape
     dx = torch.empty((n, d), device=x.device, dtype=out_dtype)
     with torch.cuda.device(x.device):
         lib.check(lib.plk_infonce_grad_finish(acc.data_ptr(), acc.shape[0], x.data_ptr(), partner.data_ptr(),
                                               PLK_F32, n, d, x.stride(0), inv_den_x.data_ptr(),
-                                              nrm_x.data_ptr(), inv_den_p.data_ptr(), logit_scale.data_ptr(),
+                                              nrm_x.data_ptr(), inv_den_p.data_ptr(), dg.data_ptr(),
+                                              rs_own.data_ptr(), cs_own.data_ptr(), logit_scale.data_ptr(),
                                               grad_out.data_ptr(), batch_global, dx.data_ptr(),
                                               _DT[out_dtype], _stream(x)), "plk_infonce_grad_finish")
     return dx
@@ -122,19 +129,19 @@ def _as_f32_rows(t: torch.Tensor) -> torch.Tensor:
 def clip_loss_fwd(image_emb: torch.Tensor, profile_emb: torch.Tensor, logit_scale: torch.Tensor,
                   buckets: int, mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
                                                     torch.Tensor]:
-    """-> (loss [], u [B,ld], v [B,ld], stats [6,B] = (1/den_x, |x|, 1/den_y, |y|, row sum-exp,
-    col sum-exp), diag_sum [1])"""
+    """-> (loss [], u [B,ld], v [B,ld], stats [7,B] = (1/den_x, |x|, 1/den_y, |y|, row sum-exp,
+    col sum-exp, diagonal logit), diag_sum [1])"""
     _require_cuda(image_emb, profile_emb, logit_scale)
     B, d = image_emb.shape
     bs = B // buckets
     x, y = _as_f32_rows(image_emb), _as_f32_rows(profile_emb)
     ls = logit_scale.detach().float()
-    u, idx, nx, _ = l2norm(x, mode)
-    v, idy, ny, _ = l2norm(y, mode)
-    rs, cs, dg = infonce_fwd_local(u, v, mode, d, 0, bs, ls)
-    out = infonce_loss_local(rs, cs, dg, ls, B)
-    stats = torch.stack((idx, nx, idy, ny, rs, cs))
-    return out[0].clone(), u, v, stats, out[1:].clone()
+    stats = torch.empty((7, B), device=x.device, dtype=torch.float32)
+    u, _, _, _ = l2norm(x, mode, True, stats[0], stats[1])
+    v, _, _, _ = l2norm(y, mode, True, stats[2], stats[3])
+    infonce_fwd_local(u, v, mode, d, 0, bs, ls, stats[4], stats[5], stats[6])
+    loss, diag_sum = infonce_loss_local(stats[4], stats[5], stats[6], ls, B)
+    return loss, u, v, stats, diag_sum
 
 
 @clip_loss_fwd.register_fake
@@ -144,7 +151,7 @@ def _(image_emb, profile_emb, logit_scale, buckets, mode):
     odt = torch.bfloat16 if mode == PLK_BF16 else torch.float32
     f = image_emb.new_empty
     return (f((), dtype=torch.float32), f((B, ld), dtype=odt), f((B, ld), dtype=odt),
-            f((6, B), dtype=torch.float32), f((1,), dtype=torch.float32))
+            f((7, B), dtype=torch.float32), f((1,), dtype=torch.float32))
 
 
 @torch.library.custom_op("plk::clip_loss_bwd", mutates_args=())
@@ -157,11 +164,11 @@ def clip_loss_bwd(grad_out: torch.Tensor, image_emb: torch.Tensor, profile_emb: 
     x, y = _as_f32_rows(image_emb), _as_f32_rows(profile_emb)
     ls = logit_scale.detach().float()
     go = grad_out.detach().float().reshape(1).contiguous()
-    idx, nx, idy, ny, rs, cs = stats.unbind(0)
+    idx, nx, idy, ny, rs, cs, dg = stats.unbind(0)
     acc_x, gs = infonce_grad_local(u, v, mode, d, 0, bs, ls, rs, cs, True)
     acc_y, _ = infonce_grad_local(v, u, mode, d, 0, bs, ls, cs, rs, False)
-    dx = infonce_grad_finish(acc_x, x, y, idx, nx, idy, ls, go, B, image_emb.dtype)
-    dy = infonce_grad_finish(acc_y, y, x, idy, ny, idx, ls, go, B, profile_emb.dtype)
+    dx = infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs, cs, ls, go, B, image_emb.dtype)
+    dy = infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs, cs, ls, go, B, profile_emb.dtype)
     dls = infonce_dls(gs, diag_sum, go, B).to(logit_scale.dtype)
     return dx, dy, dls
 
