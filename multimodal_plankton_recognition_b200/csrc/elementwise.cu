@@ -74,11 +74,78 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const TI* __restrict__ x, i
   }
 }
 
+// Fast path: fp32 rows with d % 128 == 0 (d <= 1024) held entirely in registers, one warp per row,
+// every global access a 16-byte vector with all loads of a row in flight at once.
+template <int NV, typename TO>
+__global__ void __launch_bounds__(256) l2norm_vec_kernel(const float* __restrict__ x, int64_t n, int64_t ldx,
+                                                         TO* __restrict__ u, int64_t ldu,
+                                                         float* __restrict__ inv_den,
+                                                         float* __restrict__ nrm_out,
+                                                         float* __restrict__ sqn_out, int normalise) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ss = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, ss))));
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float den = fmaxf(nrm, kNormEps);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float4 w = v[i];
+    if (normalise) { w.x /= den; w.y /= den; w.z /= den; w.w /= den; }
+    if constexpr (sizeof(TO) == 4) {
+      reinterpret_cast<float4*>(u + row * ldu)[lane + 32 * i] = w;
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = pk;
+      w.x = __bfloat162float(lo.x); w.y = __bfloat162float(lo.y);
+      w.z = __bfloat162float(hi.x); w.w = __bfloat162float(hi.y);
+    }
+    sq = fmaf(w.x, w.x, fmaf(w.y, w.y, fmaf(w.z, w.z, fmaf(w.w, w.w, sq))));
+  }
+  if (sqn_out) sq = warp_sum(sq);
+  if (lane == 0) {
+    if (inv_den) inv_den[row] = normalise ? 1.0f / den : 1.0f;
+    if (nrm_out) nrm_out[row] = nrm;
+    if (sqn_out) sqn_out[row] = sq;
+  }
+}
+
+template <typename TO>
+static bool l2norm_try_vec(const float* x, int64_t n, int64_t d, int64_t ldx, TO* u, int64_t ldu,
+                           float* inv_den, float* nrm, float* sqn, int normalise, cudaStream_t st) {
+  if (d % 128 != 0 || d > 1024 || ldu != d || (ldx & 3) || ((uintptr_t)x & 15) || ((uintptr_t)u & 15)) return false;
+  dim3 block(256), grid((unsigned)ceil_div(n, 8));
+  switch (d / 128) {
+#define PLK_CASE(NV) case NV: l2norm_vec_kernel<NV, TO><<<grid, block, 0, st>>>(x, n, ldx, u, ldu, inv_den, nrm, sqn, normalise); return true;
+    PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
+#undef PLK_CASE
+  }
+  return false;
+}
+
 template <typename TI>
 static int l2norm_dispatch_out(const TI* x, int64_t n, int64_t d, int64_t ldx, void* u, int u_dtype,
                                int64_t ldu, float* inv_den, float* nrm, float* sqn, int normalise,
                                cudaStream_t st) {
   dim3 block(256), grid((unsigned)ceil_div(n, 8));
+  if constexpr (sizeof(TI) == 4) {
+    const bool done = u_dtype == PLK_F32
+                          ? l2norm_try_vec((const float*)x, n, d, ldx, (float*)u, ldu, inv_den, nrm, sqn, normalise, st)
+                          : l2norm_try_vec((const float*)x, n, d, ldx, (__nv_bfloat16*)u, ldu, inv_den, nrm, sqn, normalise, st);
+    if (done) {
+      PLK_LAUNCHED(1);
+      return PLK_OK;
+    }
+  }
   if (u_dtype == PLK_F32)
     l2norm_kernel<TI, float><<<grid, block, 0, st>>>(x, n, d, ldx, (float*)u, ldu, inv_den, nrm, sqn, normalise);
   else
@@ -168,12 +235,78 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(
   }
 }
 
+// Fast path (fp32 in / fp32 out, d % 128 == 0, d <= 1024): the row lives in registers, single pass.
+template <int NV>
+__global__ void __launch_bounds__(256) grad_finish_vec_kernel(
+    const float* __restrict__ acc, int parts, const float* __restrict__ x,
+    const float* __restrict__ partner, int64_t n, int64_t ldx, const float* __restrict__ inv_den_x,
+    const float* __restrict__ nrm_x, const float* __restrict__ inv_den_p,
+    const float* __restrict__ diag, const float* __restrict__ rs, const float* __restrict__ cs,
+    const float* __restrict__ ls, const float* __restrict__ grad_out, int64_t batch,
+    float* __restrict__ dx) {
+  constexpr int64_t d = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float4* ar = reinterpret_cast<const float4*>(acc + row * d);
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  const float4* pr = reinterpret_cast<const float4*>(partner + row * ldx);
+  const int64_t slab4 = n * d / 4;
+  float4 a[NV], xv[NV], pv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    a[i] = ar[lane + 32 * i];
+    xv[i] = xr[lane + 32 * i];
+    pv[i] = pr[lane + 32 * i];
+  }
+  for (int p = 1; p < parts; ++p) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 t = ar[lane + 32 * i + p * slab4];
+      a[i].x += t.x; a[i].y += t.y; a[i].z += t.z; a[i].w += t.w;
+    }
+  }
+  const float s = expf(*ls);
+  const float coef = (*grad_out) * s / (2.0f * (float)batch);
+  const float idx_ = inv_den_x[row], idp = inv_den_p[row];
+  const bool clamped = !(nrm_x[row] > kNormEps);
+  const float dterm = expf(diag[row] - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    a[i].x = coef * fmaf(dterm, pv[i].x * idp, a[i].x);
+    a[i].y = coef * fmaf(dterm, pv[i].y * idp, a[i].y);
+    a[i].z = coef * fmaf(dterm, pv[i].z * idp, a[i].z);
+    a[i].w = coef * fmaf(dterm, pv[i].w * idp, a[i].w);
+    xv[i].x *= idx_; xv[i].y *= idx_; xv[i].z *= idx_; xv[i].w *= idx_;
+    dot = fmaf(xv[i].x, a[i].x, fmaf(xv[i].y, a[i].y, fmaf(xv[i].z, a[i].z, fmaf(xv[i].w, a[i].w, dot))));
+  }
+  dot = warp_sum(dot);
+  if (clamped) dot = 0.f;
+  float4* dr = reinterpret_cast<float4*>(dx + row * d);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    dr[lane + 32 * i] = make_float4((a[i].x - xv[i].x * dot) * idx_, (a[i].y - xv[i].y * dot) * idx_,
+                                    (a[i].z - xv[i].z * dot) * idx_, (a[i].w - xv[i].w * dot) * idx_);
+}
+
 template <typename TI>
 static int grad_finish_dispatch(const float* acc, int parts, const TI* x, const TI* p, int64_t n, int64_t d,
                                 int64_t ldx, const float* idx_, const float* nrm, const float* idp,
                                 const float* diag, const float* rs, const float* cs, const float* ls, const float* go, int64_t batch, void* dx,
                                 int dx_dtype, cudaStream_t st) {
   dim3 block(256), grid((unsigned)ceil_div(n, 8));
+  if constexpr (sizeof(TI) == 4) {
+    if (dx_dtype == PLK_F32 && d % 128 == 0 && d <= 1024 && (ldx & 3) == 0 && (((uintptr_t)x | (uintptr_t)p | (uintptr_t)acc | (uintptr_t)dx) & 15) == 0) {
+      switch (d / 128) {
+#define PLK_CASE(NV) case NV: grad_finish_vec_kernel<NV><<<grid, block, 0, st>>>(acc, parts, (const float*)x, (const float*)p, n, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (float*)dx); break;
+        PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
+#undef PLK_CASE
+      }
+      PLK_LAUNCHED(1);
+      return PLK_OK;
+    }
+  }
   if (dx_dtype == PLK_F32)
     grad_finish_kernel<TI, float><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (float*)dx);
   else if (dx_dtype == PLK_BF16)

@@ -3,7 +3,8 @@
 // Both kernels are warp-specialised:
 //   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor into a 16 KiB-stage ring)
 //   warp 1      MMA issuer     (one elected lane; tcgen05.mma, accumulators in TMEM) + TMEM alloc
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread = one logit row, 32 columns per load)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b: thread = one logit row, 32 columns per load;
+//                               warps w and w+4 share a TMEM lane quadrant and split the columns)
 // A CTA owns 128 rows of the "a" operand (resident in shared memory, K-major SWIZZLE_128B) and
 // streams [128 x 64] chunks of the "b" operand.  The B x B logits only ever exist as 128x128 fp32
 // tiles in TMEM (double buffered so the epilogue of tile t overlaps the MMAs of tile t+1).
@@ -19,8 +20,8 @@
 namespace plk {
 using namespace tc;
 
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kNumThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;   // two warps per SM sub-partition: each takes 64 of a tile's 128 columns
 constexpr int kAuxBytes = 8192;  // barriers + tmem pointer (first 512 B), per-tile column scratch
 
 __device__ __forceinline__ void row_block_cols(int64_t i0, int64_t n_rows, int64_t row_offset,
@@ -62,10 +63,10 @@ struct FwdCfg {
   static_assert(kStages >= 2, "not enough shared memory for the ring");
 };
 
-template <int KD>
+template <int KD, int CS>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-    int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tiles_per_seg,
+    const __grid_constant__ CUtensorMap tmap_bp, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tiles_per_seg,
     const float* __restrict__ ls, float* __restrict__ row_sumexp, float* __restrict__ col_sumexp,
     float* __restrict__ diag) {
   using Cfg = FwdCfg<KD>;
@@ -85,19 +86,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
-  int64_t jlo, jhi;
-  row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  int64_t jlo = 0, jhi = n_cols;  // clusters are only launched for the single-bucket case
+  if constexpr (CS == 1) row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
   const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
   const int t_begin = blockIdx.x * tiles_per_seg;
   int t_end = t_begin + tiles_per_seg;
   if (t_end > total_tiles) t_end = total_tiles;
-  if (t_begin >= t_end) return;  // uniform across the CTA
+  if (t_begin >= t_end) return;  // uniform across the CTA (and across the cluster)
   const int T = t_end - t_begin;
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
     mbar_init(bar_a, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
     fence_barrier_init();
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   if (warp == 1) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -117,8 +120,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
         const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
         for (int c = 0; c < KD; ++c) {
           mbar_wait(bar_empty + st, ph ^ 1);
-          mbar_expect_tx(bar_full + st, kChunkBytes);
-          tma_load_2d(sm_ring + st * kChunkBytes, &tmap_b, bar_full + st, c * kChunkK, j0);
+          ring_load<CS>(sm_ring + st * kChunkBytes, &tmap_b, &tmap_bp, bar_full + st, c * kChunkK, j0, cta_rank);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
       mbar_wait(bar_a, 0);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
@@ -137,13 +140,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
         for (int c = 0; c < KD; ++c) {
           mbar_wait(bar_full + st, ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sm_a + c * kChunkBytes);
-          const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+          const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
+          const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kChunkK / kUmmaK; ++k)
-            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16), umma_smem_desc(b_addr + k * 32, 16),
-                      idesc, (c | k) != 0);
-          umma_commit(bar_empty + st);
+          for (int k = 0; k < kChunkK / kUmmaK; ++k)   // 32 bytes (>>4 = 2) per K step inside the swizzle row
+            umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (c | k) != 0);
+          ring_release<CS>(bar_empty + st);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
         umma_commit(bar_sfull + buf);
@@ -151,10 +153,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: 4 warps, thread = one logit row ----------------
+    // ---------------- epilogue: 8 warps, thread = one logit row x 64 columns ----------------
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;        // which 64 columns of the tile
     const int r = q * 32 + lane;             // row inside the 128-row block
-    const int e_tid = r;                     // 0..127
     const int64_t i = i0 + r;
     const int64_t gi = row_offset + i;
     int64_t lo = 0, hi = 0;
@@ -171,7 +173,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       const bool warp_full = __all_sync(0xffffffffu, full);
       const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + kTileRows && i < n_rows);
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int cc = half * 2 + c2;
         uint32_t raw[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cc * 32, raw);
         tmem_ld_wait();
@@ -190,28 +193,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
         if (has_diag) {
           const int64_t de = gi - (j0 + cc * 32);
           if (de >= 0 && de < 32 && i < n_rows) {
+            // mask-FMA pick (keeps raw[] in registers: a select chain gets turned into a
+            // dynamically indexed local-memory array by the compiler)
+            const int dei = (int)de;
             float dv = 0.f;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) dv = (e == (int)de) ? __uint_as_float(raw[e]) : dv;
+            for (int e = 0; e < 32; ++e) dv = fmaf(__uint_as_float(raw[e]), (e == dei) ? 1.0f : 0.0f, dv);
             diag[i] = s * dv;
           }
         }
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) rsum += v[e];
+        for (int e = 0; e < 32; e += 4) { p0 += v[e]; p1 += v[e + 1]; p2 += v[e + 2]; p3 += v[e + 3]; }
+        rsum += (p0 + p1) + (p2 + p3);
         warp_transpose_reduce(v, lane);
         colpart[(buf * 4 + q) * 128 + cc * 32 + lane] = v[0];
       }
       tc_fence_before();
       mbar_arrive(bar_sempty + buf);
       named_barrier_sync(1, kEpiThreads);
-      const float* cp = colpart + buf * 4 * 128;
-      const float cs = cp[e_tid] + cp[128 + e_tid] + cp[256 + e_tid] + cp[384 + e_tid];
-      if (j0 + e_tid < n_cols && cs != 0.f) atomicAdd(col_sumexp + j0 + e_tid, cs);
+      if (half == (r >> 6)) {
+        const float* cp = colpart + buf * 4 * 128;
+        const float cs = cp[r] + cp[128 + r] + cp[256 + r] + cp[384 + r];
+        if (j0 + r < n_cols && cs != 0.f) atomicAdd(col_sumexp + j0 + r, cs);
+      }
     }
     if (i < n_rows) atomicAdd(row_sumexp + i, rsum);
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
@@ -232,10 +243,10 @@ struct GradCfg {
   static_assert(DNC >= 1 && DNC <= 4, "at most 256 accumulator columns per CTA");
 };
 
-template <int KD, int DNC>
+template <int KD, int DNC, int CS>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-    int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tiles_per_seg,
+    const __grid_constant__ CUtensorMap tmap_bp, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tiles_per_seg,
     const float* __restrict__ ls, const float* __restrict__ rs, const float* __restrict__ cs,
     float* __restrict__ acc_parts /* [nseg][n_rows][d] */, float* __restrict__ gs_out) {
   using Cfg = GradCfg<KD, DNC>;
@@ -260,13 +271,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
   const int h = blockIdx.z;  // which block of DNC*64 output columns
-  int64_t jlo, jhi;
-  row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  int64_t jlo = 0, jhi = n_cols;  // clusters are only launched for the single-bucket case
+  if constexpr (CS == 1) row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
   const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
   const int t_begin = blockIdx.x * tiles_per_seg;
   int t_end = t_begin + tiles_per_seg;
   if (t_end > total_tiles) t_end = total_tiles;
   const int T = t_end > t_begin ? t_end - t_begin : 0;
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
   float* acc_out = acc_parts + (int64_t)blockIdx.x * n_rows * d;
   if (T == 0) {  // this segment has no tiles: its partial is zero (uniform across the CTA)
     for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DNC * 64; e += kNumThreads) {
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
     mbar_init(bar_a, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
     mbar_init(bar_gfull, kEpiThreads);
@@ -290,6 +302,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kAccCol = 256;
@@ -302,8 +315,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       int st = 0; uint32_t ph = 0;
       auto push = [&](int col_chunk, int j0) {
         mbar_wait(bar_empty + st, ph ^ 1);
-        mbar_expect_tx(bar_full + st, kChunkBytes);
-        tma_load_2d(sm_ring + st * kChunkBytes, &tmap_b, bar_full + st, col_chunk * kChunkK, j0);
+        ring_load<CS>(sm_ring + st * kChunkBytes, &tmap_b, &tmap_bp, bar_full + st, col_chunk * kChunkK, j0, cta_rank);
         if (++st == NST) { st = 0; ph ^= 1; }
       };
       for (int t = 0; t <= T; ++t) {
@@ -323,8 +335,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);  // B = streamed chunk, MN-major
       mbar_wait(bar_a, 0);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
-      const uint32_t g_addr = smem_u32(sm_g);
+      const uint32_t g_lo0 = umma_desc_lo(smem_u32(sm_g), 16);
+      const uint32_t b2_lo0 = umma_desc_lo(smem_u32(sm_ring), kChunkBytes);
       for (int t = 0; t <= T; ++t) {
         if (t < T) {
           const int buf = t & 1;
@@ -334,13 +348,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
           for (int c = 0; c < KD; ++c) {
             mbar_wait(bar_full + st, ph);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(sm_a + c * kChunkBytes);
-            const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+            const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
+            const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
 #pragma unroll
             for (int k = 0; k < kChunkK / kUmmaK; ++k)
-              umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16), umma_smem_desc(b_addr + k * 32, 16),
-                        idesc_s, (c | k) != 0);
-            umma_commit(bar_empty + st);
+              umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
+            ring_release<CS>(bar_empty + st);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
           umma_commit(bar_sfull + buf);
@@ -352,18 +365,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
           for (int dc = 0; dc < DNC; ++dc) {
             mbar_wait(bar_full + st, ph);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+            const uint32_t b_lo = b2_lo0 + st * (kChunkBytes >> 4);
             const uint32_t d_tmem = tmem_base + kAccCol + dc * 64;
 #pragma unroll
             for (int k = 0; k < kTileRows / kUmmaK; ++k) {
               // A = G[128 x 128] K-major: K 0..63 in sub-tile 0, 64..127 in sub-tile 1
-              const uint32_t a_k = g_addr + (k >> 2) * kChunkBytes + (k & 3) * 32;
               // B = chunk[128 j x 64 cols] read MN-major: 16 K-rows (j) = 2048 bytes per step
-              const uint32_t b_k = b_addr + k * 2048;
-              umma_bf16(d_tmem, umma_smem_desc(a_k, 16), umma_smem_desc(b_k, kChunkBytes), idesc_g,
-                        (u | k) != 0);
+              umma_bf16_lo(d_tmem, g_lo0 + (k >> 2) * (kChunkBytes >> 4) + (k & 3) * 2, b_lo + k * (2048 >> 4),
+                           idesc_g, (u | k) != 0);
             }
-            umma_commit(bar_empty + st);
+            ring_release<CS>(bar_empty + st);
             if (++st == NST) { st = 0; ph ^= 1; }
           }
           umma_commit(bar_gempty);
@@ -374,6 +385,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     __syncwarp();
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;        // which 64 columns (= which G sub-tile) this warp owns
     const int r = q * 32 + lane;
     const int64_t i = i0 + r;
     const int64_t gi = row_offset + i;
@@ -391,19 +403,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
-      rcs_s[buf * 128 + r] = (j0 + r < n_cols) ? 1.0f / cs[j0 + r] : 0.f;
+      if (half == 0) rcs_s[buf * 128 + r] = (j0 + r < n_cols) ? 1.0f / cs[j0 + r] : 0.f;
       named_barrier_sync(1, kEpiThreads);
       mbar_wait(bar_sfull + buf, (t >> 1) & 1);
       tc_fence_after();
       const bool full = (j0 >= lo) && (j0 + kTileRows <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full);
-      const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + kTileRows && i < n_rows);
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int cc = half * 2 + c2;
         uint32_t raw[32];
         tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, raw);
         tmem_ld_wait();
         uint32_t packed[16];
+        const int64_t de = gi - (j0 + cc * 32);
+        const int dei = (de >= 0 && de < 32) ? (int)de : -1;   // diagonal column inside this chunk
         const float4* rc4 = reinterpret_cast<const float4*>(rcs_s + buf * 128 + cc * 32);
 #pragma unroll
         for (int e4 = 0; e4 < 8; ++e4) {
@@ -420,23 +434,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
               G = (j >= lo && j < hi) ? G : 0.f;
             }
             if (want_gs) gs_local = fmaf(G, a, gs_local);
-            g[x] = G;
+            // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked
+            // softmax and nearly cancels against the -2*delta term): drop it from the bf16 operand
+            g[x] = (e == dei) ? 0.f : G;
           }
           packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
           packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
         }
-        if (has_diag) {
-          // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked
-          // softmax and nearly cancels against the -2*delta term): drop it from the bf16 operand
-          const int64_t de = gi - (j0 + cc * 32);
-          if (de >= 0 && de < 32) {
-#pragma unroll
-            for (int p = 0; p < 16; ++p)
-              if (p == (int)(de >> 1)) packed[p] &= (de & 1) ? 0x0000FFFFu : 0xFFFF0000u;
-          }
-        }
-        if (cc == 0) mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
-        // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
+        if (c2 == 0) mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
+        // G[r][cc*32 .. +32): sub-tile cc/2 (= half), logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
         uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
@@ -450,11 +456,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       fence_proxy_async_smem();
       mbar_arrive(bar_gfull);
     }
-    // drain the resident accumulator
+    // drain the resident accumulator: each half takes DNC of the 2*DNC 32-column chunks
     mbar_wait(bar_accfull, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int cc = 0; cc < DNC * 2; ++cc) {
+    for (int c2 = 0; c2 < DNC; ++c2) {
+      const int cc = half * DNC + c2;
       uint32_t raw[32];
       tmem_ld32(tmem_base + lane_addr + kAccCol + cc * 32, raw);
       tmem_ld_wait();
@@ -483,6 +490,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -515,17 +523,25 @@ static int check_tc_shape(int64_t ld, int64_t d) {
   return PLK_OK;
 }
 
-template <int KD>
-static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, dim3 grid, int64_t n_rows,
-                      int64_t row_offset, int64_t n_cols, int64_t bs, int tps, const float* ls,
-                      float* rsum, float* csum, float* diag, cudaStream_t st) {
-  auto kern = infonce_fwd_tc<KD>;
+// Clusters of 2 row blocks share every streamed chunk (multicast) when all row blocks sweep the
+// same columns, i.e. in the single-bucket case.
+static int pick_cluster(int64_t row_blocks, int64_t bs, int64_t n_cols) {
+  return (bs >= n_cols && row_blocks >= 2) ? 2 : 1;
+}
+
+template <int KD, int CS>
+static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
+                      int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tps,
+                      const float* ls, float* rsum, float* csum, float* diag, cudaStream_t st) {
+  auto kern = infonce_fwd_tc<KD, CS>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<KD>::kSmem));
     configured = true;
   }
-  kern<<<grid, kNumThreads, FwdCfg<KD>::kSmem, st>>>(ta, tb, n_rows, row_offset, n_cols, bs, tps, ls, rsum, csum, diag);
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, ta, tb, tbp, n_rows,
+                         row_offset, n_cols, bs, tps, ls, rsum, csum, diag);
+  if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
@@ -535,19 +551,25 @@ int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld,
                      float* row_sumexp, float* col_sumexp, float* diag, cudaStream_t st) {
   int rc = check_tc_shape(ld, d);
   if (rc) return rc;
-  CUtensorMap ta, tb;
+  int64_t row_blocks = ceil_div(n_rows, kTileRows);
+  const int cs = pick_cluster(row_blocks, bs, n_cols);
+  CUtensorMap ta, tb, tbp;
   if ((rc = make_tmap_bf16(&ta, u, n_rows, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tb, v, n_cols, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&tbp, v, n_cols, ld, ld, kTileRows / 2))) return rc;
   PLK_CUDA(cudaMemsetAsync(row_sumexp, 0, sizeof(float) * n_rows, st));
   PLK_CUDA(cudaMemsetAsync(col_sumexp, 0, sizeof(float) * n_cols, st));
   PLK_CUDA(cudaMemsetAsync(diag, 0, sizeof(float) * n_rows, st));
-  const int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
   const int nseg = pick_segments(row_blocks, max_tiles, 1);
   const int tps = (int)ceil_div(max_tiles, nseg);
+  row_blocks = ceil_div(row_blocks, cs) * cs;   // phantom row block (all rows masked) pads the last cluster
   dim3 grid((unsigned)nseg, (unsigned)row_blocks, 1);
   switch (ld / kChunkK) {
-#define PLK_CASE(KD) case KD: return launch_fwd<KD>(ta, tb, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, st);
+#define PLK_CASE(KD)                                                                                         \
+  case KD:                                                                                                   \
+    return cs == 2 ? launch_fwd<KD, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, st) \
+                   : launch_fwd<KD, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, st);
     PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
   }
@@ -555,18 +577,20 @@ int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld,
   return PLK_ERR_UNSUPPORTED;
 }
 
-template <int KD, int DNC>
-static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, dim3 grid, int64_t n_rows,
-                       int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tps,
+template <int KD, int DNC, int CS>
+static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
+                       int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tps,
                        const float* ls, const float* rs, const float* cs, float* acc, float* gs,
                        cudaStream_t st) {
-  auto kern = infonce_grad_tc<KD, DNC>;
+  auto kern = infonce_grad_tc<KD, DNC, CS>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GradCfg<KD, DNC>::kSmem));
     configured = true;
   }
-  kern<<<grid, kNumThreads, GradCfg<KD, DNC>::kSmem, st>>>(ta, tb, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs);
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), GradCfg<KD, DNC>::kSmem, st, CS, ta, tb, tbp, n_rows,
+                         row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs);
+  if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
@@ -585,19 +609,25 @@ int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld
                       const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st) {
   int rc = check_tc_shape(ld, d);
   if (rc) return rc;
-  CUtensorMap ta, tb;
+  int64_t row_blocks = ceil_div(n_rows, kTileRows);
+  const int csz = pick_cluster(row_blocks, bs, n_cols);
+  CUtensorMap ta, tb, tbp;
   if ((rc = make_tmap_bf16(&ta, a, n_rows, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tb, b, n_cols, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&tbp, b, n_cols, ld, ld, kTileRows / 2))) return rc;
   if (gs) PLK_CUDA(cudaMemsetAsync(gs, 0, sizeof(float), st));
   const int kd = (int)(ld / kChunkK);
   const int z = kd > 4 ? 2 : 1;
-  const int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
   const int nseg = pick_segments(row_blocks, max_tiles, z);
   const int tps = (int)ceil_div(max_tiles, nseg);
+  row_blocks = ceil_div(row_blocks, csz) * csz;
   dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
   switch (kd) {
-#define PLK_CASE(KD, DNC) case KD: return launch_grad<KD, DNC>(ta, tb, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs, st);
+#define PLK_CASE(KD, DNC)                                                                                     \
+  case KD:                                                                                                    \
+    return csz == 2 ? launch_grad<KD, DNC, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs, st) \
+                    : launch_grad<KD, DNC, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs, st);
     PLK_CASE(1, 1) PLK_CASE(2, 2) PLK_CASE(3, 3) PLK_CASE(4, 4) PLK_CASE(5, 3) PLK_CASE(6, 3) PLK_CASE(7, 4) PLK_CASE(8, 4)
 #undef PLK_CASE
   }

@@ -83,6 +83,31 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// Multicast variant: the box is written at the same CTA-relative offset in every CTA of `mask`
+// and complete_tx is signalled on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                               int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "h"(mask)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// thread-block clusters
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA in the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // TMEM + tcgen05
 // ------------------------------------------------------------------------------------------
@@ -113,11 +138,33 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the two shared-memory descriptors given as (low word, shared high word): the issuing
+// thread is a single serial instruction stream, so everything loop-invariant is hoisted and a
+// K-step costs two integer adds (see umma_desc_lo / kUmmaDescHi).
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(0x40004040u /* kUmmaDescHi */), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// Same, arriving on the barrier at this offset in every CTA of `mask` (multicast ring release).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp reads TMEM lane (base_lane + t).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -155,6 +202,13 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)2 << 61;                               // [61,64) layout = SWIZZLE_128B
   return d;
 }
+// The same descriptor split in words: high word = SBO 1024 B (>>4 = 64), version 1 (bit 46 -> 14),
+// SWIZZLE_128B (bits 61..63 -> 29..31); low word = start address >> 4 | (LBO >> 4) << 16.
+constexpr uint32_t kUmmaDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+static_assert(kUmmaDescHi == 0x40004040u, "descriptor high word");
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4)                       // [4,6)   D format  = F32
@@ -164,6 +218,31 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
          | ((uint32_t)b_mn_major << 16)  // [16]    B major
          | ((uint32_t)(n >> 3) << 17)    // [17,23) N >> 3
          | ((uint32_t)(m >> 4) << 24);   // [24,29) M >> 4
+}
+
+// ------------------------------------------------------------------------------------------
+// streamed-operand ring shared by a cluster of CS CTAs that sweep the SAME [128 x 64] chunks
+// (different resident rows): every CTA fetches 1/CS of each chunk and multicasts it to all, so
+// the L2 -> SM traffic of the streamed operand drops by CS.  A slot may be refilled only after
+// every CTA's MMAs have read it: the `empty` barriers count CS arrivals (one multicast
+// tcgen05.commit per CTA); the `full` barriers count the local producer + 16 KiB of tx bytes.
+// ------------------------------------------------------------------------------------------
+template <int CS>
+__device__ __forceinline__ void ring_load(uint8_t* slot, const CUtensorMap* tm_full,
+                                          const CUtensorMap* tm_part, uint64_t* full_bar, int c0,
+                                          int row0, uint32_t cta_rank) {
+  mbar_expect_tx(full_bar, kChunkBytes);
+  if constexpr (CS == 1) {
+    tma_load_2d(slot, tm_full, full_bar, c0, row0);
+  } else {
+    tma_load_2d_mc(slot + cta_rank * (kChunkBytes / CS), tm_part, full_bar, c0,
+                   row0 + (int)cta_rank * (kTileRows / CS), (uint16_t)((1u << CS) - 1));
+  }
+}
+template <int CS>
+__device__ __forceinline__ void ring_release(uint64_t* empty_bar) {
+  if constexpr (CS == 1) umma_commit(empty_bar);
+  else umma_commit_mc(empty_bar, (uint16_t)((1u << CS) - 1));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -189,6 +268,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // 128-byte swizzle, out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                    int box_rows);
+
+// launch with an optional {1, cluster_y, 1} thread-block cluster
+template <typename... KArgs, typename... Args>
+int launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                  int cluster_y, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)cluster_y;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster_y > 1 ? 1 : 0;
+  PLK_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+  return PLK_OK;
+}
 
 }  // namespace tc
 }  // namespace plk

@@ -1,16 +1,18 @@
 // tcgen05 (sm_100a) path of the k-nearest candidate search.
 // Same mainloop as the InfoNCE forward (128 resident query rows, gallery streamed as [128 x 64]
 // bf16 TMA chunks, double-buffered 128x128 fp32 score tiles in TMEM); the epilogue keeps, per
-// thread (= per query row), a sorted register list of the KC smallest keys |g|^2 - 2 q.g.
-// The common case is one FFMA + one compare per score; insertions are rare after the first tiles.
+// thread (= per query row x 64 of the tile's 128 columns), a sorted list of the KC smallest keys
+// |g|^2 - 2 q.g.  The common case is one FFMA + one FMNMX per score and a single compare of the
+// 32-column minimum against the current KC-th best; the insertion code exists once (not inlined,
+// lists in thread-local memory) so the hot loop stays small enough for the instruction cache.
 #include <math_constants.h>
 #include "tc_common.cuh"
 
 namespace plk {
 using namespace tc;
 
-constexpr int kTkThreads = 192;
-constexpr int kTkEpi = 128;
+constexpr int kTkThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per sub-partition)
+constexpr int kTkEpi = 256;
 constexpr int kTkAux = 4096;
 
 template <int KD>
@@ -22,9 +24,11 @@ struct TopkCfg {
   static_assert(kStages >= 2, "not enough shared memory for the ring");
 };
 
+// Insert (key, id) into the ascending register list (fully unrolled, static indices only).
+// The new entry starts in the last slot and bubbles forward with strict '<', so among equal
+// keys the one inserted first (lower gallery index) stays in front.
 template <int KC>
 __device__ __forceinline__ void list_insert(float (&bk)[KC], int32_t (&bi)[KC], float key, int32_t id) {
-  // replace the current worst, then bubble towards the front (fully unrolled, registers only)
   bk[KC - 1] = key;
   bi[KC - 1] = id;
 #pragma unroll
@@ -37,10 +41,10 @@ __device__ __forceinline__ void list_insert(float (&bk)[KC], int32_t (&bi)[KC], 
   }
 }
 
-template <int KD, int KC>
+template <int KD, int KC, int CS>
 __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
-    const float* __restrict__ g_sqn, int64_t nq, int64_t ng, int64_t goff, int tiles_per_chunk,
+    const __grid_constant__ CUtensorMap tmap_gp, const float* __restrict__ g_sqn, int64_t nq, int64_t ng, int64_t goff, int tiles_per_chunk,
     int nchunks, int kc_out, int32_t* __restrict__ out_idx, float* __restrict__ out_key) {
   using Cfg = TopkCfg<KD>;
   constexpr int NST = Cfg::kStages;
@@ -66,10 +70,10 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   if (t_end > total_tiles) t_end = total_tiles;
   const int T = t_end > t_begin ? t_end - t_begin : 0;
   if (T == 0) {  // empty chunk: emit empty lists
-    for (int e = threadIdx.x; e < kTileRows * kc_out; e += kTkThreads) {
-      const int64_t qi = q0 + e / kc_out;
+    for (int e = threadIdx.x; e < kTileRows * 2 * kc_out; e += kTkThreads) {
+      const int64_t qi = q0 + e / (2 * kc_out);
       if (qi < nq) {
-        const int64_t o = (qi * nchunks + chunk) * kc_out + e % kc_out;
+        const int64_t o = (qi * nchunks + chunk) * 2 * kc_out + e % (2 * kc_out);
         out_idx[o] = -1;
         out_key[o] = CUDART_INF_F;
       }
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_g);
-    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
     mbar_init(bar_a, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kTkEpi); }
     fence_barrier_init();
@@ -88,7 +92,9 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   if (warp == 1) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();
   tc_fence_after();
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -100,8 +106,7 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
         const int j0 = (t_begin + t) * kTileRows;
         for (int c = 0; c < KD; ++c) {
           mbar_wait(bar_empty + st, ph ^ 1);
-          mbar_expect_tx(bar_full + st, kChunkBytes);
-          tma_load_2d(sm_ring + st * kChunkBytes, &tmap_g, bar_full + st, c * kChunkK, j0);
+          ring_load<CS>(sm_ring + st * kChunkBytes, &tmap_g, &tmap_gp, bar_full + st, c * kChunkK, j0, cta_rank);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
@@ -111,6 +116,7 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
       mbar_wait(bar_a, 0);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
@@ -120,13 +126,12 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
         for (int c = 0; c < KD; ++c) {
           mbar_wait(bar_full + st, ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sm_a + c * kChunkBytes);
-          const uint32_t b_addr = smem_u32(sm_ring + st * kChunkBytes);
+          const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
+          const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kChunkK / kUmmaK; ++k)
-            umma_bf16(d_tmem, umma_smem_desc(a_addr + k * 32, 16), umma_smem_desc(b_addr + k * 32, 16),
-                      idesc, (c | k) != 0);
-          umma_commit(bar_empty + st);
+          for (int k = 0; k < kChunkK / kUmmaK; ++k)   // 32 bytes (>>4 = 2) per K step inside the swizzle row
+            umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (c | k) != 0);
+          ring_release<CS>(bar_empty + st);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
         umma_commit(bar_sfull + buf);
@@ -135,59 +140,77 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     __syncwarp();
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int64_t qi = q0 + r;
     float bk[KC];
     int32_t bi[KC];
 #pragma unroll
     for (int e = 0; e < KC; ++e) { bk[e] = CUDART_INF_F; bi[e] = -1; }
+    float thresh = CUDART_INF_F;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = (int64_t)(t_begin + t) * kTileRows;
-      gsq_s[buf * 128 + r] = (j0 + r < ng) ? g_sqn[j0 + r] : CUDART_INF_F;
+      if (half == 0) gsq_s[buf * 128 + r] = (j0 + r < ng) ? g_sqn[j0 + r] : CUDART_INF_F;
       named_barrier_sync(1, kTkEpi);
       mbar_wait(bar_sfull + buf, (t >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int cc = half * 2 + c2;
         uint32_t raw[32];
         tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, raw);
         tmem_ld_wait();
         const float4* g4 = reinterpret_cast<const float4*>(gsq_s + buf * 128 + cc * 32);
+        float key[32];
+        float m0 = CUDART_INF_F, m1 = CUDART_INF_F;
 #pragma unroll
         for (int e4 = 0; e4 < 8; ++e4) {
           const float4 gq = g4[e4];
-          const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+          key[e4 * 4 + 0] = fmaf(-2.0f, __uint_as_float(raw[e4 * 4 + 0]), gq.x);
+          key[e4 * 4 + 1] = fmaf(-2.0f, __uint_as_float(raw[e4 * 4 + 1]), gq.y);
+          key[e4 * 4 + 2] = fmaf(-2.0f, __uint_as_float(raw[e4 * 4 + 2]), gq.z);
+          key[e4 * 4 + 3] = fmaf(-2.0f, __uint_as_float(raw[e4 * 4 + 3]), gq.w);
+          m0 = fminf(m0, fminf(key[e4 * 4 + 0], key[e4 * 4 + 1]));
+          m1 = fminf(m1, fminf(key[e4 * 4 + 2], key[e4 * 4 + 3]));
+        }
+        // Slow path, taken by the whole warp while any lane still holds a key below its current
+        // KC-th best: extract-min from the 32 register keys, insert, clear, repeat.  One copy of
+        // the insertion code (the column-chunk loop is not unrolled), no local memory.
+        float m = fminf(m0, m1);
+        while (__any_sync(0xffffffffu, m < thresh)) {
+          if (m < thresh) {
+            int me = 0;
 #pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const int e = e4 * 4 + x;
-            const float key = fmaf(-2.0f, __uint_as_float(raw[e]), gv[x]);
-            if (key < bk[KC - 1]) list_insert<KC>(bk, bi, key, (int32_t)(goff + j0 + cc * 32 + e));
+            for (int e = 31; e >= 0; --e) me = (key[e] == m) ? e : me;   // lowest column on ties
+            list_insert<KC>(bk, bi, m, (int32_t)(goff + j0 + cc * 32) + me);
+            thresh = bk[KC - 1];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) key[e] = (e == me) ? CUDART_INF_F : key[e];
           }
+          float a0 = CUDART_INF_F, a1 = CUDART_INF_F;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) { a0 = fminf(a0, key[e]); a1 = fminf(a1, key[e + 1]); }
+          m = fminf(a0, a1);
         }
       }
       tc_fence_before();
       mbar_arrive(bar_sempty + buf);
     }
     if (qi < nq) {
-      const int64_t o = (qi * nchunks + chunk) * kc_out;
-      for (int e = 0; e < kc_out; ++e) {
-        // KC >= kc_out; static indexing keeps the lists in registers
-        float kv = CUDART_INF_F;
-        int32_t iv = -1;
+      const int64_t o = (qi * (nchunks * 2) + chunk * 2 + half) * kc_out;
 #pragma unroll
-        for (int p = 0; p < KC; ++p) {
-          kv = (p == e) ? bk[p] : kv;
-          iv = (p == e) ? bi[p] : iv;
+      for (int e = 0; e < KC; ++e)
+        if (e < kc_out) {
+          out_idx[o + e] = bi[e];
+          out_key[o + e] = bk[e];
         }
-        out_idx[o + e] = iv;
-        out_key[o + e] = kv;
-      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
@@ -197,9 +220,10 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
 static int topk_bf16_chunks(int64_t nq, int64_t ng) {
   const int64_t qblocks = ceil_div(nq, kTileRows);
   const int64_t tiles = ceil_div(ng, kTileRows);
-  // want (query blocks x chunks) to be many waves of 148 CTAs, but chunks of >= 16 tiles
-  int64_t c = ceil_div(148 * 8, qblocks);
-  const int64_t maxc = tiles / 16 > 0 ? tiles / 16 : 1;
+  // enough (query block, chunk) CTAs for ~4 waves of 148 SMs, but chunks of >= 64 tiles: every
+  // chunk restarts the per-thread lists, and the warm-up phase of a list is the slow path
+  int64_t c = ceil_div(148 * 4, qblocks);
+  const int64_t maxc = tiles / 64 > 0 ? tiles / 64 : 1;
   if (c > maxc) c = maxc;
   if (c > 64) c = 64;
   if (c < 1) c = 1;
@@ -208,21 +232,22 @@ static int topk_bf16_chunks(int64_t nq, int64_t ng) {
 
 size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc) {
   const int c = topk_bf16_chunks(nq, ng);
-  if (c == 1) return 0;
-  return (size_t)nq * c * kc * (sizeof(int32_t) + sizeof(float));
+  return (size_t)nq * c * 2 * kc * (sizeof(int32_t) + sizeof(float));  // two column-half lists per chunk
 }
 
-template <int KD, int KC>
-static int launch_topk(const CUtensorMap& tq, const CUtensorMap& tg, dim3 grid, const float* g_sqn,
-                       int64_t nq, int64_t ng, int64_t goff, int tpc, int nchunks, int kc,
-                       int32_t* o_idx, float* o_key, cudaStream_t st) {
-  auto kern = topk_tc_kernel<KD, KC>;
+template <int KD, int KC, int CS>
+static int launch_topk(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tgp, dim3 grid,
+                       const float* g_sqn, int64_t nq, int64_t ng, int64_t goff, int tpc, int nchunks,
+                       int kc, int32_t* o_idx, float* o_key, cudaStream_t st) {
+  auto kern = topk_tc_kernel<KD, KC, CS>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TopkCfg<KD>::kSmem));
     configured = true;
   }
-  kern<<<grid, kTkThreads, TopkCfg<KD>::kSmem, st>>>(tq, tg, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key);
+  int rc = launch_kernel(kern, grid, dim3(kTkThreads), TopkCfg<KD>::kSmem, st, CS, tq, tg, tgp, g_sqn, nq, ng,
+                         goff, tpc, nchunks, kc, o_idx, o_key);
+  if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
@@ -237,30 +262,31 @@ int topk_candidates_bf16(const __nv_bfloat16* q, const __nv_bfloat16* g, int64_t
   PLK_REQUIRE(kc <= 32, PLK_ERR_UNSUPPORTED, "bf16 path keeps at most 32 candidates per query (got %d)", kc);
   PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the bf16 path needs an sm_100 device");
   int rc;
-  CUtensorMap tq, tg;
+  CUtensorMap tq, tg, tgp;
   if ((rc = make_tmap_bf16(&tq, q, nq, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tg, g, ng, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&tgp, g, ng, ld, ld, kTileRows / 2))) return rc;
   const int nchunks = topk_bf16_chunks(nq, ng);
   const int tpc = (int)ceil_div(ceil_div(ng, kTileRows), nchunks);
-  int32_t* o_idx = cand_idx;
-  float* o_key = cand_key;
-  if (nchunks > 1) {
-    o_idx = (int32_t*)ws;
-    o_key = (float*)((char*)ws + (size_t)nq * nchunks * kc * sizeof(int32_t));
-  }
-  dim3 grid((unsigned)nchunks, (unsigned)ceil_div(nq, kTileRows), 1);
+  int32_t* o_idx = (int32_t*)ws;
+  float* o_key = (float*)((char*)ws + (size_t)nq * nchunks * 2 * kc * sizeof(int32_t));
+  int64_t qblocks = ceil_div(nq, kTileRows);
+  const int cs = qblocks >= 2 ? 2 : 1;   // pairs of query blocks share every gallery chunk (multicast)
+  qblocks = ceil_div(qblocks, cs) * cs;
+  dim3 grid((unsigned)nchunks, (unsigned)qblocks, 1);
   const int kd = (int)(ld / kChunkK);
   rc = PLK_ERR_UNSUPPORTED;
-#define PLK_CASE(KD)                                                                                  \
-  case KD:                                                                                            \
-    rc = kc <= 16 ? launch_topk<KD, 16>(tq, tg, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, st) \
-                  : launch_topk<KD, 32>(tq, tg, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, st); \
+#define PLK_TK(KD, KC, CS) launch_topk<KD, KC, CS>(tq, tg, tgp, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, st)
+#define PLK_CASE(KD)                                                              \
+  case KD:                                                                        \
+    rc = kc <= 16 ? (cs == 2 ? PLK_TK(KD, 16, 2) : PLK_TK(KD, 16, 1))              \
+                  : (cs == 2 ? PLK_TK(KD, 32, 2) : PLK_TK(KD, 32, 1));             \
     break;
   switch (kd) { PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8) }
+#undef PLK_TK
 #undef PLK_CASE
   if (rc) return rc;
-  if (nchunks > 1) return select_candidates(o_idx, o_key, nq, nchunks * kc, kc, cand_idx, cand_key, st);
-  return PLK_OK;
+  return select_candidates(o_idx, o_key, nq, nchunks * 2 * kc, kc, cand_idx, cand_key, st);
 }
 
 }  // namespace plk
