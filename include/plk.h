@@ -88,10 +88,11 @@ int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld,
 /* a8. loss partial over owned rows:
  *   *loss_out = (1/(2*B_global)) * sum_i [ 2 s + log R_i + log C_i - 2 S_ii ]      reference src/coordination.py:45
  *   col_sumexp_own points at the n_rows entries of the (all-reduced) column sums that
- *   belong to the owned rows.  Also writes sum_i S_ii to *diag_sum_out (used by d logit_scale). */
+ *   belong to the owned rows.  Also writes sum_i S_ii to *diag_sum_out (used by d logit_scale) and,
+ *   if gs_zero is not NULL, stores 0 to *gs_zero (the accumulator plk_infonce_grad adds into). */
 int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const float* diag,
                      const float* logit_scale, int64_t n_rows, int64_t batch_global,
-                     float* loss_out, float* diag_sum_out, void* stream);
+                     float* loss_out, float* diag_sum_out, float* gs_zero, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a9. Recompute backward, one direction (flash-style: logits are never materialised).
@@ -102,7 +103,8 @@ int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const
  *   Direction profile: (a,b,rs,cs) = (v, u, col_sumexp, row_sumexp)   (S is symmetric in roles)
  *   acc  [parts, n_rows, d] fp32 OUT: `parts` partial sums (column sweep split across CTAs to fill
  *        the 148 SMs; parts = plk_infonce_grad_parts(...)); plk_infonce_grad_finish adds them.
- *   gs   nullable; OUT scalar  sum_ij E_ij (1/rs_i + 1/cs_j) S_ij, j == i included (for d logit_scale)
+ *   gs   nullable; IN/OUT scalar, ADDED to: sum_ij E_ij (1/rs_i + 1/cs_j) S_ij, j == i included (for
+ *        d logit_scale).  The caller zero-initialises it (plk_infonce_loss does, via gs_zero).
  * ------------------------------------------------------------------------------------------ */
 int plk_infonce_grad_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
                            int64_t bucket_size);
@@ -110,6 +112,18 @@ int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld,
                      int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
                      int64_t bucket_size, const float* logit_scale,
                      const float* rs, const float* cs, float* acc, float* gs, void* stream);
+
+/* Both directions in ONE launch (fills the SMs with half as many column segments at small batches):
+ *   direction 0: (a0, b0, rs0, cs0) -> acc0 [parts, n_rows, d]  (+= gs)
+ *   direction 1: (a1, b1, rs1, cs1) -> acc1 [parts, n_rows, d]
+ * with parts = plk_infonce_grad_pair_parts(...).  All other arguments as plk_infonce_grad. */
+int plk_infonce_grad_pair_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
+                                int64_t bucket_size);
+int plk_infonce_grad_pair(const void* a0, const void* b0, const void* a1, const void* b1, int op_dtype,
+                          int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
+                          int64_t bucket_size, const float* logit_scale,
+                          const float* rs0, const float* cs0, const float* rs1, const float* cs1,
+                          float* acc0, float* acc1, float* gs, void* stream);
 
 /* a9 (tail). Adds the j == i term and the -2*delta_ij term in fp32, applies g*s/(2B) and the
  * normalisation backward:

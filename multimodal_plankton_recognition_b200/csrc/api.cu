@@ -65,7 +65,13 @@ int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld, int6
 int plk_infonce_grad_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
                            int64_t bucket_size) {
   if (op_dtype != PLK_BF16 || n_rows <= 0 || n_cols <= 0 || d <= 0 || bucket_size <= 0) return 1;
-  return grad_parts_bf16(n_rows, n_cols, d, bucket_size);
+  return grad_parts_bf16(n_rows, n_cols, d, bucket_size, 1);
+}
+
+int plk_infonce_grad_pair_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
+                                int64_t bucket_size) {
+  if (op_dtype != PLK_BF16 || n_rows <= 0 || n_cols <= 0 || d <= 0 || bucket_size <= 0) return 1;
+  return grad_parts_bf16(n_rows, n_cols, d, bucket_size, 2);
 }
 
 int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld, int64_t n_rows,
@@ -83,6 +89,29 @@ int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld, int
                             bucket_size, logit_scale, rs, cs, acc, gs, st);
   return infonce_grad_bf16((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, ld, n_rows, row_offset,
                            n_cols, d, bucket_size, logit_scale, rs, cs, acc, gs, st);
+}
+
+int plk_infonce_grad_pair(const void* a0, const void* b0, const void* a1, const void* b1, int op_dtype,
+                          int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
+                          int64_t bucket_size, const float* logit_scale, const float* rs0,
+                          const float* cs0, const float* rs1, const float* cs1, float* acc0, float* acc1,
+                          float* gs, void* stream) {
+  int rc = check_common(a0, b0, op_dtype, ld, n_rows, n_cols, d, bucket_size);
+  if (rc) return rc;
+  PLK_REQUIRE(a1 && b1 && logit_scale && rs0 && cs0 && rs1 && cs1 && acc0 && acc1, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(row_offset >= 0 && row_offset + n_rows <= n_cols, PLK_ERR_INVALID,
+              "owned rows outside the global batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op_dtype == PLK_F32) {
+    rc = infonce_grad_f32((const float*)a0, (const float*)b0, ld, n_rows, row_offset, n_cols, d, bucket_size,
+                          logit_scale, rs0, cs0, acc0, gs, st);
+    if (rc) return rc;
+    return infonce_grad_f32((const float*)a1, (const float*)b1, ld, n_rows, row_offset, n_cols, d, bucket_size,
+                            logit_scale, rs1, cs1, acc1, nullptr, st);
+  }
+  return infonce_grad_pair_bf16((const __nv_bfloat16*)a0, (const __nv_bfloat16*)b0, (const __nv_bfloat16*)a1,
+                                (const __nv_bfloat16*)b1, ld, n_rows, row_offset, n_cols, d, bucket_size,
+                                logit_scale, rs0, cs0, rs1, cs1, acc0, acc1, gs, st);
 }
 
 size_t plk_topk_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int kc, int op_dtype) {

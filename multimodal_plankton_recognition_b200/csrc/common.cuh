@@ -60,12 +60,18 @@ int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld,
 int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
                       int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
                       const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st);
-int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs);
+int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir);
+int infonce_grad_pair_bf16(const __nv_bfloat16* a0, const __nv_bfloat16* b0, const __nv_bfloat16* a1,
+                           const __nv_bfloat16* b1, int64_t ld, int64_t n_rows, int64_t row_offset,
+                           int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs0,
+                           const float* cs0, const float* rs1, const float* cs1, float* acc0, float* acc1,
+                           float* gs, cudaStream_t st);
 int topk_candidates_bf16(const __nv_bfloat16* q, const __nv_bfloat16* g, int64_t ld,
                          const float* g_sqn, int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff,
                          int32_t* cand_idx, float* cand_key, void* ws, size_t ws_bytes,
                          cudaStream_t st);
 size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc);
+int zero2(float* a, int64_t na, float* b, int64_t nb, cudaStream_t st);
 int select_candidates(const int32_t* in_idx, const float* in_key, int64_t nq, int m, int kc,
                       int32_t* out_idx, float* out_key, cudaStream_t st);
 

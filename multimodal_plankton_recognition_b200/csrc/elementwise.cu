@@ -162,8 +162,10 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ rs
                                                     const float* __restrict__ diag,
                                                     const float* __restrict__ ls, int64_t n,
                                                     int64_t batch, float* __restrict__ loss_out,
-                                                    float* __restrict__ diag_sum_out) {
+                                                    float* __restrict__ diag_sum_out,
+                                                    float* __restrict__ gs_zero) {
   __shared__ double sh[2][32];
+  if (threadIdx.x == 0 && gs_zero != nullptr) *gs_zero = 0.f;
   const double s = (double)expf(*ls);
   double a = 0.0, dsum = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -361,6 +363,20 @@ __global__ void __launch_bounds__(128) select_kernel(const int32_t* __restrict__
   }
 }
 
+// One small kernel instead of several memset nodes (a memset node costs more than a kernel node
+// inside a CUDA graph and this path is launch-bound at the reference's batch sizes).
+__global__ void __launch_bounds__(256) zero2_kernel(float* __restrict__ a, int64_t na, float* __restrict__ b, int64_t nb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < na) a[i] = 0.f;
+  if (i < nb) b[i] = 0.f;
+}
+int zero2(float* a, int64_t na, float* b, int64_t nb, cudaStream_t st) {
+  const int64_t n = na > nb ? na : nb;
+  zero2_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(a, na, b, nb);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
 int select_candidates(const int32_t* in_idx, const float* in_key, int64_t nq, int m, int kc,
                       int32_t* out_idx, float* out_key, cudaStream_t st) {
   select_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, st>>>(in_idx, in_key, nq, m, kc, out_idx, out_key);
@@ -462,10 +478,10 @@ int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx
 
 int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const float* diag,
                      const float* logit_scale, int64_t n_rows, int64_t batch_global, float* loss_out,
-                     float* diag_sum_out, void* stream) {
+                     float* diag_sum_out, float* gs_zero, void* stream) {
   PLK_REQUIRE(row_sumexp && col_sumexp_own && diag && logit_scale && loss_out, PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(n_rows > 0 && batch_global >= n_rows, PLK_ERR_INVALID, "bad sizes");
-  loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_sumexp, col_sumexp_own, diag, logit_scale, n_rows, batch_global, loss_out, diag_sum_out);
+  loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_sumexp, col_sumexp_own, diag, logit_scale, n_rows, batch_global, loss_out, diag_sum_out, gs_zero);
   PLK_LAUNCHED(1);
   return PLK_OK;
 }

@@ -217,9 +217,10 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
 int infonce_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset,
                     int64_t n_cols, int64_t d, int64_t bs, const float* ls, float* row_sumexp,
                     float* col_sumexp, float* diag, cudaStream_t st) {
-  PLK_CUDA(cudaMemsetAsync(row_sumexp, 0, sizeof(float) * n_rows, st));
-  PLK_CUDA(cudaMemsetAsync(col_sumexp, 0, sizeof(float) * n_cols, st));
-  PLK_CUDA(cudaMemsetAsync(diag, 0, sizeof(float) * n_rows, st));
+  int rc;
+  // sums are accumulated with atomics -> zero first; diag needs no init (every owned row has its
+  // diagonal column inside its bucket, so it is always written)
+  if ((rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
   dim3 grid((unsigned)ceil_div(n_cols, BN), (unsigned)ceil_div(n_rows, BM));
   infonce_fwd_simt<<<grid, NT, 0, st>>>(u, v, ld, n_rows, row_offset, n_cols, d, bs, ls, row_sumexp,
                                         col_sumexp, diag);
@@ -230,7 +231,6 @@ int infonce_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, 
 int infonce_grad_f32(const float* a, const float* b, int64_t ld, int64_t n_rows, int64_t row_offset,
                      int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs,
                      const float* cs, float* acc, float* gs, cudaStream_t st) {
-  if (gs) PLK_CUDA(cudaMemsetAsync(gs, 0, sizeof(float), st));
   dim3 grid((unsigned)ceil_div(d, DC), (unsigned)ceil_div(n_rows, BM));
   infonce_grad_simt<<<grid, NT, 0, st>>>(a, b, ld, n_rows, row_offset, n_cols, d, bs, ls, rs, cs, acc, gs);
   PLK_LAUNCHED(1);

@@ -3,8 +3,8 @@
 // Both kernels are warp-specialised:
 //   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor into a 16 KiB-stage ring)
 //   warp 1      MMA issuer     (one elected lane; tcgen05.mma, accumulators in TMEM) + TMEM alloc
-//   warps 2..9  epilogue       (tcgen05.ld 32x32b: thread = one logit row, 32 columns per load;
-//                               warps w and w+4 share a TMEM lane quadrant and split the columns)
+//   warps 2..17 epilogue       (tcgen05.ld 32x32b: thread = one logit row, 32 columns per load;
+//                               warps w, w+4, w+8, w+12 share a TMEM lane quadrant and split the columns)
 // A CTA owns 128 rows of the "a" operand (resident in shared memory, K-major SWIZZLE_128B) and
 // streams [128 x 64] chunks of the "b" operand.  The B x B logits only ever exist as 128x128 fp32
 // tiles in TMEM (double buffered so the epilogue of tile t overlaps the MMAs of tile t+1).
@@ -20,8 +20,9 @@
 namespace plk {
 using namespace tc;
 
-constexpr int kNumThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kEpiThreads = 256;   // two warps per SM sub-partition: each takes 64 of a tile's 128 columns
+constexpr int kNumThreads = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int kEpiThreads = 512;   // four warps per SM sub-partition (latency hiding): each takes one
+                                   // 32-column chunk of a tile's 128 columns
 constexpr int kAuxBytes = 8192;  // barriers + tmem pointer (first 512 B), per-tile column scratch
 
 __device__ __forceinline__ void row_block_cols(int64_t i0, int64_t n_rows, int64_t row_offset,
@@ -82,7 +83,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   uint64_t* bar_sfull = bar_a + 1;                        // [2]
   uint64_t* bar_sempty = bar_sfull + 2;                   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sempty + 2);
-  float* colpart = reinterpret_cast<float*>(aux + 512);   // [2][4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: 8 warps, thread = one logit row x 64 columns ----------------
+    // ---------------- epilogue: 16 warps, thread = one logit row x 32 columns ----------------
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;        // which 64 columns of the tile
+    const int cc = (warp - 2) >> 2;          // which 32-column chunk of the tile
     const int r = q * 32 + lane;             // row inside the 128-row block
     const int64_t i = i0 + r;
     const int64_t gi = row_offset + i;
@@ -166,57 +166,49 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     float rsum = 0.f;
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
-      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows + cc * 32;   // first column of this chunk
       mbar_wait(bar_sfull + buf, (t >> 1) & 1);
       tc_fence_after();
-      const bool full = (j0 >= lo) && (j0 + kTileRows <= hi);
-      const bool warp_full = __all_sync(0xffffffffu, full);
-      const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + kTileRows && i < n_rows);
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int cc = half * 2 + c2;
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cc * 32, raw);
-        tmem_ld_wait();
-        float v[32];
-        if (warp_full) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int64_t j = j0 + cc * 32 + e;
-            const float E = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
-            v[e] = (j >= lo && j < hi) ? E : 0.f;
-          }
-        }
-        if (has_diag) {
-          const int64_t de = gi - (j0 + cc * 32);
-          if (de >= 0 && de < 32 && i < n_rows) {
-            // mask-FMA pick (keeps raw[] in registers: a select chain gets turned into a
-            // dynamically indexed local-memory array by the compiler)
-            const int dei = (int)de;
-            float dv = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) dv = fmaf(__uint_as_float(raw[e]), (e == dei) ? 1.0f : 0.0f, dv);
-            diag[i] = s * dv;
-          }
-        }
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) { p0 += v[e]; p1 += v[e + 1]; p2 += v[e + 2]; p3 += v[e + 3]; }
-        rsum += (p0 + p1) + (p2 + p3);
-        warp_transpose_reduce(v, lane);
-        colpart[(buf * 4 + q) * 128 + cc * 32 + lane] = v[0];
-      }
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cc * 32, raw);
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar_sempty + buf);
-      named_barrier_sync(1, kEpiThreads);
-      if (half == (r >> 6)) {
-        const float* cp = colpart + buf * 4 * 128;
-        const float cs = cp[r] + cp[128 + r] + cp[256 + r] + cp[384 + r];
-        if (j0 + r < n_cols && cs != 0.f) atomicAdd(col_sumexp + j0 + r, cs);
+      mbar_arrive(bar_sempty + buf);   // the accumulator buffer goes back to the MMA warp right away
+      const bool full = (j0 >= lo) && (j0 + 32 <= hi);
+      const bool warp_full = __all_sync(0xffffffffu, full);
+      const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + 32 && i < n_rows);
+      float v[32];
+      if (warp_full) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int64_t j = j0 + e;
+          const float E = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
+          v[e] = (j >= lo && j < hi) ? E : 0.f;
+        }
       }
+      if (has_diag) {
+        const int64_t de = gi - j0;
+        if (de >= 0 && de < 32 && i < n_rows) {
+          // mask-FMA pick (keeps raw[] in registers: a select chain gets turned into a
+          // dynamically indexed local-memory array by the compiler)
+          const int dei = (int)de;
+          float dv = 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) dv = fmaf(__uint_as_float(raw[e]), (e == dei) ? 1.0f : 0.0f, dv);
+          diag[i] = s * dv;
+        }
+      }
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) { p0 += v[e]; p1 += v[e + 1]; p2 += v[e + 2]; p3 += v[e + 3]; }
+      rsum += (p0 + p1) + (p2 + p3);
+      // column sums over this warp's 32 rows, then one 128-byte reduction per warp
+      warp_transpose_reduce(v, lane);
+      const int64_t j = j0 + lane;
+      if (j < n_cols && v[0] != 0.f) atomicAdd(col_sumexp + j, v[0]);
     }
     if (i < n_rows) atomicAdd(row_sumexp + i, rsum);
   }
@@ -230,8 +222,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 }
 
 // =============================================================================================
-// backward (one direction)
+// backward.  One launch serves one direction (ndir = 1) or both (ndir = 2: blockIdx.z % 2 picks
+// the operand set), so that at small batches all SMs are busy with half as many column segments
+// and a single prologue / drain.
 // =============================================================================================
+struct GradDir {
+  CUtensorMap ta, tb, tbp;   // owned rows (box 128), streamed rows (box 128), streamed rows (box 64, multicast)
+  const float* rs;           // sum-exp along the owned rows
+  const float* cs;           // sum-exp along the streamed rows
+  float* acc;                // [nseg][n_rows][d] partial accumulators
+  float* gs;                 // nullable: += sum G*S
+};
+struct GradArgs {
+  GradDir dir[2];
+  int ndir;
+};
 template <int KD, int DNC>
 struct GradCfg {
   static constexpr int kResident = KD * kChunkBytes;
@@ -245,10 +250,9 @@ struct GradCfg {
 
 template <int KD, int DNC, int CS>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
-    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-    const __grid_constant__ CUtensorMap tmap_bp, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tiles_per_seg,
-    const float* __restrict__ ls, const float* __restrict__ rs, const float* __restrict__ cs,
-    float* __restrict__ acc_parts /* [nseg][n_rows][d] */, float* __restrict__ gs_out) {
+    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tiles_per_seg,
+    const float* __restrict__ ls) {
+  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
   using Cfg = GradCfg<KD, DNC>;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
-  const int h = blockIdx.z;  // which block of DNC*64 output columns
+  const int h = blockIdx.z / ga.ndir;  // which block of DNC*64 output columns
   int64_t jlo = 0, jhi = n_cols;  // clusters are only launched for the single-bucket case
   if constexpr (CS == 1) row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
   const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   if (t_end > total_tiles) t_end = total_tiles;
   const int T = t_end > t_begin ? t_end - t_begin : 0;
   const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
-  float* acc_out = acc_parts + (int64_t)blockIdx.x * n_rows * d;
+  float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
   if (T == 0) {  // this segment has no tiles: its partial is zero (uniform across the CTA)
     for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DNC * 64; e += kNumThreads) {
       const int64_t rr = i0 + e / (DNC * 64), col = (int64_t)h * DNC * 64 + e % (DNC * 64);
@@ -289,8 +293,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   }
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&g.ta);
+    tma_prefetch_desc(&g.tb);
     for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
     mbar_init(bar_a, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
@@ -311,11 +315,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(bar_a, Cfg::kResident);
-      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &tmap_a, bar_a, c * kChunkK, (int)i0);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &g.ta, bar_a, c * kChunkK, (int)i0);
       int st = 0; uint32_t ph = 0;
       auto push = [&](int col_chunk, int j0) {
         mbar_wait(bar_empty + st, ph ^ 1);
-        ring_load<CS>(sm_ring + st * kChunkBytes, &tmap_b, &tmap_bp, bar_full + st, col_chunk * kChunkK, j0, cta_rank);
+        ring_load<CS>(sm_ring + st * kChunkBytes, &g.tb, &g.tbp, bar_full + st, col_chunk * kChunkK, j0, cta_rank);
         if (++st == NST) { st = 0; ph ^= 1; }
       };
       for (int t = 0; t <= T; ++t) {
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;        // which 64 columns (= which G sub-tile) this warp owns
+    const int cc = (warp - 2) >> 2;          // which 32-column chunk of the tile this warp owns
     const int r = q * 32 + lane;
     const int64_t i = i0 + r;
     const int64_t gi = row_offset + i;
@@ -393,79 +397,74 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     float rrs = 0.f;
     if (i < n_rows) {
       bucket_range(gi, bs, n_cols, lo, hi);
-      rrs = 1.0f / rs[i];
+      rrs = 1.0f / g.rs[i];
     }
     const float s = expf(*ls);
     const float c1 = s * kLog2e, c0 = -c1;
-    const bool want_gs = (gs_out != nullptr) && (h == 0);
+    const bool want_gs = (g.gs != nullptr) && (h == 0);
     float gs_local = 0.f;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
-      if (half == 0) rcs_s[buf * 128 + r] = (j0 + r < n_cols) ? 1.0f / cs[j0 + r] : 0.f;
+      if (cc == 0) rcs_s[buf * 128 + r] = (j0 + r < n_cols) ? 1.0f / g.cs[j0 + r] : 0.f;
       named_barrier_sync(1, kEpiThreads);
       mbar_wait(bar_sfull + buf, (t >> 1) & 1);
       tc_fence_after();
-      const bool full = (j0 >= lo) && (j0 + kTileRows <= hi);
+      const bool full = (j0 + cc * 32 >= lo) && (j0 + cc * 32 + 32 <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full);
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {
-        const int cc = half * 2 + c2;
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, raw);
-        tmem_ld_wait();
-        uint32_t packed[16];
-        const int64_t de = gi - (j0 + cc * 32);
-        const int dei = (de >= 0 && de < 32) ? (int)de : -1;   // diagonal column inside this chunk
-        const float4* rc4 = reinterpret_cast<const float4*>(rcs_s + buf * 128 + cc * 32);
-#pragma unroll
-        for (int e4 = 0; e4 < 8; ++e4) {
-          const float4 rc = rc4[e4];
-          const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
-          float g[4];
-#pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const int e = e4 * 4 + x;
-            const float a = __uint_as_float(raw[e]);
-            float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
-            if (!warp_full) {
-              const int64_t j = j0 + cc * 32 + e;
-              G = (j >= lo && j < hi) ? G : 0.f;
-            }
-            if (want_gs) gs_local = fmaf(G, a, gs_local);
-            // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked
-            // softmax and nearly cancels against the -2*delta term): drop it from the bf16 operand
-            g[x] = (e == dei) ? 0.f : G;
-          }
-          packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
-          packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
-        }
-        if (c2 == 0) mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
-        // G[r][cc*32 .. +32): sub-tile cc/2 (= half), logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
-        uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
-#pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-          const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
-          *reinterpret_cast<uint4*>(grow + chunk * 16) =
-              make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
-        }
-      }
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + buf * 128 + cc * 32, raw);
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_sempty + buf);
+      uint32_t packed[16];
+      const int64_t de = gi - (j0 + cc * 32);
+      const int dei = (de >= 0 && de < 32) ? (int)de : -1;   // diagonal column inside this chunk
+      const float4* rc4 = reinterpret_cast<const float4*>(rcs_s + buf * 128 + cc * 32);
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        const float4 rc = rc4[e4];
+        const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
+        float g[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const int e = e4 * 4 + x;
+          const float a = __uint_as_float(raw[e]);
+          float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
+          if (!warp_full) {
+            const int64_t j = j0 + cc * 32 + e;
+            G = (j >= lo && j < hi) ? G : 0.f;
+          }
+          if (want_gs) gs_local = fmaf(G, a, gs_local);
+          // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked
+          // softmax and nearly cancels against the -2*delta term): drop it from the bf16 operand
+          g[x] = (e == dei) ? 0.f : G;
+        }
+        packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
+        packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
+      }
+      mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
+      // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
+      uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
+        *reinterpret_cast<uint4*>(grow + chunk * 16) =
+            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+      }
       fence_proxy_async_smem();
       mbar_arrive(bar_gfull);
     }
-    // drain the resident accumulator: each half takes DNC of the 2*DNC 32-column chunks
+    // drain the resident accumulator: 2*DNC 32-column chunks over the four warps of a quadrant
     mbar_wait(bar_accfull, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c2 = 0; c2 < DNC; ++c2) {
-      const int cc = half * DNC + c2;
+    for (int ch = cc; ch < DNC * 2; ch += 4) {
       uint32_t raw[32];
-      tmem_ld32(tmem_base + lane_addr + kAccCol + cc * 32, raw);
+      tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
       tmem_ld_wait();
-      const int64_t col0 = (int64_t)h * DNC * 64 + cc * 32;
+      const int64_t col0 = (int64_t)h * DNC * 64 + ch * 32;
       if (i < n_rows) {
         float* dst = acc_out + i * d + col0;
         if (col0 + 32 <= d && (d & 3) == 0) {
@@ -485,12 +484,259 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       gs_local *= s;  // sum G * S with S = s * (u.v)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
-      if (lane == 0) atomicAdd(gs_out, gs_local);
+      if (lane == 0) atomicAdd(g.gs, gs_local);
     }
   }
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// =============================================================================================
+// backward, d <= 256: the streamed operand tile (<= 64 KiB) is kept in shared memory for BOTH
+// GEMMs of a tile, and G never touches shared memory -- the epilogue warps overwrite the fp32
+// logits tile in TMEM with the packed bf16 G (tcgen05.st), which the second tcgen05.mma reads as
+// its A operand straight from tensor memory (B = the same tile viewed MN-major, N = d):
+//     S(t)    = a . b_t^T                 SS-mode, D = logits buffer t&1
+//     G(t)    = E (1/rs + 1/cs)           epilogue warps, in place
+//     acc    += G(t) . b_t                TS-mode, D = resident accumulator
+// Issue order S(0), S(1), GV(0), S(2), GV(1), ...: the in-order tensor pipe protects buffer t&1
+// (S(t+2) is issued after GV(t)), so the only barriers are tile-full / G-ready / tile-free.
+// =============================================================================================
+template <int KD>
+struct Grad2Cfg {
+  static constexpr int kResident = KD * kChunkBytes;
+  static constexpr int kTileBuf = KD * kChunkBytes;
+  static constexpr int kSmem = 1024 + kResident + 2 * kTileBuf + kAuxBytes;
+  static_assert(kSmem <= kMaxSmem, "tile-buffer backward needs d <= 256");
+};
+
+template <int KD, int CS>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
+    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+    int64_t d, int64_t bs, int tiles_per_seg, const float* __restrict__ ls) {
+  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
+  using Cfg = Grad2Cfg<KD>;
+  constexpr int DN = KD * 64;  // accumulator columns = padded d
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_a = smem;
+  uint8_t* sm_y = smem + Cfg::kResident;                  // [2][KD chunks]
+  uint8_t* aux = sm_y + 2 * Cfg::kTileBuf;
+  uint64_t* bar_a = reinterpret_cast<uint64_t*>(aux);     // [1]
+  uint64_t* bar_yfull = bar_a + 1;                        // [2]
+  uint64_t* bar_yempty = bar_yfull + 2;                   // [2]
+  uint64_t* bar_sfull = bar_yempty + 2;                   // [2]
+  uint64_t* bar_gfull = bar_sfull + 2;                    // [2]
+  uint64_t* bar_accfull = bar_gfull + 2;                  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
+  float* rcs_s = reinterpret_cast<float*>(aux + 512);     // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
+  int64_t jlo = 0, jhi = n_cols;
+  if constexpr (CS == 1) row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
+  const int t_begin = blockIdx.x * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
+  float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
+  if (T == 0) {
+    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DN; e += kNumThreads) {
+      const int64_t rr = i0 + e / DN, col = e % DN;
+      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.ta);
+    tma_prefetch_desc(&g.tb);
+    tma_prefetch_desc(&g.tbp);
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_yfull + b, 1);
+      mbar_init(bar_yempty + b, CS);
+      mbar_init(bar_sfull + b, 1);
+      mbar_init(bar_gfull + b, kEpiThreads);
+    }
+    mbar_init(bar_accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kAccCol = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, Cfg::kResident);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &g.ta, bar_a, c * kChunkK, (int)i0);
+      for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+        mbar_wait(bar_yempty + b, ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
+        for (int c = 0; c < KD; ++c)
+          chunk_load<CS>(sm_y + (b * KD + c) * kChunkBytes, &g.tb, &g.tbp, bar_yfull + b, c * kChunkK, j0, cta_rank);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DN, 0, 1);   // A from TMEM (K-major), B MN-major
+      mbar_wait(bar_a, 0);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
+      const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);               // K-major view (S)
+      const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), kChunkBytes);     // MN-major view (G.V), LBO = chunk
+      for (int t = 0; t <= T; ++t) {
+        if (t < T) {
+          const int b = t & 1;
+          mbar_wait(bar_yfull + b, (t >> 1) & 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + b * 128;
+#pragma unroll
+          for (int c = 0; c < KD; ++c) {
+            const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
+            const uint32_t b_lo = y_lo0 + (b * KD + c) * (kChunkBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < kChunkK / kUmmaK; ++k)
+              umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
+          }
+          umma_commit(bar_sfull + b);
+        }
+        if (t >= 1) {
+          const int u = t - 1, b = u & 1;
+          mbar_wait(bar_gfull + b, (u >> 1) & 1);
+          tc_fence_after();
+          const uint32_t b_lo = y2_lo0 + b * KD * (kChunkBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kTileRows / kUmmaK; ++k) {
+            // A: packed G, K elements 32c..32c+31 live in columns 32c .. 32c+15 of logits buffer b
+            const uint32_t a_tmem = tmem_base + b * 128 + (k >> 1) * 32 + (k & 1) * 8;
+            umma_bf16_ts(tmem_base + kAccCol, a_tmem, b_lo + k * (2048 >> 4), idesc_g, (u | k) != 0);
+          }
+          ring_release<CS>(bar_yempty + b);   // tile buffer b (and logits buffer b) free once these retire
+        }
+      }
+      umma_commit(bar_accfull);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int cc = (warp - 2) >> 2;          // which 32-column chunk of the tile this warp owns
+    const int r = q * 32 + lane;
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    float rrs = 0.f;
+    if (i < n_rows) {
+      bucket_range(gi, bs, n_cols, lo, hi);
+      rrs = 1.0f / g.rs[i];
+    }
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = -c1;
+    const bool want_gs = g.gs != nullptr;
+    float gs_local = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // 1/cs of the NEXT tile is fetched one tile ahead (its global-load latency hides behind the
+    // exp work of the current tile) and parked in the other half of rcs_s
+    float rc_next = 0.f;
+    if (cc == 0) {
+      const int64_t jc = jlo + (int64_t)t_begin * kTileRows + r;
+      rcs_s[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+    }
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      named_barrier_sync(1, kEpiThreads);   // rcs_s[buf] visible; everyone is done with tile t-1
+      if (cc == 0 && t + 1 < T) {
+        const int64_t jc = j0 + kTileRows + r;
+        rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
+      }
+      mbar_wait(bar_sfull + buf, (t >> 1) & 1);
+      tc_fence_after();
+      const bool full = (j0 + cc * 32 >= lo) && (j0 + cc * 32 + 32 <= hi);
+      const bool warp_full = __all_sync(0xffffffffu, full);
+      const uint32_t col0 = tmem_base + lane_addr + buf * 128 + cc * 32;
+      uint32_t raw[32];
+      tmem_ld32(col0, raw);
+      tmem_ld_wait();
+      uint32_t packed[16];
+      const int64_t de = gi - (j0 + cc * 32);
+      const int dei = (de >= 0 && de < 32) ? (int)de : -1;   // diagonal column inside this chunk
+      const float4* rc4 = reinterpret_cast<const float4*>(rcs_s + buf * 128 + cc * 32);
+#pragma unroll
+      for (int e4 = 0; e4 < 8; ++e4) {
+        const float4 rc = rc4[e4];
+        const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
+        float g[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const int e = e4 * 4 + x;
+          const float a = __uint_as_float(raw[e]);
+          float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
+          if (!warp_full) {
+            const int64_t j = j0 + cc * 32 + e;
+            G = (j >= lo && j < hi) ? G : 0.f;
+          }
+          if (want_gs) gs_local = fmaf(G, a, gs_local);
+          g[x] = (e == dei) ? 0.f : G;   // the j == i term is added in fp32 by plk_infonce_grad_finish
+        }
+        packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
+        packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
+      }
+      // G overwrites the first 16 of this warp's own 32 logits columns (all 32 were read above)
+      tmem_st16(col0, packed);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_gfull + buf);
+      if (cc == 0 && t + 1 < T) rcs_s[(buf ^ 1) * 128 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+    }
+    mbar_wait(bar_accfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = cc; ch < 2 * KD; ch += 4) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+      tmem_ld_wait();
+      const int64_t col0 = (int64_t)ch * 32;
+      if (i < n_rows) {
+        float* dst = acc_out + i * d + col0;
+        if (col0 + 32 <= d && (d & 3) == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(dst + e) =
+                make_float4(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]),
+                            __uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (col0 + e < d) dst[e] = __uint_as_float(raw[e]);
+        }
+      }
+    }
+    if (want_gs) {
+      gs_local *= s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+      if (lane == 0) atomicAdd(g.gs, gs_local);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -557,9 +803,9 @@ int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld,
   if ((rc = make_tmap_bf16(&ta, u, n_rows, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tb, v, n_cols, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tbp, v, n_cols, ld, ld, kTileRows / 2))) return rc;
-  PLK_CUDA(cudaMemsetAsync(row_sumexp, 0, sizeof(float) * n_rows, st));
-  PLK_CUDA(cudaMemsetAsync(col_sumexp, 0, sizeof(float) * n_cols, st));
-  PLK_CUDA(cudaMemsetAsync(diag, 0, sizeof(float) * n_rows, st));
+  // sums are accumulated with atomics -> zero first; diag needs no init (every owned row has its
+  // diagonal column inside its bucket, so it is always written)
+  if ((rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
   const int nseg = pick_segments(row_blocks, max_tiles, 1);
   const int tps = (int)ceil_div(max_tiles, nseg);
@@ -578,30 +824,87 @@ int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld,
 }
 
 template <int KD, int DNC, int CS>
-static int launch_grad(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
-                       int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tps,
-                       const float* ls, const float* rs, const float* cs, float* acc, float* gs,
-                       cudaStream_t st) {
+static int launch_grad(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                       int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st) {
   auto kern = infonce_grad_tc<KD, DNC, CS>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GradCfg<KD, DNC>::kSmem));
     configured = true;
   }
-  int rc = launch_kernel(kern, grid, dim3(kNumThreads), GradCfg<KD, DNC>::kSmem, st, CS, ta, tb, tbp, n_rows,
-                         row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs);
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), GradCfg<KD, DNC>::kSmem, st, CS, ga, n_rows, row_offset,
+                         n_cols, d, bs, tps, ls);
   if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
 
-// number of partial accumulators plk_infonce_grad writes for this shape (bf16 path)
-int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs) {
+template <int KD, int CS>
+static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st) {
+  auto kern = infonce_grad_tc2<KD, CS>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad2Cfg<KD>::kSmem));
+    configured = true;
+  }
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), Grad2Cfg<KD>::kSmem, st, CS, ga, n_rows, row_offset,
+                         n_cols, d, bs, tps, ls);
+  if (rc) return rc;
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+// number of partial accumulators per direction for this shape (bf16 path); ndir = 1 or 2 directions per launch
+int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir) {
   const int64_t ld = ceil_div(d, kChunkK) * kChunkK;
-  const int z = ld > 256 ? 2 : 1;
+  const int z = (ld > 256 ? 2 : 1) * ndir;
   const int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
   return pick_segments(row_blocks, max_tiles, z);
+}
+
+static int fill_dir(GradDir& g, const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
+                    int64_t n_cols, const float* rs, const float* cs, float* acc, float* gs) {
+  int rc;
+  if ((rc = make_tmap_bf16(&g.ta, a, n_rows, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&g.tb, b, n_cols, ld, ld, kTileRows))) return rc;
+  if ((rc = make_tmap_bf16(&g.tbp, b, n_cols, ld, ld, kTileRows / 2))) return rc;
+  g.rs = rs; g.cs = cs; g.acc = acc; g.gs = gs;
+  return PLK_OK;
+}
+
+static int grad_launch_bf16(const GradArgs& ga, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                            int64_t d, int64_t bs, const float* ls, cudaStream_t st) {
+  int64_t row_blocks = ceil_div(n_rows, kTileRows);
+  const int csz = pick_cluster(row_blocks, bs, n_cols);
+  const int kd = (int)(ld / kChunkK);
+  const int z = (kd > 4 ? 2 : 1) * ga.ndir;
+  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
+  const int nseg = pick_segments(row_blocks, max_tiles, z);
+  const int tps = (int)ceil_div(max_tiles, nseg);
+  row_blocks = ceil_div(row_blocks, csz) * csz;
+  dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
+  if (kd <= 4) {   // the streamed tile fits next to the resident rows: tile-buffer kernel, G in TMEM
+    switch (kd) {
+#define PLK_CASE2(KD)                                                                                   \
+  case KD:                                                                                              \
+    return csz == 2 ? launch_grad2<KD, 2>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st)     \
+                    : launch_grad2<KD, 1>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
+      PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
+#undef PLK_CASE2
+    }
+  }
+  switch (kd) {
+#define PLK_CASE(KD, DNC)                                                                               \
+  case KD:                                                                                              \
+    return csz == 2 ? launch_grad<KD, DNC, 2>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st) \
+                    : launch_grad<KD, DNC, 1>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
+    PLK_CASE(5, 3) PLK_CASE(6, 3) PLK_CASE(7, 4) PLK_CASE(8, 4)
+#undef PLK_CASE
+  }
+  set_error("unsupported padded width %lld", (long long)ld);
+  return PLK_ERR_UNSUPPORTED;
 }
 
 int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
@@ -609,30 +912,25 @@ int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld
                       const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st) {
   int rc = check_tc_shape(ld, d);
   if (rc) return rc;
-  int64_t row_blocks = ceil_div(n_rows, kTileRows);
-  const int csz = pick_cluster(row_blocks, bs, n_cols);
-  CUtensorMap ta, tb, tbp;
-  if ((rc = make_tmap_bf16(&ta, a, n_rows, ld, ld, kTileRows))) return rc;
-  if ((rc = make_tmap_bf16(&tb, b, n_cols, ld, ld, kTileRows))) return rc;
-  if ((rc = make_tmap_bf16(&tbp, b, n_cols, ld, ld, kTileRows / 2))) return rc;
-  if (gs) PLK_CUDA(cudaMemsetAsync(gs, 0, sizeof(float), st));
-  const int kd = (int)(ld / kChunkK);
-  const int z = kd > 4 ? 2 : 1;
-  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
-  const int nseg = pick_segments(row_blocks, max_tiles, z);
-  const int tps = (int)ceil_div(max_tiles, nseg);
-  row_blocks = ceil_div(row_blocks, csz) * csz;
-  dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
-  switch (kd) {
-#define PLK_CASE(KD, DNC)                                                                                     \
-  case KD:                                                                                                    \
-    return csz == 2 ? launch_grad<KD, DNC, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs, st) \
-                    : launch_grad<KD, DNC, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, rs, cs, acc, gs, st);
-    PLK_CASE(1, 1) PLK_CASE(2, 2) PLK_CASE(3, 3) PLK_CASE(4, 4) PLK_CASE(5, 3) PLK_CASE(6, 3) PLK_CASE(7, 4) PLK_CASE(8, 4)
-#undef PLK_CASE
-  }
-  set_error("unsupported padded width %lld", (long long)ld);
-  return PLK_ERR_UNSUPPORTED;
+  GradArgs ga;
+  ga.ndir = 1;
+  if ((rc = fill_dir(ga.dir[0], a, b, ld, n_rows, n_cols, rs, cs, acc, gs))) return rc;
+  ga.dir[1] = ga.dir[0];
+  return grad_launch_bf16(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
+}
+
+int infonce_grad_pair_bf16(const __nv_bfloat16* a0, const __nv_bfloat16* b0, const __nv_bfloat16* a1,
+                           const __nv_bfloat16* b1, int64_t ld, int64_t n_rows, int64_t row_offset,
+                           int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs0,
+                           const float* cs0, const float* rs1, const float* cs1, float* acc0, float* acc1,
+                           float* gs, cudaStream_t st) {
+  int rc = check_tc_shape(ld, d);
+  if (rc) return rc;
+  GradArgs ga;
+  ga.ndir = 2;
+  if ((rc = fill_dir(ga.dir[0], a0, b0, ld, n_rows, n_cols, rs0, cs0, acc0, gs))) return rc;
+  if ((rc = fill_dir(ga.dir[1], a1, b1, ld, n_rows, n_cols, rs1, cs1, acc1, nullptr))) return rc;
+  return grad_launch_bf16(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
 }
 
 }  // namespace plk

@@ -153,6 +153,20 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uin
       "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (bf16, K-major, two K elements per 32-bit column,
+// row m in TMEM lane m) is read straight from tensor memory -- used for G . V in the backward,
+// where G was just produced from the logits tile by the epilogue warps (tcgen05.st).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(0x40004040u /* kUmmaDescHi */), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -179,6 +193,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns, registers -> TMEM (thread t writes lane base_lane + t)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]),
+        "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -232,6 +271,18 @@ __device__ __forceinline__ void ring_load(uint8_t* slot, const CUtensorMap* tm_f
                                           const CUtensorMap* tm_part, uint64_t* full_bar, int c0,
                                           int row0, uint32_t cta_rank) {
   mbar_expect_tx(full_bar, kChunkBytes);
+  if constexpr (CS == 1) {
+    tma_load_2d(slot, tm_full, full_bar, c0, row0);
+  } else {
+    tma_load_2d_mc(slot + cta_rank * (kChunkBytes / CS), tm_part, full_bar, c0,
+                   row0 + (int)cta_rank * (kTileRows / CS), (uint16_t)((1u << CS) - 1));
+  }
+}
+// one chunk of a multi-chunk transaction (the caller armed `full_bar` with the total byte count)
+template <int CS>
+__device__ __forceinline__ void chunk_load(uint8_t* slot, const CUtensorMap* tm_full,
+                                           const CUtensorMap* tm_part, uint64_t* full_bar, int c0,
+                                           int row0, uint32_t cta_rank) {
   if constexpr (CS == 1) {
     tma_load_2d(slot, tm_full, full_bar, c0, row0);
   } else {

@@ -63,29 +63,30 @@ class _ShardedClipLoss(torch.autograd.Function):
             dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
             rs_all = _all_gather_rows(rs, group)
         off = loc_off
-        loss, diag_sum = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
+        loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-        ctx.save_for_backward(x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, diag_sum)
+        ctx.save_for_backward(x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux)
         ctx.meta = (n, d, B, bs, off, mode, group, grad_scale, image_emb.dtype, profile_emb.dtype,
                     logit_scale.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, diag_sum = ctx.saved_tensors
+        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux = ctx.saved_tensors
         n, d, B, bs, off, mode, group, grad_scale, dt_x, dt_y, dt_ls = ctx.meta
         R, _ = _world(group)
         go = g.detach().float().reshape(1).contiguous()
         rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
-        acc_x, gs = ops.infonce_grad_local(u, v_all, mode, d, off, bs, ls, rs_own, cs_all, True)
-        acc_y, _ = ops.infonce_grad_local(v, u_all, mode, d, off, bs, ls, cs_own, rs_all, False)
+        gs = aux[1:].clone()
+        acc_x, acc_y = ops.infonce_grad_pair_local(u, v_all, v, u_all, mode, d, off, bs, ls, rs_own, cs_all,
+                                                   cs_own, rs_all, gs)
         # grad_scale == "ddp": DistributedDataParallel AVERAGES parameter gradients over ranks, while
         # each rank holds the exact d(global loss)/d(local rows); pre-multiplying by the world size
         # makes the averaged encoder gradients equal the true global-batch gradients.
         go_emb = go * R if grad_scale == "ddp" else go
         dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs_own, cs_own, ls, go_emb, B, dt_x)
         dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs_own, cs_own, ls, go_emb, B, dt_y)
-        dls = ops.infonce_dls(gs, diag_sum, go, B)
+        dls = ops.infonce_dls(gs, aux[0:1], go, B)
         dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
         return dx, dy, dls.to(dt_ls), None, None, None, None
 

@@ -65,30 +65,49 @@ def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale, rs=No
 
 
 def infonce_loss_local(rs, cs_own, dg, logit_scale, batch_global):
-    """-> (loss partial over the owned rows [] , sum of the owned diagonal logits [1])"""
+    """-> (loss partial over the owned rows [], aux [2] = (sum of the owned diagonal logits, 0.0)).
+    aux[1] is the zero-initialised accumulator the backward adds sum G*S into (`gs`)."""
     lib = _lib.load()
     loss = torch.empty((), device=rs.device, dtype=torch.float32)
-    diag_sum = torch.empty(1, device=rs.device, dtype=torch.float32)
+    aux = torch.empty(2, device=rs.device, dtype=torch.float32)
     with torch.cuda.device(rs.device):
         lib.check(lib.plk_infonce_loss(rs.data_ptr(), cs_own.data_ptr(), dg.data_ptr(), logit_scale.data_ptr(),
-                                       rs.shape[0], batch_global, loss.data_ptr(), diag_sum.data_ptr(),
-                                       _stream(rs)), "plk_infonce_loss")
-    return loss, diag_sum
+                                       rs.shape[0], batch_global, loss.data_ptr(), aux.data_ptr(),
+                                       aux[1:].data_ptr(), _stream(rs)), "plk_infonce_loss")
+    return loss, aux
 
 
-def infonce_grad_local(a, b, mode, d, row_offset, bucket_size, logit_scale, rs, cs, want_gs):
-    """One direction of the recompute backward -> (acc [parts, n_rows, d], gs [1] or None)"""
+def infonce_grad_local(a, b, mode, d, row_offset, bucket_size, logit_scale, rs, cs, gs=None):
+    """One direction of the recompute backward -> acc [parts, n_rows, d].
+    `gs` (optional fp32 [1], already zeroed or holding a partial sum) is ADDED to."""
     lib = _lib.load()
     n_rows, n_cols = a.shape[0], b.shape[0]
     parts = lib.plk_infonce_grad_parts(mode, n_rows, n_cols, d, bucket_size)
     acc = torch.empty((parts, n_rows, d), device=a.device, dtype=torch.float32)
-    gs = torch.empty(1, device=a.device, dtype=torch.float32) if want_gs else None
     with torch.cuda.device(a.device):
         lib.check(lib.plk_infonce_grad(a.data_ptr(), b.data_ptr(), mode, a.stride(0), n_rows, row_offset, n_cols,
                                        d, bucket_size, logit_scale.data_ptr(), rs.data_ptr(), cs.data_ptr(),
-                                       acc.data_ptr(), gs.data_ptr() if want_gs else None, _stream(a)),
+                                       acc.data_ptr(), gs.data_ptr() if gs is not None else None, _stream(a)),
                   "plk_infonce_grad")
-    return acc, gs
+    return acc
+
+
+def infonce_grad_pair_local(a0, b0, a1, b1, mode, d, row_offset, bucket_size, logit_scale, rs0, cs0, rs1, cs1,
+                            gs=None):
+    """Both directions of the recompute backward in one launch -> (acc0, acc1), each
+    [parts, n_rows, d]; direction 0 adds sum G*S into `gs`."""
+    lib = _lib.load()
+    n_rows, n_cols = a0.shape[0], b0.shape[0]
+    parts = lib.plk_infonce_grad_pair_parts(mode, n_rows, n_cols, d, bucket_size)
+    acc = torch.empty((2, parts, n_rows, d), device=a0.device, dtype=torch.float32)
+    with torch.cuda.device(a0.device):
+        lib.check(lib.plk_infonce_grad_pair(a0.data_ptr(), b0.data_ptr(), a1.data_ptr(), b1.data_ptr(), mode,
+                                            a0.stride(0), n_rows, row_offset, n_cols, d, bucket_size,
+                                            logit_scale.data_ptr(), rs0.data_ptr(), cs0.data_ptr(),
+                                            rs1.data_ptr(), cs1.data_ptr(), acc[0].data_ptr(), acc[1].data_ptr(),
+                                            gs.data_ptr() if gs is not None else None, _stream(a0)),
+                  "plk_infonce_grad_pair")
+    return acc[0], acc[1]
 
 
 def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own, cs_own, logit_scale, grad_out,
@@ -130,7 +149,7 @@ def clip_loss_fwd(image_emb: torch.Tensor, profile_emb: torch.Tensor, logit_scal
                   buckets: int, mode: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor,
                                                     torch.Tensor]:
     """-> (loss [], u [B,ld], v [B,ld], stats [7,B] = (1/den_x, |x|, 1/den_y, |y|, row sum-exp,
-    col sum-exp, diagonal logit), diag_sum [1])"""
+    col sum-exp, diagonal logit), aux [2] = (sum of diagonal logits, zeroed `gs` accumulator))"""
     _require_cuda(image_emb, profile_emb, logit_scale)
     B, d = image_emb.shape
     bs = B // buckets
@@ -140,8 +159,8 @@ def clip_loss_fwd(image_emb: torch.Tensor, profile_emb: torch.Tensor, logit_scal
     u, _, _, _ = l2norm(x, mode, True, stats[0], stats[1])
     v, _, _, _ = l2norm(y, mode, True, stats[2], stats[3])
     infonce_fwd_local(u, v, mode, d, 0, bs, ls, stats[4], stats[5], stats[6])
-    loss, diag_sum = infonce_loss_local(stats[4], stats[5], stats[6], ls, B)
-    return loss, u, v, stats, diag_sum
+    loss, aux = infonce_loss_local(stats[4], stats[5], stats[6], ls, B)
+    return loss, u, v, stats, aux
 
 
 @clip_loss_fwd.register_fake
@@ -151,13 +170,13 @@ def _(image_emb, profile_emb, logit_scale, buckets, mode):
     odt = torch.bfloat16 if mode == PLK_BF16 else torch.float32
     f = image_emb.new_empty
     return (f((), dtype=torch.float32), f((B, ld), dtype=odt), f((B, ld), dtype=odt),
-            f((7, B), dtype=torch.float32), f((1,), dtype=torch.float32))
+            f((7, B), dtype=torch.float32), f((2,), dtype=torch.float32))
 
 
 @torch.library.custom_op("plk::clip_loss_bwd", mutates_args=())
 def clip_loss_bwd(grad_out: torch.Tensor, image_emb: torch.Tensor, profile_emb: torch.Tensor,
                   logit_scale: torch.Tensor, u: torch.Tensor, v: torch.Tensor, stats: torch.Tensor,
-                  diag_sum: torch.Tensor, buckets: int, mode: int) -> tuple[torch.Tensor, torch.Tensor,
+                  aux: torch.Tensor, buckets: int, mode: int) -> tuple[torch.Tensor, torch.Tensor,
                                                                            torch.Tensor]:
     B, d = image_emb.shape
     bs = B // buckets
@@ -165,29 +184,29 @@ def clip_loss_bwd(grad_out: torch.Tensor, image_emb: torch.Tensor, profile_emb: 
     ls = logit_scale.detach().float()
     go = grad_out.detach().float().reshape(1).contiguous()
     idx, nx, idy, ny, rs, cs, dg = stats.unbind(0)
-    acc_x, gs = infonce_grad_local(u, v, mode, d, 0, bs, ls, rs, cs, True)
-    acc_y, _ = infonce_grad_local(v, u, mode, d, 0, bs, ls, cs, rs, False)
+    gs = aux[1:].clone()      # accumulator for sum G*S (aux[1] is 0 from the forward; keep aux reusable)
+    acc_x, acc_y = infonce_grad_pair_local(u, v, v, u, mode, d, 0, bs, ls, rs, cs, cs, rs, gs)
     dx = infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs, cs, ls, go, B, image_emb.dtype)
     dy = infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs, cs, ls, go, B, profile_emb.dtype)
-    dls = infonce_dls(gs, diag_sum, go, B).to(logit_scale.dtype)
+    dls = infonce_dls(gs, aux[0:1], go, B).to(logit_scale.dtype)
     return dx, dy, dls
 
 
 @clip_loss_bwd.register_fake
-def _(grad_out, image_emb, profile_emb, logit_scale, u, v, stats, diag_sum, buckets, mode):
+def _(grad_out, image_emb, profile_emb, logit_scale, u, v, stats, aux, buckets, mode):
     return torch.empty_like(image_emb), torch.empty_like(profile_emb), torch.empty_like(logit_scale)
 
 
 def _setup_ctx(ctx, inputs, output):
     image_emb, profile_emb, logit_scale, buckets, mode = inputs
-    _, u, v, stats, diag_sum = output
-    ctx.save_for_backward(image_emb, profile_emb, logit_scale, u, v, stats, diag_sum)
+    _, u, v, stats, aux = output
+    ctx.save_for_backward(image_emb, profile_emb, logit_scale, u, v, stats, aux)
     ctx.buckets, ctx.mode = buckets, mode
 
 
 def _backward(ctx, g_loss, *_unused):
-    image_emb, profile_emb, logit_scale, u, v, stats, diag_sum = ctx.saved_tensors
-    dx, dy, dls = clip_loss_bwd(g_loss, image_emb, profile_emb, logit_scale, u, v, stats, diag_sum,
+    image_emb, profile_emb, logit_scale, u, v, stats, aux = ctx.saved_tensors
+    dx, dy, dls = clip_loss_bwd(g_loss, image_emb, profile_emb, logit_scale, u, v, stats, aux,
                                 ctx.buckets, ctx.mode)
     return dx, dy, dls, None, None
 
