@@ -102,6 +102,20 @@ class GpuExactIndex:
         return idx.cpu().numpy(), dist.cpu().numpy()
 
 
+def topk_merge_device(cand_i: torch.Tensor, cand_d: torch.Tensor, k: int):
+    """cand [nq, m] (global index, exact distance; -1 = empty) -> the k best per query by
+    (distance, index)   (plk_topk_merge)"""
+    lib = _lib.load()
+    nq, m = cand_i.shape
+    out_i = torch.empty((nq, k), device=cand_i.device, dtype=torch.int32)
+    out_d = torch.empty((nq, k), device=cand_i.device, dtype=torch.float32)
+    with torch.cuda.device(cand_i.device):
+        lib.check(lib.plk_topk_merge(cand_i.data_ptr(), cand_d.data_ptr(), nq, m, k, out_i.data_ptr(),
+                                     out_d.data_ptr(), torch.cuda.current_stream(cand_i.device).cuda_stream),
+                  "plk_topk_merge")
+    return out_i, out_d
+
+
 def knn_vote_device(idx: torch.Tensor, dist: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
     """idx/dist [nq, m] on device, labels int64 [ng] on device -> int64 [nq]   (plk_knn_vote)"""
     lib = _lib.load()

@@ -105,23 +105,16 @@ def sharded_clip_loss(image_emb, profile_emb, logit_scale, buckets: int = 1, mod
 def merge_shard_results(idx: torch.Tensor, dst: torch.Tensor, k: int, group=None):
     """All-gather the per-shard (global index, exact distance) lists [nq, k] and keep the k best per
     query by (distance, index) on the device (plk_topk_merge)."""
-    from . import _lib
-    lib = _lib.load()
+    from . import ann
     R, _ = _world(group)
     nq = idx.shape[0]
-    all_i = torch.empty((R, nq, k), device=idx.device, dtype=torch.int32)
-    all_d = torch.empty((R, nq, k), device=idx.device, dtype=torch.float32)
+    all_i = torch.empty((R * nq, k), device=idx.device, dtype=torch.int32)
+    all_d = torch.empty((R * nq, k), device=idx.device, dtype=torch.float32)
     dist.all_gather_into_tensor(all_i, idx.contiguous(), group=group)
     dist.all_gather_into_tensor(all_d, dst.contiguous(), group=group)
-    cand_i = all_i.permute(1, 0, 2).reshape(nq, R * k).contiguous()
-    cand_d = all_d.permute(1, 0, 2).reshape(nq, R * k).contiguous()
-    out_i = torch.empty((nq, k), device=idx.device, dtype=torch.int32)
-    out_d = torch.empty((nq, k), device=idx.device, dtype=torch.float32)
-    with torch.cuda.device(idx.device):
-        lib.check(lib.plk_topk_merge(cand_i.data_ptr(), cand_d.data_ptr(), nq, R * k, k, out_i.data_ptr(),
-                                     out_d.data_ptr(), torch.cuda.current_stream(idx.device).cuda_stream),
-                  "plk_topk_merge")
-    return out_i, out_d
+    cand_i = all_i.view(R, nq, k).permute(1, 0, 2).reshape(nq, R * k).contiguous()
+    cand_d = all_d.view(R, nq, k).permute(1, 0, 2).reshape(nq, R * k).contiguous()
+    return ann.topk_merge_device(cand_i, cand_d, k)
 
 
 class ShardedANNClassifier:
@@ -129,7 +122,7 @@ class ShardedANNClassifier:
     are replicated.  Global gallery index = rank-ordered concatenation of the shards."""
 
     def __init__(self, X, y, group=None, **nndescent_args):
-        from .ann import GpuExactIndex
+        from . import ann
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("ShardedANNClassifier needs an initialised torch.distributed process group")
         self.group = group
@@ -143,7 +136,7 @@ class ShardedANNClassifier:
         self.counts = counts.cpu().tolist()
         self.offset = int(sum(self.counts[:r]))
         self.total = int(sum(self.counts))
-        self.index = GpuExactIndex(X, precision=precision, device=dev, gallery_offset=self.offset)
+        self.index = ann.GpuExactIndex(X, precision=precision, device=dev, gallery_offset=self.offset)
         labels = torch.zeros(self.total, dtype=torch.int64, device=dev)
         labels[self.offset:self.offset + len(X)] = torch.from_numpy(np.asarray(y).astype(np.int64)).to(dev)
         dist.all_reduce(labels, group=group)
@@ -169,10 +162,10 @@ class ShardedANNClassifier:
         return tuple(out)
 
     def predict(self, *X, **query_args):
-        from .ann import knn_vote_device
+        from . import ann
         k = min(int(query_args.get("k", 10)), self.total)
         lists = [self.search_device(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.index.device), k)
                  for x in X]
         idx = torch.cat([p[0] for p in lists], dim=1).contiguous()
         dst = torch.cat([p[1] for p in lists], dim=1).contiguous()
-        return knn_vote_device(idx, dst, self._labels_dev).cpu().numpy().astype(int).ravel()
+        return ann.knn_vote_device(idx, dst, self._labels_dev).cpu().numpy().astype(int).ravel()
