@@ -73,7 +73,8 @@ int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx
  *   S_ij = exp(*logit_scale) * u_i . v_j, restricted to j in the bucket of global row i
  *          (bucket b = global_i / bucket_size, columns [b*bs, (b+1)*bs)).
  *   Fixed shift: because |u.v| <= 1, E_ij = exp(S_ij - s) never overflows, so ONE exp
- *   serves the row and the column sums (valid for s = exp(logit_scale) <= 64).
+ *   serves the row and the column sums.  E underflows only when s*(1 - cos) > 87, so the sums are
+ *   exact for any data while s = exp(logit_scale) <= 43.
  *
  *   row_sumexp [n_rows]  OUT  sum_j E_ij                (complete)
  *   col_sumexp [n_cols]  OUT  sum_{i owned} E_ij        (partial when rows are sharded)

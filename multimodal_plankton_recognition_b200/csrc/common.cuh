@@ -14,7 +14,6 @@ void count_launch(int n = 1);
 
 constexpr float kNormEps = 1e-12f;   // F.normalize eps, reference src/coordination.py:33-34
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kMaxScale = 64.0f;   // fixed-shift validity bound on s = exp(logit_scale)
 
 #define PLK_CUDA(expr)                                                                   \
   do {                                                                                   \
