@@ -35,59 +35,72 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
+def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group):
+    """Forward of the row-block sharded loss without autograd: -> (global loss [], saved state).
+    Pure stream-ordered work (kernels + NCCL), so it can be captured in a CUDA graph."""
+    R, r = _world(group)
+    n, d = image_emb.shape
+    B = n * R
+    assert B % buckets == 0, "Batch size must be divisible by number of buckets!"
+    bs = B // buckets
+    off = r * n
+    x, y = ops._as_f32_rows(image_emb), ops._as_f32_rows(profile_emb)
+    ls = logit_scale.detach().float()
+    u, idx, nx, _ = ops.l2norm(x, mode)
+    v, idy, ny, _ = ops.l2norm(y, mode)
+    if n % bs == 0:
+        # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange,
+        # the local problem is complete; only the scalars are reduced.
+        u_all, v_all, off = u, v, 0
+        rs, cs_all, dg = ops.infonce_fwd_local(u, v, mode, d, 0, bs, ls)
+        rs_all = rs
+    else:
+        u_all = _all_gather_rows(u, group)
+        v_all = _all_gather_rows(v, group)
+        rs, cs_all, dg = ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls)
+        dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
+        rs_all = _all_gather_rows(rs, group)
+    loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
+    dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux,
+             (n, d, B, bs, off, mode, group))
+    return loss, state
+
+
+def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, torch.float32)):
+    """Backward of `sharded_fwd`: -> (d image_emb [n,d], d profile_emb [n,d], d logit_scale [])."""
+    x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, meta = state
+    n, d, B, bs, off, mode, group = meta
+    R, _ = _world(group)
+    go = grad_out.detach().float().reshape(1).contiguous()
+    rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
+    gs = aux[1:].clone()
+    acc_x, acc_y = ops.infonce_grad_pair_local(u, v_all, v, u_all, mode, d, off, bs, ls, rs_own, cs_all,
+                                               cs_own, rs_all, gs)
+    # grad_scale == "ddp": DistributedDataParallel AVERAGES parameter gradients over ranks, while
+    # each rank holds the exact d(global loss)/d(local rows); pre-multiplying by the world size
+    # makes the averaged encoder gradients equal the true global-batch gradients.
+    go_emb = go * R if grad_scale == "ddp" else go
+    dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[0])
+    dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[1])
+    dls = ops.infonce_dls(gs, aux[0:1], go, B)
+    dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
+    return dx, dy, dls
+
+
 class _ShardedClipLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, image_emb, profile_emb, logit_scale, buckets, mode, group, grad_scale):
-        R, r = _world(group)
-        n, d = image_emb.shape
-        B = n * R
-        assert B % buckets == 0, "Batch size must be divisible by number of buckets!"
-        bs = B // buckets
-        off = r * n
-        x, y = ops._as_f32_rows(image_emb), ops._as_f32_rows(profile_emb)
-        ls = logit_scale.detach().float()
-        u, idx, nx, _ = ops.l2norm(x, mode)
-        v, idy, ny, _ = ops.l2norm(y, mode)
-        if n % bs == 0:
-            # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange,
-            # the local problem is complete; only the scalars are reduced.
-            u_all, v_all, loc_off = u, v, 0
-            rs, cs_all, dg = ops.infonce_fwd_local(u, v, mode, d, 0, bs, ls)
-            rs_all = rs
-        else:
-            loc_off = off
-            u_all = _all_gather_rows(u, group)
-            v_all = _all_gather_rows(v, group)
-            rs, cs_all, dg = ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls)
-            dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
-            rs_all = _all_gather_rows(rs, group)
-        off = loc_off
-        loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-        ctx.save_for_backward(x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux)
-        ctx.meta = (n, d, B, bs, off, mode, group, grad_scale, image_emb.dtype, profile_emb.dtype,
-                    logit_scale.dtype)
+        loss, state = sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group)
+        ctx.save_for_backward(*state[:-1])
+        ctx.meta = (state[-1], grad_scale, image_emb.dtype, profile_emb.dtype, logit_scale.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux = ctx.saved_tensors
-        n, d, B, bs, off, mode, group, grad_scale, dt_x, dt_y, dt_ls = ctx.meta
-        R, _ = _world(group)
-        go = g.detach().float().reshape(1).contiguous()
-        rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
-        gs = aux[1:].clone()
-        acc_x, acc_y = ops.infonce_grad_pair_local(u, v_all, v, u_all, mode, d, off, bs, ls, rs_own, cs_all,
-                                                   cs_own, rs_all, gs)
-        # grad_scale == "ddp": DistributedDataParallel AVERAGES parameter gradients over ranks, while
-        # each rank holds the exact d(global loss)/d(local rows); pre-multiplying by the world size
-        # makes the averaged encoder gradients equal the true global-batch gradients.
-        go_emb = go * R if grad_scale == "ddp" else go
-        dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs_own, cs_own, ls, go_emb, B, dt_x)
-        dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs_own, cs_own, ls, go_emb, B, dt_y)
-        dls = ops.infonce_dls(gs, aux[0:1], go, B)
-        dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
+        meta, grad_scale, dt_x, dt_y, dt_ls = ctx.meta
+        dx, dy, dls = sharded_bwd(tuple(ctx.saved_tensors) + (meta,), g, grad_scale, (dt_x, dt_y))
         return dx, dy, dls.to(dt_ls), None, None, None, None
 
 
