@@ -35,9 +35,10 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
-def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group):
+def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduce_scalars=True):
     """Forward of the row-block sharded loss without autograd: -> (global loss [], saved state).
-    Pure stream-ordered work (kernels + NCCL), so it can be captured in a CUDA graph."""
+    With reduce_scalars=False the returned loss is this rank's partial sum (the caller all-reduces
+    it); in the bucket-aligned case the call then contains no collective at all."""
     R, r = _world(group)
     n, d = image_emb.shape
     B = n * R
@@ -61,14 +62,17 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group):
         dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
         rs_all = _all_gather_rows(rs, group)
     loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
-    dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    if reduce_scalars:
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux,
              (n, d, B, bs, off, mode, group))
     return loss, state
 
 
-def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, torch.float32)):
-    """Backward of `sharded_fwd`: -> (d image_emb [n,d], d profile_emb [n,d], d logit_scale [])."""
+def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, torch.float32),
+                reduce_scalars=True):
+    """Backward of `sharded_fwd`: -> (d image_emb [n,d], d profile_emb [n,d], d logit_scale []).
+    With reduce_scalars=False d logit_scale is this rank's partial (the caller all-reduces it)."""
     x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, meta = state
     n, d, B, bs, off, mode, group = meta
     R, _ = _world(group)
@@ -84,7 +88,8 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
     dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[0])
     dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[1])
     dls = ops.infonce_dls(gs, aux[0:1], go, B)
-    dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
+    if reduce_scalars:
+        dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
     return dx, dy, dls
 
 
