@@ -61,10 +61,11 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
         rs, cs_all, dg = ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls)
         dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
         rs_all = _all_gather_rows(rs, group)
-    loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B)
+    scal = torch.empty(2, device=x.device, dtype=torch.float32)   # (loss, d logit_scale) partials side by side
+    loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B, scal[0])
     if reduce_scalars:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-    state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux,
+    state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal,
              (n, d, B, bs, off, mode, group))
     return loss, state
 
@@ -73,7 +74,7 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
                 reduce_scalars=True):
     """Backward of `sharded_fwd`: -> (d image_emb [n,d], d profile_emb [n,d], d logit_scale []).
     With reduce_scalars=False d logit_scale is this rank's partial (the caller all-reduces it)."""
-    x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, meta = state
+    x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal, meta = state
     n, d, B, bs, off, mode, group = meta
     R, _ = _world(group)
     go = grad_out.detach().float().reshape(1).contiguous()
@@ -87,7 +88,7 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
     go_emb = go * R if grad_scale == "ddp" else go
     dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[0])
     dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[1])
-    dls = ops.infonce_dls(gs, aux[0:1], go, B)
+    dls = ops.infonce_dls(gs, aux[0:1], go, B, scal[1] if not reduce_scalars else None)
     if reduce_scalars:
         dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
     return dx, dy, dls

@@ -64,11 +64,11 @@ def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale, rs=No
     return rs, cs, dg
 
 
-def infonce_loss_local(rs, cs_own, dg, logit_scale, batch_global):
+def infonce_loss_local(rs, cs_own, dg, logit_scale, batch_global, loss_out=None):
     """-> (loss partial over the owned rows [], aux [2] = (sum of the owned diagonal logits, 0.0)).
     aux[1] is the zero-initialised accumulator the backward adds sum G*S into (`gs`)."""
     lib = _lib.load()
-    loss = torch.empty((), device=rs.device, dtype=torch.float32)
+    loss = torch.empty((), device=rs.device, dtype=torch.float32) if loss_out is None else loss_out
     aux = torch.empty(2, device=rs.device, dtype=torch.float32)
     with torch.cuda.device(rs.device):
         lib.check(lib.plk_infonce_loss(rs.data_ptr(), cs_own.data_ptr(), dg.data_ptr(), logit_scale.data_ptr(),
@@ -125,9 +125,9 @@ def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own
     return dx
 
 
-def infonce_dls(gs, diag_sum, grad_out, batch_global):
+def infonce_dls(gs, diag_sum, grad_out, batch_global, out=None):
     lib = _lib.load()
-    out = torch.empty((), device=gs.device, dtype=torch.float32)
+    out = torch.empty((), device=gs.device, dtype=torch.float32) if out is None else out
     with torch.cuda.device(gs.device):
         lib.check(lib.plk_infonce_dls(gs.data_ptr(), diag_sum.data_ptr(), grad_out.data_ptr(), batch_global,
                                       out.data_ptr(), _stream(gs)), "plk_infonce_dls")

@@ -38,10 +38,13 @@ def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, ls, rs=None, cs=No
     return E.sum(1).float(), E.sum(0).float(), S[torch.arange(n), torch.arange(n) + row_offset].float()
 
 
-def infonce_loss_local(rs, cs_own, dg, ls, batch_global):
+def infonce_loss_local(rs, cs_own, dg, ls, batch_global, loss_out=None):
     s = float(torch.exp(ls.double()))
-    loss = (2 * s + rs.double().log() + cs_own.double().log() - 2 * dg.double()).sum() / (2 * batch_global)
-    return loss.float(), torch.tensor([float(dg.double().sum()), 0.0])
+    loss = ((2 * s + rs.double().log() + cs_own.double().log() - 2 * dg.double()).sum() / (2 * batch_global)).float()
+    if loss_out is not None:
+        loss_out.copy_(loss)
+        loss = loss_out
+    return loss, torch.tensor([float(dg.double().sum()), 0.0])
 
 
 def infonce_grad_pair_local(a0, b0, a1, b1, mode, d, off, bs, ls, rs0, cs0, rs1, cs1, gs=None):
@@ -70,8 +73,12 @@ def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own
     return ((dU - u * dot) * inv_den_x.double()[:, None]).to(out_dtype)
 
 
-def infonce_dls(gs, diag_sum, go, batch_global):
-    return (go.double() / (2 * batch_global) * (gs.double() - 2 * diag_sum.double())).float().reshape(())
+def infonce_dls(gs, diag_sum, go, batch_global, out=None):
+    val = (go.double() / (2 * batch_global) * (gs.double() - 2 * diag_sum.double())).float().reshape(())
+    if out is not None:
+        out.copy_(val)
+        return out
+    return val
 
 
 class CpuExactIndex:
