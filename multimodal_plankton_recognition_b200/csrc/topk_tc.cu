@@ -218,16 +218,22 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
 }
 
 static int topk_bf16_chunks(int64_t nq, int64_t ng) {
-  const int64_t qblocks = ceil_div(nq, kTileRows);
+  // (query-block pairs x gallery chunks) clusters run in waves of 74 (148 SMs / cluster of 2).
+  // Pick the chunk count (chunks of >= 64 tiles: every chunk restarts the per-thread lists, and the
+  // warm-up phase of a list is the slow path) that wastes the least of the last wave.
+  const int64_t clusters = ceil_div(ceil_div(nq, kTileRows), 2);
   const int64_t tiles = ceil_div(ng, kTileRows);
-  // enough (query block, chunk) CTAs for ~4 waves of 148 SMs, but chunks of >= 64 tiles: every
-  // chunk restarts the per-thread lists, and the warm-up phase of a list is the slow path
-  int64_t c = ceil_div(148 * 4, qblocks);
-  const int64_t maxc = tiles / 64 > 0 ? tiles / 64 : 1;
-  if (c > maxc) c = maxc;
-  if (c > 64) c = 64;
-  if (c < 1) c = 1;
-  return (int)c;
+  int64_t maxc = tiles / 64;
+  if (maxc < 1) maxc = 1;
+  if (maxc > 16) maxc = 16;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int64_t c = 1; c <= maxc; ++c) {
+    const int64_t work = clusters * c;
+    const double eff = (double)work / (double)(ceil_div(work, 74) * 74);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = (int)c; }
+  }
+  return best;
 }
 
 size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc) {

@@ -202,9 +202,12 @@ def _setup_ctx(ctx, inputs, output):
     _, u, v, stats, aux = output
     ctx.save_for_backward(image_emb, profile_emb, logit_scale, u, v, stats, aux)
     ctx.buckets, ctx.mode = buckets, mode
+    ctx.set_materialize_grads(False)   # no zero-filled gradients for the auxiliary outputs
 
 
 def _backward(ctx, g_loss, *_unused):
+    if g_loss is None:
+        return None, None, None, None, None
     image_emb, profile_emb, logit_scale, u, v, stats, aux = ctx.saved_tensors
     dx, dy, dls = clip_loss_bwd(g_loss, image_emb, profile_emb, logit_scale, u, v, stats, aux,
                                 ctx.buckets, ctx.mode)

@@ -19,7 +19,7 @@ if kind in ("fwd", "grad"):
     for _ in range(3):
         rs, cs, dg = ops.infonce_fwd_local(u, v, mode, d, 0, B, ls)
         if kind == "grad":
-            acc = ops.infonce_grad_local(u, v, mode, d, 0, B, ls, rs, cs, torch.zeros(1, device="cuda"))
+            acc = ops.infonce_grad_pair_local(u, v, v, u, mode, d, 0, B, ls, rs, cs, cs, rs, torch.zeros(1, device="cuda"))
 else:
     ng = int(sys.argv[4])
     gal, _ = synth.unit_embeddings(ng, d, 5, "cuda", 1)
