@@ -20,6 +20,7 @@
  *   - operand dtype `op_dtype` selects the arithmetic path:
  *       PLK_F32  : fp32 CUDA-core path (parity mode, <=1e-5 rel vs the reference)
  *       PLK_BF16 : tcgen05 bf16 MMA, fp32 TMEM accumulators (<=2e-3 rel)
+ *       PLK_F16  : the same kernels with fp16 operands (unit-norm rows fit fp16; 8x finer rounding)
  *     There is no CPU fallback.
  */
 #ifndef PLK_H_
@@ -52,7 +53,7 @@ int64_t plk_launch_count(void);
 /* ------------------------------------------------------------------------------------------
  * a2. L2 normalisation   u = x / max(||x||_2, 1e-12)            reference src/coordination.py:33-34
  *   x        [n, d]      x_dtype in {F32, BF16, F16}, leading dim ldx
- *   u        [n, ldu]    u_dtype in {F32, BF16}; columns d..ldu-1 are written as zero (the
+ *   u        [n, ldu]    u_dtype in {F32, BF16, F16}; columns d..ldu-1 are written as zero (the
  *                        tcgen05 path wants ldu = d rounded up to 64)
  *   inv_den  [n]  fp32   1 / max(||x||, eps)
  *   nrm      [n]  fp32   ||x||           (needed by the backward to detect the eps clamp)

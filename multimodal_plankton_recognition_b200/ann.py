@@ -66,10 +66,10 @@ class GpuExactIndex:
     def search_device(self, q32: torch.Tensor, k: int):
         lib = self.lib
         nq = q32.shape[0]
-        kmax = 32 if self.mode == PLK_BF16 else 64
+        kmax = 64 if self.mode == PLK_F32 else 32
         if k < 1 or k > kmax:
             raise ValueError(f"k must be in [1, {kmax}] for this precision, got {k}")
-        kc = min(kmax, max(k + self.slack, 16 if self.mode == PLK_BF16 else k + self.slack))
+        kc = min(kmax, max(k + self.slack, k + self.slack if self.mode == PLK_F32 else 16))
         q_op, _, _, _ = ops.l2norm(q32, self.mode, normalise=False)
         dev = self.device
         cand_idx = torch.empty((nq, kc), device=dev, dtype=torch.int32)

@@ -21,8 +21,10 @@ from . import ops
 class CLIPLoss(Module):
     """Symmetric CLIP-style InfoNCE (https://arxiv.org/abs/2103.00020), reference src/coordination.py:17-47.
 
-    ``precision``: "bf16" (tcgen05 tensor-core path, <=2e-3 relative vs the reference) or
-    "fp32" (CUDA-core parity path, <=1e-5 relative).  Default: env ``PLK_PRECISION`` or "bf16".
+    ``precision``: "bf16" (tcgen05 tensor-core path, <=2e-3 relative vs the reference at the
+    reference's temperature), "fp16" (same kernels and speed with fp16 operands -- the reference's own
+    '16-mixed' precision; 8x tighter, <=2e-3 at any temperature) or "fp32" (CUDA-core parity path,
+    <=1e-5 relative).  Default: env ``PLK_PRECISION`` or "bf16".
     ``process_group``: if given (or ``sharded=True`` with the default group), the batch seen by
     ``forward`` is this rank's slice of a global batch and the loss is the global-batch loss
     (`dist.sharded_clip_loss`); the reference has no multi-GPU path, this is new functionality.

@@ -35,8 +35,8 @@ int plk_device_supports_tc(void) {
 static int check_common(const void* a, const void* b, int op_dtype, int64_t ld, int64_t n_rows,
                         int64_t n_cols, int64_t d, int64_t bs) {
   PLK_REQUIRE(a && b, PLK_ERR_INVALID, "null operand pointer");
-  PLK_REQUIRE(op_dtype == PLK_F32 || op_dtype == PLK_BF16, PLK_ERR_INVALID,
-              "op_dtype must be PLK_F32 or PLK_BF16 (got %d)", op_dtype);
+  PLK_REQUIRE(op_dtype == PLK_F32 || op_dtype == PLK_BF16 || op_dtype == PLK_F16, PLK_ERR_INVALID,
+              "op_dtype must be PLK_F32, PLK_BF16 or PLK_F16 (got %d)", op_dtype);
   PLK_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0 && ld >= d, PLK_ERR_INVALID,
               "bad shape n_rows=%lld n_cols=%lld d=%lld ld=%lld", (long long)n_rows,
               (long long)n_cols, (long long)d, (long long)ld);
@@ -58,20 +58,20 @@ int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld, int6
   if (op_dtype == PLK_F32)
     return infonce_fwd_f32((const float*)u, (const float*)v, ld, n_rows, row_offset, n_cols, d,
                            bucket_size, logit_scale, row_sumexp, col_sumexp, diag, st);
-  return infonce_fwd_bf16((const __nv_bfloat16*)u, (const __nv_bfloat16*)v, ld, n_rows, row_offset,
-                          n_cols, d, bucket_size, logit_scale, row_sumexp, col_sumexp, diag, st);
+  return infonce_fwd_tc16(u, v, op_dtype == PLK_F16, ld, n_rows, row_offset, n_cols, d, bucket_size,
+                          logit_scale, row_sumexp, col_sumexp, diag, st);
 }
 
 int plk_infonce_grad_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
                            int64_t bucket_size) {
-  if (op_dtype != PLK_BF16 || n_rows <= 0 || n_cols <= 0 || d <= 0 || bucket_size <= 0) return 1;
-  return grad_parts_bf16(n_rows, n_cols, d, bucket_size, 1);
+  if (op_dtype == PLK_F32 || n_rows <= 0 || n_cols <= 0 || d <= 0 || bucket_size <= 0) return 1;
+  return grad_parts_tc16(n_rows, n_cols, d, bucket_size, 1);
 }
 
 int plk_infonce_grad_pair_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,
                                 int64_t bucket_size) {
-  if (op_dtype != PLK_BF16 || n_rows <= 0 || n_cols <= 0 || d <= 0 || bucket_size <= 0) return 1;
-  return grad_parts_bf16(n_rows, n_cols, d, bucket_size, 2);
+  if (op_dtype == PLK_F32 || n_rows <= 0 || n_cols <= 0 || d <= 0 || bucket_size <= 0) return 1;
+  return grad_parts_tc16(n_rows, n_cols, d, bucket_size, 2);
 }
 
 int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld, int64_t n_rows,
@@ -87,8 +87,8 @@ int plk_infonce_grad(const void* a, const void* b, int op_dtype, int64_t ld, int
   if (op_dtype == PLK_F32)
     return infonce_grad_f32((const float*)a, (const float*)b, ld, n_rows, row_offset, n_cols, d,
                             bucket_size, logit_scale, rs, cs, acc, gs, st);
-  return infonce_grad_bf16((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, ld, n_rows, row_offset,
-                           n_cols, d, bucket_size, logit_scale, rs, cs, acc, gs, st);
+  return infonce_grad_tc16(a, b, op_dtype == PLK_F16, ld, n_rows, row_offset, n_cols, d, bucket_size,
+                           logit_scale, rs, cs, acc, gs, st);
 }
 
 int plk_infonce_grad_pair(const void* a0, const void* b0, const void* a1, const void* b1, int op_dtype,
@@ -109,13 +109,12 @@ int plk_infonce_grad_pair(const void* a0, const void* b0, const void* a1, const 
     return infonce_grad_f32((const float*)a1, (const float*)b1, ld, n_rows, row_offset, n_cols, d, bucket_size,
                             logit_scale, rs1, cs1, acc1, nullptr, st);
   }
-  return infonce_grad_pair_bf16((const __nv_bfloat16*)a0, (const __nv_bfloat16*)b0, (const __nv_bfloat16*)a1,
-                                (const __nv_bfloat16*)b1, ld, n_rows, row_offset, n_cols, d, bucket_size,
-                                logit_scale, rs0, cs0, rs1, cs1, acc0, acc1, gs, st);
+  return infonce_grad_pair_tc16(a0, b0, a1, b1, op_dtype == PLK_F16, ld, n_rows, row_offset, n_cols, d,
+                                bucket_size, logit_scale, rs0, cs0, rs1, cs1, acc0, acc1, gs, st);
 }
 
 size_t plk_topk_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int kc, int op_dtype) {
-  return op_dtype == PLK_BF16 ? topk_ws_bf16(nq, ng, d, kc) : topk_ws_f32(nq, ng, d, kc);
+  return op_dtype == PLK_F32 ? topk_ws_f32(nq, ng, d, kc) : topk_ws_tc16(nq, ng, d, kc);
 }
 
 int plk_topk_candidates(const void* q, const void* g, int op_dtype, int64_t ld, const float* g_sqn,
@@ -123,7 +122,7 @@ int plk_topk_candidates(const void* q, const void* g, int op_dtype, int64_t ld, 
                         int32_t* cand_idx, float* cand_key, void* workspace, size_t workspace_bytes,
                         void* stream) {
   PLK_REQUIRE(q && g && g_sqn && cand_idx && cand_key, PLK_ERR_INVALID, "null pointer");
-  PLK_REQUIRE(op_dtype == PLK_F32 || op_dtype == PLK_BF16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
+  PLK_REQUIRE(op_dtype == PLK_F32 || op_dtype == PLK_BF16 || op_dtype == PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
   PLK_REQUIRE(nq > 0 && ng > 0 && d > 0 && ld >= d, PLK_ERR_INVALID, "bad shape");
   PLK_REQUIRE(kc >= 1 && kc <= 64, PLK_ERR_INVALID, "kc must be in [1,64] (got %d)", kc);
   PLK_REQUIRE(gallery_offset >= 0 && gallery_offset + ng < (int64_t)1 << 31, PLK_ERR_INVALID,
@@ -135,8 +134,8 @@ int plk_topk_candidates(const void* q, const void* g, int op_dtype, int64_t ld, 
   if (op_dtype == PLK_F32)
     return topk_candidates_f32((const float*)q, (const float*)g, ld, g_sqn, nq, ng, d, kc,
                                gallery_offset, cand_idx, cand_key, workspace, workspace_bytes, st);
-  return topk_candidates_bf16((const __nv_bfloat16*)q, (const __nv_bfloat16*)g, ld, g_sqn, nq, ng, d,
-                              kc, gallery_offset, cand_idx, cand_key, workspace, workspace_bytes, st);
+  return topk_candidates_tc16(q, g, op_dtype == PLK_F16, ld, g_sqn, nq, ng, d, kc, gallery_offset, cand_idx,
+                              cand_key, workspace, workspace_bytes, st);
 }
 
 }  // extern "C"

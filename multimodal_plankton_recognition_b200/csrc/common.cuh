@@ -53,23 +53,23 @@ int topk_candidates_f32(const float* q, const float* g, int64_t ld, const float*
                         float* cand_key, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t topk_ws_f32(int64_t nq, int64_t ng, int64_t d, int kc);
 
-int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld, int64_t n_rows,
+// 16-bit tensor-core path: f16 = 0 -> bf16 operands, 1 -> fp16 operands
+int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows,
                      int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
                      float* row_sumexp, float* col_sumexp, float* diag, cudaStream_t st);
-int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
+int infonce_grad_tc16(const void* a, const void* b, int f16, int64_t ld, int64_t n_rows,
                       int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
                       const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st);
-int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir);
-int infonce_grad_pair_bf16(const __nv_bfloat16* a0, const __nv_bfloat16* b0, const __nv_bfloat16* a1,
-                           const __nv_bfloat16* b1, int64_t ld, int64_t n_rows, int64_t row_offset,
-                           int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs0,
-                           const float* cs0, const float* rs1, const float* cs1, float* acc0, float* acc1,
-                           float* gs, cudaStream_t st);
-int topk_candidates_bf16(const __nv_bfloat16* q, const __nv_bfloat16* g, int64_t ld,
-                         const float* g_sqn, int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff,
-                         int32_t* cand_idx, float* cand_key, void* ws, size_t ws_bytes,
-                         cudaStream_t st);
-size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc);
+int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir);
+int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1, const void* b1, int f16,
+                           int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
+                           int64_t bs, const float* ls, const float* rs0, const float* cs0,
+                           const float* rs1, const float* cs1, float* acc0, float* acc1, float* gs,
+                           cudaStream_t st);
+int topk_candidates_tc16(const void* q, const void* g, int f16, int64_t ld, const float* g_sqn,
+                         int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff, int32_t* cand_idx,
+                         float* cand_key, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t topk_ws_tc16(int64_t nq, int64_t ng, int64_t d, int kc);
 int zero2(float* a, int64_t na, float* b, int64_t nb, cudaStream_t st);
 int select_candidates(const int32_t* in_idx, const float* in_key, int64_t nq, int m, int kc,
                       int32_t* out_idx, float* out_key, cudaStream_t st);

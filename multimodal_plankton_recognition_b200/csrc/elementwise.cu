@@ -24,6 +24,9 @@ __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bfloat16* p, f
 template <>
 __device__ __forceinline__ void st_from_float<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
+template <typename T> constexpr bool kIsHalf = false;
+template <> constexpr bool kIsHalf<__half> = true;
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -102,12 +105,18 @@ __global__ void __launch_bounds__(256) l2norm_vec_kernel(const float* __restrict
     if (normalise) { w.x /= den; w.y /= den; w.z /= den; w.w /= den; }
     if constexpr (sizeof(TO) == 4) {
       reinterpret_cast<float4*>(u + row * ldu)[lane + 32 * i] = w;
-    } else {
+    } else if constexpr (sizeof(TO) == 2 && !kIsHalf<TO>) {
       __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
       uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
       reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = pk;
       w.x = __bfloat162float(lo.x); w.y = __bfloat162float(lo.y);
       w.z = __bfloat162float(hi.x); w.w = __bfloat162float(hi.y);
+    } else {
+      __half2 lo = __floats2half2_rn(w.x, w.y), hi = __floats2half2_rn(w.z, w.w);
+      uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = pk;
+      w.x = __half2float(lo.x); w.y = __half2float(lo.y);
+      w.z = __half2float(hi.x); w.w = __half2float(hi.y);
     }
     sq = fmaf(w.x, w.x, fmaf(w.y, w.y, fmaf(w.z, w.z, fmaf(w.w, w.w, sq))));
   }
@@ -140,7 +149,9 @@ static int l2norm_dispatch_out(const TI* x, int64_t n, int64_t d, int64_t ldx, v
   if constexpr (sizeof(TI) == 4) {
     const bool done = u_dtype == PLK_F32
                           ? l2norm_try_vec((const float*)x, n, d, ldx, (float*)u, ldu, inv_den, nrm, sqn, normalise, st)
-                          : l2norm_try_vec((const float*)x, n, d, ldx, (__nv_bfloat16*)u, ldu, inv_den, nrm, sqn, normalise, st);
+                          : u_dtype == PLK_BF16
+                                ? l2norm_try_vec((const float*)x, n, d, ldx, (__nv_bfloat16*)u, ldu, inv_den, nrm, sqn, normalise, st)
+                                : l2norm_try_vec((const float*)x, n, d, ldx, (__half*)u, ldu, inv_den, nrm, sqn, normalise, st);
     if (done) {
       PLK_LAUNCHED(1);
       return PLK_OK;
@@ -148,8 +159,10 @@ static int l2norm_dispatch_out(const TI* x, int64_t n, int64_t d, int64_t ldx, v
   }
   if (u_dtype == PLK_F32)
     l2norm_kernel<TI, float><<<grid, block, 0, st>>>(x, n, d, ldx, (float*)u, ldu, inv_den, nrm, sqn, normalise);
-  else
+  else if (u_dtype == PLK_BF16)
     l2norm_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(x, n, d, ldx, (__nv_bfloat16*)u, ldu, inv_den, nrm, sqn, normalise);
+  else
+    l2norm_kernel<TI, __half><<<grid, block, 0, st>>>(x, n, d, ldx, (__half*)u, ldu, inv_den, nrm, sqn, normalise);
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
@@ -465,7 +478,7 @@ int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx
   PLK_REQUIRE(x && u, PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(n > 0 && d > 0 && ldx >= d && ldu >= d, PLK_ERR_INVALID, "bad shape n=%lld d=%lld ldx=%lld ldu=%lld",
               (long long)n, (long long)d, (long long)ldx, (long long)ldu);
-  PLK_REQUIRE(u_dtype == PLK_F32 || u_dtype == PLK_BF16, PLK_ERR_INVALID, "u_dtype must be F32 or BF16");
+  PLK_REQUIRE(u_dtype == PLK_F32 || u_dtype == PLK_BF16 || u_dtype == PLK_F16, PLK_ERR_INVALID, "u_dtype must be F32, BF16 or F16");
   cudaStream_t st = (cudaStream_t)stream;
   switch (x_dtype) {
     case PLK_F32: return l2norm_dispatch_out((const float*)x, n, d, ldx, u, u_dtype, ldu, inv_den, nrm, sqn, normalise, st);

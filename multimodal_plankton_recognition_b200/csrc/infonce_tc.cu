@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_bp, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tiles_per_seg,
     const float* __restrict__ ls, float* __restrict__ row_sumexp, float* __restrict__ col_sumexp,
-    float* __restrict__ diag) {
+    float* __restrict__ diag, int f16) {
   using Cfg = FwdCfg<KD>;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
       mbar_wait(bar_a, 0);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
@@ -248,7 +248,7 @@ struct GradCfg {
   static_assert(DNC >= 1 && DNC <= 4, "at most 256 accumulator columns per CTA");
 };
 
-template <int KD, int DNC, int CS>
+template <int KD, int DNC, int CS, bool F16>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, int tiles_per_seg,
     const float* __restrict__ ls) {
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, 64, 0, 1);  // B = streamed chunk, MN-major
+      constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
+      constexpr uint32_t idesc_g = umma_idesc_16(128, 64, 0, 1, F16);  // B = streamed chunk, MN-major
       mbar_wait(bar_a, 0);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
@@ -441,8 +441,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
           // softmax and nearly cancels against the -2*delta term): drop it from the bf16 operand
           g[x] = (e == dei) ? 0.f : G;
         }
-        packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
-        packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
+        packed[e4 * 2] = pack_16x2<F16>(g[0], g[1]);
+        packed[e4 * 2 + 1] = pack_16x2<F16>(g[2], g[3]);
       }
       mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
       // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
@@ -516,7 +516,7 @@ struct Grad2Cfg {
   static_assert(kSmem <= kMaxSmem, "tile-buffer backward needs d <= 256");
 };
 
-template <int KD, int CS>
+template <int KD, int CS, bool F16>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
     int64_t d, int64_t bs, int tiles_per_seg, const float* __restrict__ ls) {
@@ -594,8 +594,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DN, 0, 1);   // A from TMEM (K-major), B MN-major
+      constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
+      constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A from TMEM (K-major), B MN-major
       mbar_wait(bar_a, 0);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
       const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);               // K-major view (S)
@@ -694,8 +694,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
           if (want_gs) gs_local = fmaf(G, a, gs_local);
           g[x] = (e == dei) ? 0.f : G;   // the j == i term is added in fp32 by plk_infonce_grad_finish
         }
-        packed[e4 * 2] = pack_bf16x2(g[0], g[1]);
-        packed[e4 * 2 + 1] = pack_bf16x2(g[2], g[3]);
+        packed[e4 * 2] = pack_16x2<F16>(g[0], g[1]);
+        packed[e4 * 2 + 1] = pack_16x2<F16>(g[2], g[3]);
       }
       // G overwrites the first 16 of this warp's own 32 logits columns (all 32 were read above)
       tmem_st16(col0, packed);
@@ -762,10 +762,10 @@ static int pick_segments(int64_t row_blocks, int64_t max_tiles, int z) {
 
 static int check_tc_shape(int64_t ld, int64_t d) {
   PLK_REQUIRE(ld % kChunkK == 0 && ld >= d && ld - d < kChunkK, PLK_ERR_INVALID,
-              "bf16 operands must be zero-padded to ld = ceil(d/64)*64 (d=%lld ld=%lld)", (long long)d,
+              "16-bit operands must be zero-padded to ld = ceil(d/64)*64 (d=%lld ld=%lld)", (long long)d,
               (long long)ld);
-  PLK_REQUIRE(ld <= 512, PLK_ERR_UNSUPPORTED, "bf16 path supports d <= 512 (got %lld)", (long long)d);
-  PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the bf16 path needs an sm_100 device");
+  PLK_REQUIRE(ld <= 512, PLK_ERR_UNSUPPORTED, "tensor-core path supports d <= 512 (got %lld)", (long long)d);
+  PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the tensor-core path needs an sm_100 device");
   return PLK_OK;
 }
 
@@ -778,7 +778,7 @@ static int pick_cluster(int64_t row_blocks, int64_t bs, int64_t n_cols) {
 template <int KD, int CS>
 static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
                       int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tps,
-                      const float* ls, float* rsum, float* csum, float* diag, cudaStream_t st) {
+                      const float* ls, float* rsum, float* csum, float* diag, int f16, cudaStream_t st) {
   auto kern = infonce_fwd_tc<KD, CS>;
   static bool configured = false;
   if (!configured) {
@@ -786,13 +786,13 @@ static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     configured = true;
   }
   int rc = launch_kernel(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, ta, tb, tbp, n_rows,
-                         row_offset, n_cols, bs, tps, ls, rsum, csum, diag);
+                         row_offset, n_cols, bs, tps, ls, rsum, csum, diag, f16);
   if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
 
-int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld, int64_t n_rows,
+int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows,
                      int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
                      float* row_sumexp, float* col_sumexp, float* diag, cudaStream_t st) {
   int rc = check_tc_shape(ld, d);
@@ -814,8 +814,8 @@ int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld,
   switch (ld / kChunkK) {
 #define PLK_CASE(KD)                                                                                         \
   case KD:                                                                                                   \
-    return cs == 2 ? launch_fwd<KD, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, st) \
-                   : launch_fwd<KD, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, st);
+    return cs == 2 ? launch_fwd<KD, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st) \
+                   : launch_fwd<KD, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st);
     PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
   }
@@ -823,10 +823,10 @@ int infonce_fwd_bf16(const __nv_bfloat16* u, const __nv_bfloat16* v, int64_t ld,
   return PLK_ERR_UNSUPPORTED;
 }
 
-template <int KD, int DNC, int CS>
+template <int KD, int DNC, int CS, bool F16>
 static int launch_grad(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st) {
-  auto kern = infonce_grad_tc<KD, DNC, CS>;
+  auto kern = infonce_grad_tc<KD, DNC, CS, F16>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GradCfg<KD, DNC>::kSmem));
@@ -839,10 +839,10 @@ static int launch_grad(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t ro
   return PLK_OK;
 }
 
-template <int KD, int CS>
+template <int KD, int CS, bool F16>
 static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
                         int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st) {
-  auto kern = infonce_grad_tc2<KD, CS>;
+  auto kern = infonce_grad_tc2<KD, CS, F16>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad2Cfg<KD>::kSmem));
@@ -856,7 +856,7 @@ static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
 }
 
 // number of partial accumulators per direction for this shape (bf16 path); ndir = 1 or 2 directions per launch
-int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir) {
+int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir) {
   const int64_t ld = ceil_div(d, kChunkK) * kChunkK;
   const int z = (ld > 256 ? 2 : 1) * ndir;
   const int64_t row_blocks = ceil_div(n_rows, kTileRows);
@@ -864,7 +864,7 @@ int grad_parts_bf16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int n
   return pick_segments(row_blocks, max_tiles, z);
 }
 
-static int fill_dir(GradDir& g, const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
+static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_t n_rows,
                     int64_t n_cols, const float* rs, const float* cs, float* acc, float* gs) {
   int rc;
   if ((rc = make_tmap_bf16(&g.ta, a, n_rows, ld, ld, kTileRows))) return rc;
@@ -874,8 +874,9 @@ static int fill_dir(GradDir& g, const __nv_bfloat16* a, const __nv_bfloat16* b, 
   return PLK_OK;
 }
 
-static int grad_launch_bf16(const GradArgs& ga, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
-                            int64_t d, int64_t bs, const float* ls, cudaStream_t st) {
+template <bool F16>
+static int grad_launch_16(const GradArgs& ga, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                          int64_t d, int64_t bs, const float* ls, cudaStream_t st) {
   int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int csz = pick_cluster(row_blocks, bs, n_cols);
   const int kd = (int)(ld / kChunkK);
@@ -889,8 +890,8 @@ static int grad_launch_bf16(const GradArgs& ga, int64_t ld, int64_t n_rows, int6
     switch (kd) {
 #define PLK_CASE2(KD)                                                                                   \
   case KD:                                                                                              \
-    return csz == 2 ? launch_grad2<KD, 2>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st)     \
-                    : launch_grad2<KD, 1>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
+    return csz == 2 ? launch_grad2<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st)     \
+                    : launch_grad2<KD, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
       PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
 #undef PLK_CASE2
     }
@@ -898,8 +899,8 @@ static int grad_launch_bf16(const GradArgs& ga, int64_t ld, int64_t n_rows, int6
   switch (kd) {
 #define PLK_CASE(KD, DNC)                                                                               \
   case KD:                                                                                              \
-    return csz == 2 ? launch_grad<KD, DNC, 2>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st) \
-                    : launch_grad<KD, DNC, 1>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
+    return csz == 2 ? launch_grad<KD, DNC, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st) \
+                    : launch_grad<KD, DNC, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
     PLK_CASE(5, 3) PLK_CASE(6, 3) PLK_CASE(7, 4) PLK_CASE(8, 4)
 #undef PLK_CASE
   }
@@ -907,7 +908,7 @@ static int grad_launch_bf16(const GradArgs& ga, int64_t ld, int64_t n_rows, int6
   return PLK_ERR_UNSUPPORTED;
 }
 
-int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld, int64_t n_rows,
+int infonce_grad_tc16(const void* a, const void* b, int f16, int64_t ld, int64_t n_rows,
                       int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
                       const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st) {
   int rc = check_tc_shape(ld, d);
@@ -916,11 +917,12 @@ int infonce_grad_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, int64_t ld
   ga.ndir = 1;
   if ((rc = fill_dir(ga.dir[0], a, b, ld, n_rows, n_cols, rs, cs, acc, gs))) return rc;
   ga.dir[1] = ga.dir[0];
-  return grad_launch_bf16(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
+  return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st)
+             : grad_launch_16<false>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
 }
 
-int infonce_grad_pair_bf16(const __nv_bfloat16* a0, const __nv_bfloat16* b0, const __nv_bfloat16* a1,
-                           const __nv_bfloat16* b1, int64_t ld, int64_t n_rows, int64_t row_offset,
+int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1,
+                           const void* b1, int f16, int64_t ld, int64_t n_rows, int64_t row_offset,
                            int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs0,
                            const float* cs0, const float* rs1, const float* cs1, float* acc0, float* acc1,
                            float* gs, cudaStream_t st) {
@@ -930,7 +932,8 @@ int infonce_grad_pair_bf16(const __nv_bfloat16* a0, const __nv_bfloat16* b0, con
   ga.ndir = 2;
   if ((rc = fill_dir(ga.dir[0], a0, b0, ld, n_rows, n_cols, rs0, cs0, acc0, gs))) return rc;
   if ((rc = fill_dir(ga.dir[1], a1, b1, ld, n_rows, n_cols, rs1, cs1, acc1, nullptr))) return rc;
-  return grad_launch_bf16(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
+  return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st)
+             : grad_launch_16<false>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
 }
 
 }  // namespace plk

@@ -249,10 +249,11 @@ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lb
   return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, int a_mn_major, int b_mn_major,
+                                                     int f16 /* 0: bf16 operands, 1: fp16 operands */) {
   return (1u << 4)                       // [4,6)   D format  = F32
-         | (1u << 7)                     // [7,10)  A format  = BF16
-         | (1u << 10)                    // [10,13) B format  = BF16
+         | ((f16 ? 0u : 1u) << 7)        // [7,10)  A format  (0 = F16, 1 = BF16)
+         | ((f16 ? 0u : 1u) << 10)       // [10,13) B format
          | ((uint32_t)a_mn_major << 15)  // [15]    A major   (0 = K, 1 = MN)
          | ((uint32_t)b_mn_major << 16)  // [16]    B major
          | ((uint32_t)(n >> 3) << 17)    // [17,23) N >> 3
@@ -307,6 +308,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
+  if constexpr (F16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
@@ -315,7 +326,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // ------------------------------------------------------------------------------------------
 // host: tensor maps
 // ------------------------------------------------------------------------------------------
-// bf16 row-major [rows, ld] matrix viewed through boxes of {64 columns, box_rows rows},
+// 16-bit (bf16 or fp16) row-major [rows, ld] matrix viewed through boxes of {64 columns, box_rows rows},
 // 128-byte swizzle, out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                    int box_rows);

@@ -45,7 +45,7 @@ template <int KD, int KC, int CS>
 __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
     const __grid_constant__ CUtensorMap tmap_gp, const float* __restrict__ g_sqn, int64_t nq, int64_t ng, int64_t goff, int tiles_per_chunk,
-    int nchunks, int kc_out, int32_t* __restrict__ out_idx, float* __restrict__ out_key) {
+    int nchunks, int kc_out, int32_t* __restrict__ out_idx, float* __restrict__ out_key, int f16) {
   using Cfg = TopkCfg<KD>;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
       mbar_wait(bar_a, 0);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
@@ -236,7 +236,7 @@ static int topk_bf16_chunks(int64_t nq, int64_t ng) {
   return best;
 }
 
-size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc) {
+size_t topk_ws_tc16(int64_t nq, int64_t ng, int64_t d, int kc) {
   const int c = topk_bf16_chunks(nq, ng);
   return (size_t)nq * c * 2 * kc * (sizeof(int32_t) + sizeof(float));  // two column-half lists per chunk
 }
@@ -244,7 +244,7 @@ size_t topk_ws_bf16(int64_t nq, int64_t ng, int64_t d, int kc) {
 template <int KD, int KC, int CS>
 static int launch_topk(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tgp, dim3 grid,
                        const float* g_sqn, int64_t nq, int64_t ng, int64_t goff, int tpc, int nchunks,
-                       int kc, int32_t* o_idx, float* o_key, cudaStream_t st) {
+                       int kc, int32_t* o_idx, float* o_key, int f16, cudaStream_t st) {
   auto kern = topk_tc_kernel<KD, KC, CS>;
   static bool configured = false;
   if (!configured) {
@@ -252,21 +252,21 @@ static int launch_topk(const CUtensorMap& tq, const CUtensorMap& tg, const CUten
     configured = true;
   }
   int rc = launch_kernel(kern, grid, dim3(kTkThreads), TopkCfg<KD>::kSmem, st, CS, tq, tg, tgp, g_sqn, nq, ng,
-                         goff, tpc, nchunks, kc, o_idx, o_key);
+                         goff, tpc, nchunks, kc, o_idx, o_key, f16);
   if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
 
-int topk_candidates_bf16(const __nv_bfloat16* q, const __nv_bfloat16* g, int64_t ld,
+int topk_candidates_tc16(const void* q, const void* g, int f16, int64_t ld,
                          const float* g_sqn, int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff,
                          int32_t* cand_idx, float* cand_key, void* ws, size_t ws_bytes,
                          cudaStream_t st) {
   PLK_REQUIRE(ld % kChunkK == 0 && ld >= d && ld - d < kChunkK, PLK_ERR_INVALID,
-              "bf16 operands must be zero-padded to ld = ceil(d/64)*64 (d=%lld ld=%lld)", (long long)d, (long long)ld);
-  PLK_REQUIRE(ld <= 512, PLK_ERR_UNSUPPORTED, "bf16 path supports d <= 512 (got %lld)", (long long)d);
-  PLK_REQUIRE(kc <= 32, PLK_ERR_UNSUPPORTED, "bf16 path keeps at most 32 candidates per query (got %d)", kc);
-  PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the bf16 path needs an sm_100 device");
+              "16-bit operands must be zero-padded to ld = ceil(d/64)*64 (d=%lld ld=%lld)", (long long)d, (long long)ld);
+  PLK_REQUIRE(ld <= 512, PLK_ERR_UNSUPPORTED, "tensor-core path supports d <= 512 (got %lld)", (long long)d);
+  PLK_REQUIRE(kc <= 32, PLK_ERR_UNSUPPORTED, "tensor-core path keeps at most 32 candidates per query (got %d)", kc);
+  PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the tensor-core path needs an sm_100 device");
   int rc;
   CUtensorMap tq, tg, tgp;
   if ((rc = make_tmap_bf16(&tq, q, nq, ld, ld, kTileRows))) return rc;
@@ -282,7 +282,7 @@ int topk_candidates_bf16(const __nv_bfloat16* q, const __nv_bfloat16* g, int64_t
   dim3 grid((unsigned)nchunks, (unsigned)qblocks, 1);
   const int kd = (int)(ld / kChunkK);
   rc = PLK_ERR_UNSUPPORTED;
-#define PLK_TK(KD, KC, CS) launch_topk<KD, KC, CS>(tq, tg, tgp, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, st)
+#define PLK_TK(KD, KC, CS) launch_topk<KD, KC, CS>(tq, tg, tgp, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, f16, st)
 #define PLK_CASE(KD)                                                              \
   case KD:                                                                        \
     rc = kc <= 16 ? (cs == 2 ? PLK_TK(KD, 16, 2) : PLK_TK(KD, 16, 1))              \

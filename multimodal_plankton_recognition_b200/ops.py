@@ -11,7 +11,8 @@ import torch
 from . import _lib
 from ._lib import PLK_BF16, PLK_F16, PLK_F32
 
-MODES = {"fp32": PLK_F32, "bf16": PLK_BF16}
+MODES = {"fp32": PLK_F32, "bf16": PLK_BF16, "fp16": PLK_F16}
+OP_TORCH_DTYPE = {PLK_F32: torch.float32, PLK_BF16: torch.bfloat16, PLK_F16: torch.float16}
 _DT = {torch.float32: PLK_F32, torch.bfloat16: PLK_BF16, torch.float16: PLK_F16}
 
 
@@ -27,7 +28,7 @@ def _require_cuda(*ts):
 
 
 def padded_width(d: int, mode: int) -> int:
-    return (d + 63) // 64 * 64 if mode == PLK_BF16 else d
+    return d if mode == PLK_F32 else (d + 63) // 64 * 64
 
 
 def l2norm(x: torch.Tensor, mode: int, normalise: bool = True, inv_den=None, nrm=None, want_sqn=False):
@@ -36,7 +37,7 @@ def l2norm(x: torch.Tensor, mode: int, normalise: bool = True, inv_den=None, nrm
     lib = _lib.load()
     n, d = x.shape
     ld = padded_width(d, mode)
-    u = torch.empty((n, ld), device=x.device, dtype=torch.bfloat16 if mode == PLK_BF16 else torch.float32)
+    u = torch.empty((n, ld), device=x.device, dtype=OP_TORCH_DTYPE[mode])
     if inv_den is None:
         inv_den = torch.empty(n, device=x.device, dtype=torch.float32)
     if nrm is None:
@@ -167,7 +168,7 @@ def clip_loss_fwd(image_emb: torch.Tensor, profile_emb: torch.Tensor, logit_scal
 def _(image_emb, profile_emb, logit_scale, buckets, mode):
     B, d = image_emb.shape
     ld = padded_width(d, mode)
-    odt = torch.bfloat16 if mode == PLK_BF16 else torch.float32
+    odt = OP_TORCH_DTYPE[mode]
     f = image_emb.new_empty
     return (f((), dtype=torch.float32), f((B, ld), dtype=odt), f((B, ld), dtype=odt),
             f((7, B), dtype=torch.float32), f((2,), dtype=torch.float32))

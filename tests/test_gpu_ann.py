@@ -14,7 +14,7 @@ KW = dict(n_neighbors=32, metric="euclidean", diversify_prob=0.0, pruning_degree
           low_memory=False, random_state=0)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
 @pytest.mark.parametrize("path", golden_files("ann_"), ids=os.path.basename)
 def test_golden_reference_vectors(path, precision):
     from multimodal_plankton_recognition_b200 import ANNClassifier

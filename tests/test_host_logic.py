@@ -18,6 +18,7 @@ def test_cliploss_surface_matches_reference():
         mod(image_emb=x, profile_emb=x, buckets=4)
     with pytest.raises(ValueError):
         CLIPLoss(precision="fp8")
+    assert CLIPLoss(precision="fp16").precision == "fp16"
 
 
 def test_no_cpu_fallback():
