@@ -65,6 +65,14 @@ int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx
                    int normalise /* 0: plain cast/copy (retrieval on pre-normalised data) */,
                    void* stream);
 
+/* Both modalities in one launch (fp32 rows in, same shapes), optionally zero-filling two fp32
+ * arrays (the sum-exp accumulators plk_infonce_fwd adds into; pass sums_zeroed = 1 there). */
+int plk_l2norm_pair_fwd(const float* x, const float* y, int64_t n, int64_t d, int64_t ldx,
+                        void* u, void* v, int u_dtype, int64_t ldu,
+                        float* inv_den_x, float* nrm_x, float* inv_den_y, float* nrm_y,
+                        float* zero_a, int64_t n_zero_a, float* zero_b, int64_t n_zero_b,
+                        void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * a3-a7. Fused similarity + temperature + online row/column sum-exp + diagonal.
  *        replaces: bmm, *exp(logit_scale), 2x cross_entropy       reference src/coordination.py:36-44
@@ -85,7 +93,9 @@ int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx
 int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld,
                     int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
                     int64_t bucket_size, const float* logit_scale,
-                    float* row_sumexp, float* col_sumexp, float* diag, void* stream);
+                    float* row_sumexp, float* col_sumexp, float* diag,
+                    int sums_zeroed /* 1: row/col_sumexp were already zero-filled (plk_l2norm_pair_fwd) */,
+                    void* stream);
 
 /* a8. loss partial over owned rows:
  *   *loss_out = (1/(2*B_global)) * sum_i [ 2 s + log R_i + log C_i - 2 S_ii ]      reference src/coordination.py:45
@@ -141,6 +151,20 @@ int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const vo
                             const float* diag, const float* rs, const float* cs,
                             const float* logit_scale, const float* grad_out, int64_t batch_global,
                             void* dx, int dx_dtype, void* stream);
+
+/* plk_infonce_grad_finish for both modalities + plk_infonce_dls in ONE launch (fp32 rows in/out):
+ *   dx from (acc_x, x, partner y), dy from (acc_y, y, partner x); embedding gradients use
+ *   *grad_out_emb, d logit_scale uses *grad_out (they differ by the world size under DDP scaling);
+ *   *dls_out = *grad_out / (2B) * (*gs - 2 * *diag_sum), after which *gs is reset to 0 (consumed). */
+int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int parts,
+                                 const float* x, const float* y, int64_t n, int64_t d, int64_t ldx,
+                                 const float* inv_den_x, const float* nrm_x,
+                                 const float* inv_den_y, const float* nrm_y,
+                                 const float* diag, const float* rs, const float* cs,
+                                 const float* logit_scale, const float* grad_out_emb,
+                                 const float* grad_out, int64_t batch_global, float* gs,
+                                 const float* diag_sum, float* dx, float* dy, float* dls_out,
+                                 void* stream);
 
 /* d logit_scale partial:  *dls_out = (*grad_out) / (2 B_global) * (*gs - 2 * *diag_sum) */
 int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_out,

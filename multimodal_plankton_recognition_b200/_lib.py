@@ -78,7 +78,11 @@ SIGNATURES = {
     "plk_device_supports_tc": (_int, []),
     "plk_launch_count": (_i64, []),
     "plk_l2norm_fwd": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _vp, _vp, _int, _vp]),
-    "plk_infonce_fwd": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "plk_l2norm_pair_fwd": (_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _int, _i64, _vp, _vp, _vp, _vp, _vp, _i64,
+                                   _vp, _i64, _vp]),
+    "plk_infonce_fwd": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp]),
+    "plk_infonce_grad_finish_pair": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plk_infonce_loss": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "plk_infonce_grad_parts": (_int, [_int, _i64, _i64, _i64, _i64]),
     "plk_infonce_grad_pair_parts": (_int, [_int, _i64, _i64, _i64, _i64]),

@@ -47,7 +47,7 @@ static int check_common(const void* a, const void* b, int op_dtype, int64_t ld, 
 int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld, int64_t n_rows,
                     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bucket_size,
                     const float* logit_scale, float* row_sumexp, float* col_sumexp, float* diag,
-                    void* stream) {
+                    int sums_zeroed, void* stream) {
   int rc = check_common(u, v, op_dtype, ld, n_rows, n_cols, d, bucket_size);
   if (rc) return rc;
   PLK_REQUIRE(logit_scale && row_sumexp && col_sumexp && diag, PLK_ERR_INVALID, "null output pointer");
@@ -57,9 +57,9 @@ int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld, int6
   cudaStream_t st = (cudaStream_t)stream;
   if (op_dtype == PLK_F32)
     return infonce_fwd_f32((const float*)u, (const float*)v, ld, n_rows, row_offset, n_cols, d,
-                           bucket_size, logit_scale, row_sumexp, col_sumexp, diag, st);
+                           bucket_size, logit_scale, row_sumexp, col_sumexp, diag, sums_zeroed, st);
   return infonce_fwd_tc16(u, v, op_dtype == PLK_F16, ld, n_rows, row_offset, n_cols, d, bucket_size,
-                          logit_scale, row_sumexp, col_sumexp, diag, st);
+                          logit_scale, row_sumexp, col_sumexp, diag, sums_zeroed, st);
 }
 
 int plk_infonce_grad_parts(int op_dtype, int64_t n_rows, int64_t n_cols, int64_t d,

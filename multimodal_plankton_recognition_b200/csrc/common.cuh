@@ -44,7 +44,7 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ---- entry points implemented per translation unit (dispatched from api.cu) ----
 int infonce_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset,
                     int64_t n_cols, int64_t d, int64_t bs, const float* ls, float* row_sumexp,
-                    float* col_sumexp, float* diag, cudaStream_t st);
+                    float* col_sumexp, float* diag, int sums_zeroed, cudaStream_t st);
 int infonce_grad_f32(const float* a, const float* b, int64_t ld, int64_t n_rows, int64_t row_offset,
                      int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs,
                      const float* cs, float* acc, float* gs, cudaStream_t st);
@@ -56,7 +56,7 @@ size_t topk_ws_f32(int64_t nq, int64_t ng, int64_t d, int kc);
 // 16-bit tensor-core path: f16 = 0 -> bf16 operands, 1 -> fp16 operands
 int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows,
                      int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
-                     float* row_sumexp, float* col_sumexp, float* diag, cudaStream_t st);
+                     float* row_sumexp, float* col_sumexp, float* diag, int sums_zeroed, cudaStream_t st);
 int infonce_grad_tc16(const void* a, const void* b, int f16, int64_t ld, int64_t n_rows,
                       int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
                       const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st);

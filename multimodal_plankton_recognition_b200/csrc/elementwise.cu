@@ -141,6 +141,71 @@ static bool l2norm_try_vec(const float* x, int64_t n, int64_t d, int64_t ldx, TO
   return false;
 }
 
+// Both modalities in one launch (blockIdx.y selects), optionally zero-filling the two sum-exp
+// accumulators the forward kernel adds into: 3 launches -> 1 on the launch-bound small-batch path.
+struct NormPairArgs {
+  const float* x[2];
+  void* u[2];
+  float* inv_den[2];
+  float* nrm[2];
+  float* zero[2];
+  int64_t nzero[2];
+};
+template <int NV, typename TO>
+__global__ void __launch_bounds__(256) l2norm_pair_vec_kernel(NormPairArgs a, int64_t n, int64_t ldx, int64_t ldu) {
+  const int m = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  {  // zero fill: thread-linear over this modality's accumulator
+    const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.zero[m] != nullptr && z < a.nzero[m]) a.zero[m][z] = 0.f;
+  }
+  if (row >= n) return;
+  const float4* xr = reinterpret_cast<const float4*>(a.x[m] + row * ldx);
+  TO* u = reinterpret_cast<TO*>(a.u[m]);
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ss = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, ss))));
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  const float den = fmaxf(nrm, kNormEps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float4 w = v[i];
+    w.x /= den; w.y /= den; w.z /= den; w.w /= den;
+    if constexpr (sizeof(TO) == 4) {
+      reinterpret_cast<float4*>(u + row * ldu)[lane + 32 * i] = w;
+    } else if constexpr (!kIsHalf<TO>) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+      reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    } else {
+      __half2 lo = __floats2half2_rn(w.x, w.y), hi = __floats2half2_rn(w.z, w.w);
+      reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+  if (lane == 0) {
+    a.inv_den[m][row] = 1.0f / den;
+    a.nrm[m][row] = nrm;
+  }
+}
+
+template <typename TO>
+static bool l2norm_pair_try(const NormPairArgs& a, int64_t n, int64_t d, int64_t ldx, int64_t ldu, cudaStream_t st) {
+  int64_t nz = a.nzero[0] > a.nzero[1] ? a.nzero[0] : a.nzero[1];
+  int64_t blocks = ceil_div(n, 8);
+  if (ceil_div(nz, 256) > blocks) blocks = ceil_div(nz, 256);
+  dim3 block(256), grid((unsigned)blocks, 2);
+  switch (d / 128) {
+#define PLK_CASE(NV) case NV: l2norm_pair_vec_kernel<NV, TO><<<grid, block, 0, st>>>(a, n, ldx, ldu); return true;
+    PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
+#undef PLK_CASE
+  }
+  return false;
+}
+
 template <typename TI>
 static int l2norm_dispatch_out(const TI* x, int64_t n, int64_t d, int64_t ldx, void* u, int u_dtype,
                                int64_t ldu, float* inv_den, float* nrm, float* sqn, int normalise,
@@ -303,6 +368,71 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(
   for (int i = 0; i < NV; ++i)
     dr[lane + 32 * i] = make_float4((a[i].x - xv[i].x * dot) * idx_, (a[i].y - xv[i].y * dot) * idx_,
                                     (a[i].z - xv[i].z * dot) * idx_, (a[i].w - xv[i].w * dot) * idx_);
+}
+
+// Both modalities + d logit_scale in one launch (blockIdx.y selects the modality).
+struct FinishPairArgs {
+  const float* acc[2];
+  const float* x[2];        // raw rows of this modality (partner = x[1 - m])
+  const float* inv_den[2];
+  const float* nrm[2];
+  float* dx[2];
+};
+template <int NV>
+__global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
+    FinishPairArgs a, int parts, int64_t n, int64_t ldx, const float* __restrict__ diag,
+    const float* __restrict__ rs, const float* __restrict__ cs, const float* __restrict__ ls,
+    const float* __restrict__ grad_out, const float* __restrict__ grad_out_dls, int64_t batch,
+    float* __restrict__ gs, const float* __restrict__ diag_sum, float* __restrict__ dls_out) {
+  constexpr int64_t d = NV * 128;
+  const int m = blockIdx.y;
+  if (blockIdx.x == 0 && m == 0 && threadIdx.x == 0 && dls_out != nullptr) {
+    *dls_out = (float)((double)(*grad_out_dls) / (2.0 * (double)batch) * ((double)(*gs) - 2.0 * (double)(*diag_sum)));
+    *gs = 0.f;   // consumed: the accumulator is back to its zero-initialised state
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float4* ar = reinterpret_cast<const float4*>(a.acc[m] + row * d);
+  const float4* xr = reinterpret_cast<const float4*>(a.x[m] + row * ldx);
+  const float4* pr = reinterpret_cast<const float4*>(a.x[1 - m] + row * ldx);
+  const int64_t slab4 = n * d / 4;
+  float4 acc[NV], xv[NV], pv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i] = ar[lane + 32 * i];
+    xv[i] = xr[lane + 32 * i];
+    pv[i] = pr[lane + 32 * i];
+  }
+  for (int p = 1; p < parts; ++p) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 t = ar[lane + 32 * i + p * slab4];
+      acc[i].x += t.x; acc[i].y += t.y; acc[i].z += t.z; acc[i].w += t.w;
+    }
+  }
+  const float s = expf(*ls);
+  const float coef = (*grad_out) * s / (2.0f * (float)batch);
+  const float idx_ = a.inv_den[m][row], idp = a.inv_den[1 - m][row];
+  const bool clamped = !(a.nrm[m][row] > kNormEps);
+  const float dterm = expf(diag[row] - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i].x = coef * fmaf(dterm, pv[i].x * idp, acc[i].x);
+    acc[i].y = coef * fmaf(dterm, pv[i].y * idp, acc[i].y);
+    acc[i].z = coef * fmaf(dterm, pv[i].z * idp, acc[i].z);
+    acc[i].w = coef * fmaf(dterm, pv[i].w * idp, acc[i].w);
+    xv[i].x *= idx_; xv[i].y *= idx_; xv[i].z *= idx_; xv[i].w *= idx_;
+    dot = fmaf(xv[i].x, acc[i].x, fmaf(xv[i].y, acc[i].y, fmaf(xv[i].z, acc[i].z, fmaf(xv[i].w, acc[i].w, dot))));
+  }
+  dot = warp_sum(dot);
+  if (clamped) dot = 0.f;
+  float4* dr = reinterpret_cast<float4*>(a.dx[m] + row * d);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    dr[lane + 32 * i] = make_float4((acc[i].x - xv[i].x * dot) * idx_, (acc[i].y - xv[i].y * dot) * idx_,
+                                    (acc[i].z - xv[i].z * dot) * idx_, (acc[i].w - xv[i].w * dot) * idx_);
 }
 
 template <typename TI>
@@ -489,6 +619,37 @@ int plk_l2norm_fwd(const void* x, int x_dtype, int64_t n, int64_t d, int64_t ldx
   return PLK_ERR_INVALID;
 }
 
+int plk_l2norm_pair_fwd(const float* x, const float* y, int64_t n, int64_t d, int64_t ldx, void* u, void* v,
+                        int u_dtype, int64_t ldu, float* inv_den_x, float* nrm_x, float* inv_den_y,
+                        float* nrm_y, float* zero_a, int64_t n_zero_a, float* zero_b, int64_t n_zero_b,
+                        void* stream) {
+  PLK_REQUIRE(x && y && u && v && inv_den_x && nrm_x && inv_den_y && nrm_y, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(n > 0 && d > 0 && ldx >= d && ldu >= d, PLK_ERR_INVALID, "bad shape");
+  PLK_REQUIRE(u_dtype >= PLK_F32 && u_dtype <= PLK_F16, PLK_ERR_INVALID, "bad u_dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = d % 128 == 0 && d <= 1024 && ldu == d && (ldx & 3) == 0 &&
+                      ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)u | (uintptr_t)v) & 15) == 0);
+  if (vec_ok) {
+    NormPairArgs a;
+    a.x[0] = x; a.x[1] = y; a.u[0] = u; a.u[1] = v;
+    a.inv_den[0] = inv_den_x; a.inv_den[1] = inv_den_y; a.nrm[0] = nrm_x; a.nrm[1] = nrm_y;
+    a.zero[0] = zero_a; a.zero[1] = zero_b; a.nzero[0] = zero_a ? n_zero_a : 0; a.nzero[1] = zero_b ? n_zero_b : 0;
+    const bool ok = u_dtype == PLK_F32 ? l2norm_pair_try<float>(a, n, d, ldx, ldu, st)
+                    : u_dtype == PLK_BF16 ? l2norm_pair_try<__nv_bfloat16>(a, n, d, ldx, ldu, st)
+                                          : l2norm_pair_try<__half>(a, n, d, ldx, ldu, st);
+    if (ok) {
+      PLK_LAUNCHED(1);
+      return PLK_OK;
+    }
+  }
+  int rc = plk_l2norm_fwd(x, PLK_F32, n, d, ldx, u, u_dtype, ldu, inv_den_x, nrm_x, nullptr, 1, stream);
+  if (rc) return rc;
+  rc = plk_l2norm_fwd(y, PLK_F32, n, d, ldx, v, u_dtype, ldu, inv_den_y, nrm_y, nullptr, 1, stream);
+  if (rc) return rc;
+  if (zero_a || zero_b) return zero2(zero_a, zero_a ? n_zero_a : 0, zero_b, zero_b ? n_zero_b : 0, st);
+  return PLK_OK;
+}
+
 int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const float* diag,
                      const float* logit_scale, int64_t n_rows, int64_t batch_global, float* loss_out,
                      float* diag_sum_out, float* gs_zero, void* stream) {
@@ -524,6 +685,47 @@ int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const vo
   }
   set_error("grad_finish: raw embeddings must be fp32 (got dtype %d); cast on the host side", x_dtype);
   return PLK_ERR_UNSUPPORTED;
+}
+
+int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int parts, const float* x,
+                                 const float* y, int64_t n, int64_t d, int64_t ldx,
+                                 const float* inv_den_x, const float* nrm_x, const float* inv_den_y,
+                                 const float* nrm_y, const float* diag, const float* rs, const float* cs,
+                                 const float* logit_scale, const float* grad_out_emb,
+                                 const float* grad_out, int64_t batch_global, float* gs,
+                                 const float* diag_sum, float* dx, float* dy, float* dls_out,
+                                 void* stream) {
+  PLK_REQUIRE(acc_x && acc_y && x && y && inv_den_x && nrm_x && inv_den_y && nrm_y && diag && rs && cs &&
+                  logit_scale && grad_out_emb && grad_out && gs && diag_sum && dx && dy && dls_out,
+              PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(n > 0 && d > 0 && ldx >= d && batch_global >= n && parts >= 1, PLK_ERR_INVALID, "bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = d % 128 == 0 && d <= 1024 && (ldx & 3) == 0 &&
+                      ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)acc_x | (uintptr_t)acc_y | (uintptr_t)dx | (uintptr_t)dy) & 15) == 0);
+  if (vec_ok) {
+    FinishPairArgs a;
+    a.acc[0] = acc_x; a.acc[1] = acc_y; a.x[0] = x; a.x[1] = y;
+    a.inv_den[0] = inv_den_x; a.inv_den[1] = inv_den_y; a.nrm[0] = nrm_x; a.nrm[1] = nrm_y;
+    a.dx[0] = dx; a.dx[1] = dy;
+    dim3 block(256), grid((unsigned)ceil_div(n, 8), 2);
+    switch (d / 128) {
+#define PLK_CASE(NV) case NV: grad_finish_pair_vec_kernel<NV><<<grid, block, 0, st>>>(a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out); break;
+      PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
+#undef PLK_CASE
+    }
+    PLK_LAUNCHED(1);
+    return PLK_OK;
+  }
+  int rc = plk_infonce_grad_finish(acc_x, parts, x, y, PLK_F32, n, d, ldx, inv_den_x, nrm_x, inv_den_y, diag, rs, cs,
+                                   logit_scale, grad_out_emb, batch_global, dx, PLK_F32, stream);
+  if (rc) return rc;
+  rc = plk_infonce_grad_finish(acc_y, parts, y, x, PLK_F32, n, d, ldx, inv_den_y, nrm_y, inv_den_x, diag, rs, cs,
+                               logit_scale, grad_out_emb, batch_global, dy, PLK_F32, stream);
+  if (rc) return rc;
+  rc = plk_infonce_dls(gs, diag_sum, grad_out, batch_global, dls_out, stream);
+  if (rc) return rc;
+  PLK_CUDA(cudaMemsetAsync(gs, 0, sizeof(float), st));
+  return PLK_OK;
 }
 
 int plk_topk_rescore(const float* q32, const float* g32, int64_t nq, int64_t ng, int64_t d,

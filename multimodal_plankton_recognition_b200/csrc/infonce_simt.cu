@@ -216,11 +216,11 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
 
 int infonce_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset,
                     int64_t n_cols, int64_t d, int64_t bs, const float* ls, float* row_sumexp,
-                    float* col_sumexp, float* diag, cudaStream_t st) {
+                    float* col_sumexp, float* diag, int sums_zeroed, cudaStream_t st) {
   int rc;
   // sums are accumulated with atomics -> zero first; diag needs no init (every owned row has its
   // diagonal column inside its bucket, so it is always written)
-  if ((rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
+  if (!sums_zeroed && (rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
   dim3 grid((unsigned)ceil_div(n_cols, BN), (unsigned)ceil_div(n_rows, BM));
   infonce_fwd_simt<<<grid, NT, 0, st>>>(u, v, ld, n_rows, row_offset, n_cols, d, bs, ls, row_sumexp,
                                         col_sumexp, diag);

@@ -794,7 +794,7 @@ static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
 
 int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows,
                      int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
-                     float* row_sumexp, float* col_sumexp, float* diag, cudaStream_t st) {
+                     float* row_sumexp, float* col_sumexp, float* diag, int sums_zeroed, cudaStream_t st) {
   int rc = check_tc_shape(ld, d);
   if (rc) return rc;
   int64_t row_blocks = ceil_div(n_rows, kTileRows);
@@ -805,7 +805,7 @@ int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t 
   if ((rc = make_tmap_bf16(&tbp, v, n_cols, ld, ld, kTileRows / 2))) return rc;
   // sums are accumulated with atomics -> zero first; diag needs no init (every owned row has its
   // diagonal column inside its bucket, so it is always written)
-  if ((rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
+  if (!sums_zeroed && (rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
   const int nseg = pick_segments(row_blocks, max_tiles, 1);
   const int tps = (int)ceil_div(max_tiles, nseg);

@@ -28,6 +28,14 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
                    int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   PLK_REQUIRE(fn != nullptr, PLK_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  // The driver entry point needs a context bound to the CALLING thread.  The runtime binds the
+  // primary context lazily, and e.g. PyTorch's autograd worker threads may not have issued any
+  // runtime call yet when they reach us: bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    PLK_CUDA(cudaFree(nullptr));
+    ctx_bound = true;
+  }
   PLK_REQUIRE(((uintptr_t)base & 15) == 0, PLK_ERR_INVALID, "bf16 operand must be 16-byte aligned");
   PLK_REQUIRE((ld * 2) % 16 == 0, PLK_ERR_INVALID, "bf16 operand leading dimension must be a multiple of 8");
   PLK_REQUIRE(cols % kChunkK == 0, PLK_ERR_INVALID, "bf16 operand width must be padded to a multiple of 64");

@@ -47,8 +47,9 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
     off = r * n
     x, y = ops._as_f32_rows(image_emb), ops._as_f32_rows(profile_emb)
     ls = logit_scale.detach().float()
-    u, idx, nx, _ = ops.l2norm(x, mode)
-    v, idy, ny, _ = ops.l2norm(y, mode)
+    st4 = torch.empty((4, n), device=x.device, dtype=torch.float32)
+    u, v = ops.l2norm_pair(x, y, mode, st4)
+    idx, nx, idy, ny = st4.unbind(0)
     if n % bs == 0:
         # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange,
         # the local problem is complete; only the scalars are reduced.
@@ -79,16 +80,17 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
     R, _ = _world(group)
     go = grad_out.detach().float().reshape(1).contiguous()
     rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
-    gs = aux[1:].clone()
+    gs = aux[1:]
     acc_x, acc_y = ops.infonce_grad_pair_local(u, v_all, v, u_all, mode, d, off, bs, ls, rs_own, cs_all,
                                                cs_own, rs_all, gs)
     # grad_scale == "ddp": DistributedDataParallel AVERAGES parameter gradients over ranks, while
     # each rank holds the exact d(global loss)/d(local rows); pre-multiplying by the world size
     # makes the averaged encoder gradients equal the true global-batch gradients.
     go_emb = go * R if grad_scale == "ddp" else go
-    dx = ops.infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[0])
-    dy = ops.infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs_own, cs_own, ls, go_emb, B, out_dtypes[1])
-    dls = ops.infonce_dls(gs, aux[0:1], go, B, scal[1] if not reduce_scalars else None)
+    dx, dy, dls = ops.infonce_grad_finish_pair(acc_x, acc_y, x, y, (idx, nx), (idy, ny), dg, rs_own, cs_own, ls,
+                                               go_emb, go, B, gs, aux[0:1],
+                                               scal[1] if not reduce_scalars else None)
+    dx, dy = dx.to(out_dtypes[0]), dy.to(out_dtypes[1])
     if reduce_scalars:
         dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
     return dx, dy, dls

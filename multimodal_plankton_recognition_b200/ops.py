@@ -50,7 +50,28 @@ def l2norm(x: torch.Tensor, mode: int, normalise: bool = True, inv_den=None, nrm
     return u, inv_den, nrm, sqn
 
 
-def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale, rs=None, cs=None, dg=None):
+def l2norm_pair(x, y, mode, stats, zero_a=None, zero_b=None):
+    """Normalise both modalities in one launch; writes (1/den, |.|) into stats rows 0..3 and
+    zero-fills the two optional fp32 vectors.  -> (u, v)   (plk_l2norm_pair_fwd)"""
+    lib = _lib.load()
+    n, d = x.shape
+    ld = padded_width(d, mode)
+    u = torch.empty((n, ld), device=x.device, dtype=OP_TORCH_DTYPE[mode])   # separate storages: custom-op
+    v = torch.empty((n, ld), device=x.device, dtype=OP_TORCH_DTYPE[mode])   # outputs must not alias each other
+    with torch.cuda.device(x.device):
+        lib.check(lib.plk_l2norm_pair_fwd(x.data_ptr(), y.data_ptr(), n, d, x.stride(0), u.data_ptr(),
+                                          v.data_ptr(), mode, ld, stats[0].data_ptr(), stats[1].data_ptr(),
+                                          stats[2].data_ptr(), stats[3].data_ptr(),
+                                          zero_a.data_ptr() if zero_a is not None else None,
+                                          zero_a.numel() if zero_a is not None else 0,
+                                          zero_b.data_ptr() if zero_b is not None else None,
+                                          zero_b.numel() if zero_b is not None else 0, _stream(x)),
+                  "plk_l2norm_pair_fwd")
+    return u, v
+
+
+def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale, rs=None, cs=None, dg=None,
+                      sums_zeroed=False):
     """Fused similarity + sum-exp for the owned rows `u` against all rows `v`.
     -> (row_sumexp [n_rows], col_sumexp [n_cols] (partial over owned rows), diag [n_rows])"""
     lib = _lib.load()
@@ -61,7 +82,7 @@ def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, logit_scale, rs=No
     with torch.cuda.device(u.device):
         lib.check(lib.plk_infonce_fwd(u.data_ptr(), v.data_ptr(), mode, u.stride(0), n_rows, row_offset, n_cols,
                                       d, bucket_size, logit_scale.data_ptr(), rs.data_ptr(), cs.data_ptr(),
-                                      dg.data_ptr(), _stream(u)), "plk_infonce_fwd")
+                                      dg.data_ptr(), 1 if sums_zeroed else 0, _stream(u)), "plk_infonce_fwd")
     return rs, cs, dg
 
 
@@ -126,6 +147,25 @@ def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own
     return dx
 
 
+def infonce_grad_finish_pair(acc_x, acc_y, x, y, stats_x, stats_y, dg, rs_own, cs_own, logit_scale, go_emb, go,
+                             batch_global, gs, diag_sum, dls_out=None):
+    """Both gradient tails + d logit_scale in one launch (fp32 rows).  stats_x / stats_y are
+    (1/den, |.|) pairs.  `gs` is consumed (reset to 0).  -> (dx, dy, dls)"""
+    lib = _lib.load()
+    n, d = x.shape
+    dx = torch.empty((n, d), device=x.device, dtype=torch.float32)
+    dy = torch.empty((n, d), device=x.device, dtype=torch.float32)
+    dls = torch.empty((), device=x.device, dtype=torch.float32) if dls_out is None else dls_out
+    with torch.cuda.device(x.device):
+        lib.check(lib.plk_infonce_grad_finish_pair(
+            acc_x.data_ptr(), acc_y.data_ptr(), acc_x.shape[0], x.data_ptr(), y.data_ptr(), n, d, x.stride(0),
+            stats_x[0].data_ptr(), stats_x[1].data_ptr(), stats_y[0].data_ptr(), stats_y[1].data_ptr(),
+            dg.data_ptr(), rs_own.data_ptr(), cs_own.data_ptr(), logit_scale.data_ptr(), go_emb.data_ptr(),
+            go.data_ptr(), batch_global, gs.data_ptr(), diag_sum.data_ptr(), dx.data_ptr(), dy.data_ptr(),
+            dls.data_ptr(), _stream(x)), "plk_infonce_grad_finish_pair")
+    return dx, dy, dls
+
+
 def infonce_dls(gs, diag_sum, grad_out, batch_global, out=None):
     lib = _lib.load()
     out = torch.empty((), device=gs.device, dtype=torch.float32) if out is None else out
@@ -157,9 +197,8 @@ def clip_loss_fwd(image_emb: torch.Tensor, profile_emb: torch.Tensor, logit_scal
     x, y = _as_f32_rows(image_emb), _as_f32_rows(profile_emb)
     ls = logit_scale.detach().float()
     stats = torch.empty((7, B), device=x.device, dtype=torch.float32)
-    u, _, _, _ = l2norm(x, mode, True, stats[0], stats[1])
-    v, _, _, _ = l2norm(y, mode, True, stats[2], stats[3])
-    infonce_fwd_local(u, v, mode, d, 0, bs, ls, stats[4], stats[5], stats[6])
+    u, v = l2norm_pair(x, y, mode, stats, stats[4], stats[5])
+    infonce_fwd_local(u, v, mode, d, 0, bs, ls, stats[4], stats[5], stats[6], sums_zeroed=True)
     loss, aux = infonce_loss_local(stats[4], stats[5], stats[6], ls, B)
     return loss, u, v, stats, aux
 
@@ -185,12 +224,11 @@ def clip_loss_bwd(grad_out: torch.Tensor, image_emb: torch.Tensor, profile_emb: 
     ls = logit_scale.detach().float()
     go = grad_out.detach().float().reshape(1).contiguous()
     idx, nx, idy, ny, rs, cs, dg = stats.unbind(0)
-    gs = aux[1:].clone()      # accumulator for sum G*S (aux[1] is 0 from the forward; keep aux reusable)
+    gs = aux[1:]              # zeroed by the forward; the gradient tail consumes it and re-zeroes it
     acc_x, acc_y = infonce_grad_pair_local(u, v, v, u, mode, d, 0, bs, ls, rs, cs, cs, rs, gs)
-    dx = infonce_grad_finish(acc_x, x, y, idx, nx, idy, dg, rs, cs, ls, go, B, image_emb.dtype)
-    dy = infonce_grad_finish(acc_y, y, x, idy, ny, idx, dg, rs, cs, ls, go, B, profile_emb.dtype)
-    dls = infonce_dls(gs, aux[0:1], go, B).to(logit_scale.dtype)
-    return dx, dy, dls
+    dx, dy, dls = infonce_grad_finish_pair(acc_x, acc_y, x, y, stats[0:2], stats[2:4], dg, rs, cs, ls, go, go, B,
+                                           gs, aux[0:1])
+    return dx.to(image_emb.dtype), dy.to(profile_emb.dtype), dls.to(logit_scale.dtype)
 
 
 @clip_loss_bwd.register_fake

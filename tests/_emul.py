@@ -25,6 +25,15 @@ def l2norm(x, mode, normalise=True, inv_den=None, nrm=None, want_sqn=False):
         (u.double() ** 2).sum(1).float() if want_sqn else None
 
 
+def l2norm_pair(x, y, mode, stats, zero_a=None, zero_b=None):
+    u, _, _, _ = l2norm(x, mode, True, stats[0], stats[1])
+    v, _, _, _ = l2norm(y, mode, True, stats[2], stats[3])
+    for z in (zero_a, zero_b):
+        if z is not None:
+            z.zero_()
+    return u, v
+
+
 def _E(a, b, off, bs, ls):
     s = float(torch.exp(ls.double()))
     S = s * (a.double() @ b.double().T)
@@ -32,7 +41,7 @@ def _E(a, b, off, bs, ls):
     return torch.where(m, torch.exp(S - s), torch.zeros_like(S)), S, s
 
 
-def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, ls, rs=None, cs=None, dg=None):
+def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, ls, rs=None, cs=None, dg=None, sums_zeroed=False):
     E, S, _ = _E(u, v, row_offset, bucket_size, ls)
     n = u.shape[0]
     return E.sum(1).float(), E.sum(0).float(), S[torch.arange(n), torch.arange(n) + row_offset].float()
@@ -71,6 +80,17 @@ def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own
     dot = (u * dU).sum(1, keepdim=True)
     dot = torch.where((nrm_x > 1e-12)[:, None], dot, torch.zeros_like(dot))
     return ((dU - u * dot) * inv_den_x.double()[:, None]).to(out_dtype)
+
+
+def infonce_grad_finish_pair(acc_x, acc_y, x, y, stats_x, stats_y, dg, rs_own, cs_own, ls, go_emb, go, batch_global,
+                             gs, diag_sum, dls_out=None):
+    dx = infonce_grad_finish(acc_x, x, y, stats_x[0], stats_x[1], stats_y[0], dg, rs_own, cs_own, ls, go_emb,
+                             batch_global, torch.float32)
+    dy = infonce_grad_finish(acc_y, y, x, stats_y[0], stats_y[1], stats_x[0], dg, rs_own, cs_own, ls, go_emb,
+                             batch_global, torch.float32)
+    dls = infonce_dls(gs, diag_sum, go, batch_global, dls_out)
+    gs.zero_()
+    return dx, dy, dls
 
 
 def infonce_dls(gs, diag_sum, go, batch_global, out=None):

@@ -37,7 +37,7 @@ def test_argument_validation_happens_before_any_launch():
     """Bad arguments are rejected with a status + message, no CUDA call needed (runs without a GPU)."""
     from multimodal_plankton_recognition_b200 import _lib
     lib = _lib.load()
-    rc = lib.plk_infonce_fwd(None, None, 0, 8, 4, 0, 4, 8, 4, None, None, None, None, None)
+    rc = lib.plk_infonce_fwd(None, None, 0, 8, 4, 0, 4, 8, 4, None, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.plk_last_error()
     rc = lib.plk_topk_candidates(1, 1, 0, 8, 1, 4, 4, 8, 100, 0, 1, 1, None, 0, None)
     assert rc == -1 and b"kc" in lib.plk_last_error()

@@ -23,8 +23,8 @@ def _free_port():
 def _patch():
     import _emul
     from multimodal_plankton_recognition_b200 import ann, ops
-    for name in ("l2norm", "infonce_fwd_local", "infonce_loss_local", "infonce_grad_pair_local",
-                 "infonce_grad_finish", "infonce_dls"):
+    for name in ("l2norm", "l2norm_pair", "infonce_fwd_local", "infonce_loss_local", "infonce_grad_pair_local",
+                 "infonce_grad_finish", "infonce_grad_finish_pair", "infonce_dls"):
         setattr(ops, name, getattr(_emul, name))
     ann.GpuExactIndex = _emul.CpuExactIndex
     ann.topk_merge_device = _emul.topk_merge_device
