@@ -13,7 +13,7 @@ import os
 
 import torch
 from torch import Tensor
-from torch.nn import Module, Parameter
+from torch.nn import Module, MSELoss, Parameter
 
 from . import ops
 
@@ -56,3 +56,19 @@ class CLIPLoss(Module):
 
     def extra_repr(self) -> str:
         return f"precision={self.precision}, sharded={self.sharded}"
+
+
+class CLIPPlus(Module):
+    """Drop-in for reference src/coordination.py:50-64: the fused InfoNCE term
+    plus ``beta`` times the MSE between the RAW embeddings.  The MSE term is one elementwise pass and
+    stays in PyTorch; parameter path ``clip.logit_scale`` matches the reference's checkpoints."""
+
+    def __init__(self, beta: float = 0.25, *, precision: str | None = None, sharded: bool = False,
+                 process_group=None) -> None:
+        super().__init__()
+        self.clip = CLIPLoss(precision=precision, sharded=sharded, process_group=process_group)
+        self.l2 = MSELoss()
+        self.beta = beta
+
+    def forward(self, image_emb: Tensor, profile_emb: Tensor, buckets: int = 1) -> Tensor:
+        return self.clip(image_emb, profile_emb, buckets) + self.beta * self.l2(image_emb, profile_emb)

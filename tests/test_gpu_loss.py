@@ -148,3 +148,22 @@ def test_error_behaviour():
     x = torch.randn(10, 8, device="cuda")
     with pytest.raises(AssertionError, match="divisible"):
         mod(image_emb=x, profile_emb=x, buckets=3)
+
+
+def test_clip_plus_matches_reference_formula():
+    """reference src/coordination.py:50-64: CLIPLoss + beta * MSE(raw embeddings); state-dict key clip.logit_scale."""
+    from multimodal_plankton_recognition_b200 import CLIPPlus
+    r = np.random.default_rng(2)
+    img = r.standard_normal((128, 96)).astype(np.float32)
+    pro = r.standard_normal((128, 96)).astype(np.float32)
+    mod = CLIPPlus(beta=0.25, precision="fp32").cuda()
+    assert list(mod.state_dict().keys()) == ["clip.logit_scale"]
+    x = torch.tensor(img, device="cuda", requires_grad=True)
+    y = torch.tensor(pro, device="cuda", requires_grad=True)
+    loss = mod(image_emb=x, profile_emb=y, buckets=2)
+    loss.backward()
+    ref = oinf.clip_loss_closed_form(img, pro, 1.0, 2)
+    mse = float(((img.astype(np.float64) - pro) ** 2).mean())
+    assert float(loss) == pytest.approx(ref["loss"] + 0.25 * mse, rel=1e-5)
+    gref = ref["d_image"] + 0.25 * 2 * (img.astype(np.float64) - pro) / img.size
+    assert _rel(x.grad.cpu().numpy(), gref) < 1e-5
