@@ -15,6 +15,7 @@
 //                     then a second tcgen05.mma  acc[128 x 64*c] += G . b_chunk  with the streamed
 //                     chunk reused as an MN-major B operand; acc (<= 256 fp32 columns) stays in TMEM
 //                     for the whole column sweep.
+#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace plk {
@@ -49,6 +50,73 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) 
       const float send = up ? v[i] : v[i + h];
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
     }
+  }
+}
+
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(p)));
+  return v;
+}
+
+// Backward epilogue for one 32-column chunk of a logits tile held one-row-per-thread:
+//   G = ex2(a*c1 + c0) * (1/rs_i + 1/cs_j)  -> packed 16-bit pairs (A operand of G.V).
+// The epilogue is instruction-issue bound (16 k elements per 128x128 tile against ~2 k cycles of
+// tensor work), so the common case -- chunk fully inside the row's bucket, no diagonal column, no
+// sum G*S wanted -- is a separate instantiation with 5.5 instructions per element; masks use
+// 32-bit chunk-relative bounds.
+template <bool F16, bool EDGE, bool GS>
+__device__ __forceinline__ void grad_chunk(const uint32_t (&raw)[32], uint32_t (&packed)[16],
+                                           const float* rc_smem, float rrs, float c1, float c0,
+                                           int lo_rel, int hi_rel, int dei, float& gs_local) {
+#pragma unroll
+  for (int e4 = 0; e4 < 8; ++e4) {
+    const float4 rc = lds_f4(rc_smem + e4 * 4);
+    const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
+    float gg[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const int e = e4 * 4 + x;
+      const float a = __uint_as_float(raw[e]);
+      float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
+      if constexpr (EDGE) G = (e >= lo_rel && e < hi_rel) ? G : 0.f;
+      if constexpr (GS) gs_local = fmaf(G, a, gs_local);
+      // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked softmax
+      // and nearly cancels against the -2*delta term): drop it from the 16-bit operand
+      if constexpr (EDGE) G = (e == dei) ? 0.f : G;
+      gg[x] = G;
+    }
+    packed[e4 * 2] = pack_16x2<F16>(gg[0], gg[1]);
+    packed[e4 * 2 + 1] = pack_16x2<F16>(gg[2], gg[3]);
+  }
+}
+
+// chunk-relative validity window [lo_rel, hi_rel) and diagonal position of a row for the 32 columns
+// starting at global column jc0 (all 32-bit)
+__device__ __forceinline__ void chunk_window(int64_t lo, int64_t hi, int64_t gi, int64_t jc0, int& lo_rel,
+                                             int& hi_rel, int& dei) {
+  const int64_t l = lo - jc0, h = hi - jc0, de = gi - jc0;
+  lo_rel = l < 0 ? 0 : (l > 32 ? 32 : (int)l);
+  hi_rel = h < 0 ? 0 : (h > 32 ? 32 : (int)h);
+  dei = (de >= 0 && de < 32) ? (int)de : -1;
+}
+
+template <bool F16>
+__device__ __forceinline__ void grad_chunk_dispatch(const uint32_t (&raw)[32], uint32_t (&packed)[16],
+                                                    const float* rc_smem, float rrs, float c1, float c0,
+                                                    int64_t lo, int64_t hi, int64_t gi, int64_t jc0,
+                                                    bool want_gs, float& gs_local) {
+  int lo_rel, hi_rel, dei;
+  chunk_window(lo, hi, gi, jc0, lo_rel, hi_rel, dei);
+  const bool plain = __all_sync(0xffffffffu, lo_rel == 0 && hi_rel == 32 && dei < 0);
+  if (plain) {
+    if (want_gs) grad_chunk<F16, false, true>(raw, packed, rc_smem, rrs, c1, c0, 0, 32, -1, gs_local);
+    else grad_chunk<F16, false, false>(raw, packed, rc_smem, rrs, c1, c0, 0, 32, -1, gs_local);
+  } else {
+    if (want_gs) grad_chunk<F16, true, true>(raw, packed, rc_smem, rrs, c1, c0, lo_rel, hi_rel, dei, gs_local);
+    else grad_chunk<F16, true, false>(raw, packed, rc_smem, rrs, c1, c0, lo_rel, hi_rel, dei, gs_local);
   }
 }
 
@@ -227,7 +295,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 // and a single prologue / drain.
 // =============================================================================================
 struct GradDir {
-  CUtensorMap ta, tb, tbp;   // owned rows (box 128), streamed rows (box 128), streamed rows (box 64, multicast)
+  CUtensorMap ta, tb, tbp, tbq;   // owned rows (box 128); streamed rows with box 128 / 64 / 32 rows
   const float* rs;           // sum-exp along the owned rows
   const float* cs;           // sum-exp along the streamed rows
   float* acc;                // [nseg][n_rows][d] partial accumulators
@@ -419,31 +487,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       tc_fence_before();
       mbar_arrive(bar_sempty + buf);
       uint32_t packed[16];
-      const int64_t de = gi - (j0 + cc * 32);
-      const int dei = (de >= 0 && de < 32) ? (int)de : -1;   // diagonal column inside this chunk
-      const float4* rc4 = reinterpret_cast<const float4*>(rcs_s + buf * 128 + cc * 32);
-#pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        const float4 rc = rc4[e4];
-        const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
-        float g[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int e = e4 * 4 + x;
-          const float a = __uint_as_float(raw[e]);
-          float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
-          if (!warp_full) {
-            const int64_t j = j0 + cc * 32 + e;
-            G = (j >= lo && j < hi) ? G : 0.f;
-          }
-          if (want_gs) gs_local = fmaf(G, a, gs_local);
-          // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked
-          // softmax and nearly cancels against the -2*delta term): drop it from the bf16 operand
-          g[x] = (e == dei) ? 0.f : G;
-        }
-        packed[e4 * 2] = pack_16x2<F16>(g[0], g[1]);
-        packed[e4 * 2 + 1] = pack_16x2<F16>(g[2], g[3]);
-      }
+      grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
+                               want_gs, gs_local);
       mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
       // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
       uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
@@ -674,29 +719,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       tmem_ld32(col0, raw);
       tmem_ld_wait();
       uint32_t packed[16];
-      const int64_t de = gi - (j0 + cc * 32);
-      const int dei = (de >= 0 && de < 32) ? (int)de : -1;   // diagonal column inside this chunk
-      const float4* rc4 = reinterpret_cast<const float4*>(rcs_s + buf * 128 + cc * 32);
-#pragma unroll
-      for (int e4 = 0; e4 < 8; ++e4) {
-        const float4 rc = rc4[e4];
-        const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
-        float g[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const int e = e4 * 4 + x;
-          const float a = __uint_as_float(raw[e]);
-          float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
-          if (!warp_full) {
-            const int64_t j = j0 + cc * 32 + e;
-            G = (j >= lo && j < hi) ? G : 0.f;
-          }
-          if (want_gs) gs_local = fmaf(G, a, gs_local);
-          g[x] = (e == dei) ? 0.f : G;   // the j == i term is added in fp32 by plk_infonce_grad_finish
-        }
-        packed[e4 * 2] = pack_16x2<F16>(g[0], g[1]);
-        packed[e4 * 2 + 1] = pack_16x2<F16>(g[2], g[3]);
-      }
+      grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
+                               want_gs, gs_local);
       // G overwrites the first 16 of this warp's own 32 logits columns (all 32 were read above)
       tmem_st16(col0, packed);
       tmem_st_wait();
@@ -708,6 +732,249 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     tc_fence_after();
 #pragma unroll 1
     for (int ch = cc; ch < 2 * KD; ch += 4) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+      tmem_ld_wait();
+      const int64_t col0 = (int64_t)ch * 32;
+      if (i < n_rows) {
+        float* dst = acc_out + i * d + col0;
+        if (col0 + 32 <= d && (d & 3) == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(dst + e) =
+                make_float4(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]),
+                            __uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (col0 + e < d) dst[e] = __uint_as_float(raw[e]);
+        }
+      }
+    }
+    if (want_gs) {
+      gs_local *= s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+      if (lane == 0) atomicAdd(g.gs, gs_local);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// =============================================================================================
+// backward, d <= 256, deep pipeline: 128 x 64 logits tiles, FOUR tile buffers in shared memory and
+// FOUR logits/G buffers in TMEM, two epilogue warp groups working on alternate tiles.  The tensor
+// pipe runs three S tiles ahead of the G.V of the oldest one, so the exp/pack latency of a tile
+// (~1.5-2 k cycles) overlaps the MMAs of its neighbours instead of stalling the issue stream
+// (the 2-buffer variant above spends half its time waiting on exactly that).
+//   MMA issue order: S(0) S(1) S(2) | GV(0) S(3) | GV(1) S(4) | ...
+// =============================================================================================
+template <int KD>
+struct Grad3Cfg {
+  static constexpr int kResident = KD * kChunkBytes;          // owned rows: [128 x 64] chunks
+  static constexpr int kYChunk = 64 * kChunkK * 2;            // streamed [64 x 64] chunk = 8 KiB
+  static constexpr int kTileBuf = KD * kYChunk;
+  static constexpr int kNB = 4;
+  static constexpr int kSmem = 1024 + kResident + kNB * kTileBuf + kAuxBytes;
+  static_assert(kSmem <= kMaxSmem, "deep-pipeline backward needs d <= 256");
+};
+
+template <int KD, int CS, bool F16>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc3(
+    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+    int64_t d, int64_t bs, int tiles_per_seg /* in 64-column tiles */, const float* __restrict__ ls) {
+  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
+  using Cfg = Grad3Cfg<KD>;
+  constexpr int DN = KD * 64;
+  constexpr int NB = Cfg::kNB;
+  constexpr int TN = 64;          // logits tile width
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_a = smem;
+  uint8_t* sm_y = smem + Cfg::kResident;                  // [NB][KD chunks of 8 KiB]
+  uint8_t* aux = sm_y + NB * Cfg::kTileBuf;
+  uint64_t* bar_a = reinterpret_cast<uint64_t*>(aux);     // [1]
+  uint64_t* bar_yfull = bar_a + 1;                        // [NB]
+  uint64_t* bar_yempty = bar_yfull + NB;                  // [NB]
+  uint64_t* bar_sfull = bar_yempty + NB;                  // [NB]
+  uint64_t* bar_gfull = bar_sfull + NB;                   // [NB]
+  uint64_t* bar_accfull = bar_gfull + NB;                 // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
+  float* rcs_s = reinterpret_cast<float*>(aux + 512);     // [2 groups][2][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
+  int64_t jlo = 0, jhi = n_cols;
+  if constexpr (CS == 1) row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const int total_tiles = (int)((jhi - jlo + TN - 1) / TN);
+  const int t_begin = blockIdx.x * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
+  float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
+  if (T == 0) {
+    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DN; e += kNumThreads) {
+      const int64_t rr = i0 + e / DN, col = e % DN;
+      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.ta);
+    tma_prefetch_desc(&g.tbp);
+    tma_prefetch_desc(&g.tbq);
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < NB; ++b) {
+      mbar_init(bar_yfull + b, 1);
+      mbar_init(bar_yempty + b, CS);
+      mbar_init(bar_sfull + b, 1);
+      mbar_init(bar_gfull + b, kEpiThreads / 2);
+    }
+    mbar_init(bar_accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kAccCol = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, Cfg::kResident);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &g.ta, bar_a, c * kChunkK, (int)i0);
+      for (int t = 0; t < T; ++t) {
+        const int b = t & (NB - 1);
+        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * TN);
+        mbar_wait(bar_yempty + b, ((t / NB) & 1) ^ 1);
+        mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
+        for (int c = 0; c < KD; ++c) {
+          uint8_t* slot = sm_y + (b * KD + c) * Cfg::kYChunk;
+          if constexpr (CS == 1) {
+            tma_load_2d(slot, &g.tbp, bar_yfull + b, c * kChunkK, j0);
+          } else {   // each CTA of the pair fetches 32 of the 64 rows and multicasts them to both
+            tma_load_2d_mc(slot + cta_rank * (Cfg::kYChunk / 2), &g.tbq, bar_yfull + b, c * kChunkK,
+                           j0 + (int)cta_rank * 32, (uint16_t)3);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_16(128, TN, 0, 0, F16);
+      constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A from TMEM (K-major), B MN-major
+      mbar_wait(bar_a, 0);
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
+      const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);                  // K-major view (S)
+      const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), Cfg::kYChunk);       // MN-major view, LBO = chunk
+      auto issue_s = [&](int t) {
+        const int b = t & (NB - 1);
+        mbar_wait(bar_yfull + b, (t / NB) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * TN;
+#pragma unroll
+        for (int c = 0; c < KD; ++c) {
+          const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
+          const uint32_t b_lo = y_lo0 + (b * KD + c) * (Cfg::kYChunk >> 4);
+#pragma unroll
+          for (int k = 0; k < kChunkK / kUmmaK; ++k)
+            umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
+        }
+        umma_commit(bar_sfull + b);
+      };
+      auto issue_gv = [&](int t) {
+        const int b = t & (NB - 1);
+        mbar_wait(bar_gfull + b, (t / NB) & 1);
+        tc_fence_after();
+        const uint32_t b_lo = y2_lo0 + b * KD * (Cfg::kYChunk >> 4);
+#pragma unroll
+        for (int k = 0; k < TN / kUmmaK; ++k) {
+          // A: packed G; K elements 32h..32h+31 live in columns 32h .. 32h+15 of logits buffer b
+          const uint32_t a_tmem = tmem_base + b * TN + (k >> 1) * 32 + (k & 1) * 8;
+          umma_bf16_ts(tmem_base + kAccCol, a_tmem, b_lo + k * (2048 >> 4), idesc_g, (t | k) != 0);
+        }
+        ring_release<CS>(bar_yempty + b);   // tile buffer b + logits buffer b are free once these retire
+      };
+      for (int t = 0; t < NB - 1 && t < T; ++t) issue_s(t);
+      for (int t = 0; t < T; ++t) {
+        issue_gv(t);
+        if (t + NB - 1 < T) issue_s(t + NB - 1);
+      }
+      umma_commit(bar_accfull);
+    }
+    __syncwarp();
+  } else {
+    // two epilogue groups of 8 warps (256 threads): group gq handles tiles t = gq, gq+2, ...
+    const int ew = warp - 2;
+    const int grp = ew >> 3;
+    const int q = warp & 3;                  // TMEM lane quadrant
+    const int half = (ew & 7) >> 2;          // which 32 of the tile's 64 columns
+    const int r = q * 32 + lane;
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    float rrs = 0.f;
+    if (i < n_rows) {
+      bucket_range(gi, bs, n_cols, lo, hi);
+      rrs = 1.0f / g.rs[i];
+    }
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = -c1;
+    const bool want_gs = g.gs != nullptr;
+    float gs_local = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    float* my_rcs = rcs_s + grp * 2 * TN;
+    const bool loader = (half == 0) && (r < TN);   // 64 threads per group stage 1/cs of a tile
+    float rc_next = 0.f;
+    if (loader && grp < T) {
+      const int64_t jc = jlo + (int64_t)(t_begin + grp) * TN + r;
+      my_rcs[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+    }
+    int it = 0;
+    for (int t = grp; t < T; t += 2, ++it) {
+      const int buf = t & (NB - 1);
+      const int pp = it & 1;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * TN;
+      named_barrier_sync(1 + grp, kEpiThreads / 2);   // my_rcs[pp] visible; group is done with its previous tile
+      if (loader && t + 2 < T) {
+        const int64_t jc = j0 + 2 * TN + r;
+        rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
+      }
+      mbar_wait(bar_sfull + buf, (t / NB) & 1);
+      tc_fence_after();
+      const int64_t jc0 = j0 + half * 32;
+      const bool full = (jc0 >= lo) && (jc0 + 32 <= hi);
+      const bool warp_full = __all_sync(0xffffffffu, full);
+      const uint32_t col0 = tmem_base + lane_addr + buf * TN + half * 32;
+      uint32_t raw[32];
+      tmem_ld32(col0, raw);
+      tmem_ld_wait();
+      uint32_t packed[16];
+      grad_chunk_dispatch<F16>(raw, packed, my_rcs + pp * TN + half * 32, rrs, c1, c0, lo, hi, gi, jc0, want_gs,
+                               gs_local);
+      // G overwrites the first 16 of this warp's own 32 logits columns (all 32 were read above)
+      tmem_st16(col0, packed);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_gfull + buf);
+      if (loader && t + 2 < T) my_rcs[(pp ^ 1) * TN + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+    }
+    mbar_wait(bar_accfull, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int ch = grp * 2 + half; ch < 2 * KD; ch += 4) {
       uint32_t raw[32];
       tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
       tmem_ld_wait();
@@ -855,6 +1122,22 @@ static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
   return PLK_OK;
 }
 
+template <int KD, int CS, bool F16>
+static int launch_grad3(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                        int64_t d, int64_t bs, int tps64, const float* ls, cudaStream_t st) {
+  auto kern = infonce_grad_tc3<KD, CS, F16>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad3Cfg<KD>::kSmem));
+    configured = true;
+  }
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), Grad3Cfg<KD>::kSmem, st, CS, ga, n_rows, row_offset,
+                         n_cols, d, bs, tps64, ls);
+  if (rc) return rc;
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
 // number of partial accumulators per direction for this shape (bf16 path); ndir = 1 or 2 directions per launch
 int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir) {
   const int64_t ld = ceil_div(d, kChunkK) * kChunkK;
@@ -870,6 +1153,7 @@ static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_
   if ((rc = make_tmap_bf16(&g.ta, a, n_rows, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&g.tb, b, n_cols, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&g.tbp, b, n_cols, ld, ld, kTileRows / 2))) return rc;
+  if ((rc = make_tmap_bf16(&g.tbq, b, n_cols, ld, ld, kTileRows / 4))) return rc;
   g.rs = rs; g.cs = cs; g.acc = acc; g.gs = gs;
   return PLK_OK;
 }
@@ -886,12 +1170,23 @@ static int grad_launch_16(const GradArgs& ga, int64_t ld, int64_t n_rows, int64_
   const int tps = (int)ceil_div(max_tiles, nseg);
   row_blocks = ceil_div(row_blocks, csz) * csz;
   dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
-  if (kd <= 4) {   // the streamed tile fits next to the resident rows: tile-buffer kernel, G in TMEM
+  static const int variant = [] { const char* e = getenv("PLK_GRAD_VARIANT"); return e ? atoi(e) : 3; }();
+  if (kd <= 4 && variant == 2) {   // 128-column tiles, two buffers
     switch (kd) {
 #define PLK_CASE2(KD)                                                                                   \
   case KD:                                                                                              \
-    return csz == 2 ? launch_grad2<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st)     \
+    return csz == 2 ? launch_grad2<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st) \
                     : launch_grad2<KD, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
+      PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
+#undef PLK_CASE2
+    }
+  }
+  if (kd <= 4) {   // the streamed tile fits next to the resident rows: deep-pipeline kernel, G in TMEM
+    switch (kd) {
+#define PLK_CASE2(KD)                                                                                   \
+  case KD:                                                                                              \
+    return csz == 2 ? launch_grad3<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps * 2, ls, st) \
+                    : launch_grad3<KD, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps * 2, ls, st);
       PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
 #undef PLK_CASE2
     }
