@@ -15,7 +15,6 @@
 //                     then a second tcgen05.mma  acc[128 x 64*c] += G . b_chunk  with the streamed
 //                     chunk reused as an MN-major B operand; acc (<= 256 fp32 columns) stays in TMEM
 //                     for the whole column sweep.
-#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace plk {
@@ -125,16 +124,17 @@ __device__ __forceinline__ void grad_chunk_dispatch(const uint32_t (&raw)[32], u
 // =============================================================================================
 template <int KD>
 struct FwdCfg {
-  static constexpr int kResident = KD * kChunkBytes;
-  static constexpr int kStagesMax = (kMaxSmem - 1024 - kAuxBytes - kResident) / kChunkBytes;
+  static constexpr int kCPS = (KD % 2 == 0) ? 2 : 1;             // 64-wide K chunks per ring stage
+  static constexpr int kStageBytes = kCPS * kChunkBytes;
+  static constexpr int kStagesMax = (kMaxSmem - 1024 - kAuxBytes) / kStageBytes;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
-  static constexpr int kSmem = 1024 + kResident + kStages * kChunkBytes + kAuxBytes;
+  static constexpr int kSmem = 1024 + kStages * kStageBytes + kAuxBytes;
   static_assert(kStages >= 2, "not enough shared memory for the ring");
 };
 
 template <int KD, int CS>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
-    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+    const uint16_t* __restrict__ a_op, int64_t lda, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_bp, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tiles_per_seg,
     const float* __restrict__ ls, float* __restrict__ row_sumexp, float* __restrict__ col_sumexp,
     float* __restrict__ diag, int f16) {
@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sm_a = smem;
-  uint8_t* sm_ring = smem + Cfg::kResident;
-  uint8_t* aux = sm_ring + NST * kChunkBytes;
+  constexpr int CPS = Cfg::kCPS;
+  uint8_t* sm_ring = smem;
+  uint8_t* aux = sm_ring + NST * Cfg::kStageBytes;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);  // [NST]
   uint64_t* bar_empty = bar_full + NST;                   // [NST]
   uint64_t* bar_a = bar_empty + NST;                      // [1]
@@ -165,14 +165,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
-    mbar_init(bar_a, 1);
+    mbar_init(bar_a, kEpiThreads);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
@@ -181,14 +180,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_a, Cfg::kResident);
-      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &tmap_a, bar_a, c * kChunkK, (int)i0);
       int st = 0; uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
-        for (int c = 0; c < KD; ++c) {
+        for (int c = 0; c < KD; c += CPS) {
           mbar_wait(bar_empty + st, ph ^ 1);
-          ring_load<CS>(sm_ring + st * kChunkBytes, &tmap_b, &tmap_bp, bar_full + st, c * kChunkK, j0, cta_rank);
+          mbar_expect_tx(bar_full + st, Cfg::kStageBytes);
+#pragma unroll
+          for (int cs = 0; cs < CPS; ++cs)
+            chunk_load<CS>(sm_ring + st * Cfg::kStageBytes + cs * kChunkBytes, &tmap_b, &tmap_bp, bar_full + st,
+                           (c + cs) * kChunkK, j0, cta_rank);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
@@ -197,22 +198,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
-      mbar_wait(bar_a, 0);
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
+      mbar_wait(bar_a, 0);     // the epilogue warps have parked the owned rows in TMEM (columns 256..)
+      tc_fence_after();
+      const uint32_t a_tmem0 = tmem_base + 256;
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
         mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 128;
-        for (int c = 0; c < KD; ++c) {
+        for (int c = 0; c < KD; c += CPS) {
           mbar_wait(bar_full + st, ph);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
-          const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
+          const uint32_t b_lo = b_lo0 + st * (Cfg::kStageBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kChunkK / kUmmaK; ++k)   // 32 bytes (>>4 = 2) per K step inside the swizzle row
-            umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (c | k) != 0);
+          for (int cs = 0; cs < CPS; ++cs)
+#pragma unroll
+            for (int k = 0; k < kChunkK / kUmmaK; ++k)   // A: 8 packed TMEM columns per K step; B: 32 bytes
+              umma_bf16_ts(d_tmem, a_tmem0 + (c + cs) * 32 + k * 8, b_lo + cs * (kChunkBytes >> 4) + 2 * k, idesc,
+                           (c | cs | k) != 0);
           ring_release<CS>(bar_empty + st);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
@@ -232,6 +237,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     const float s = expf(*ls);
     const float c1 = s * kLog2e, c0 = -c1;
     float rsum = 0.f;
+    {  // park this thread's owned row (16-bit operand, padded to KD*64) in TMEM columns 256.. as packed
+       // pairs -- the A operand of the TS-mode MMA; the four warps of a lane quadrant take alternate chunks
+      const uint4* arow = reinterpret_cast<const uint4*>(a_op + i * lda);
+      for (int c = cc; c < KD; c += 4) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) {
+          uint4 w = make_uint4(0u, 0u, 0u, 0u);
+          if (i < n_rows) w = arow[c * 8 + v4];
+          pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
+        }
+        tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + 256 + c * 32, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+    }
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows + cc * 32;   // first column of this chunk
@@ -285,7 +307,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -295,7 +317,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 // and a single prologue / drain.
 // =============================================================================================
 struct GradDir {
-  CUtensorMap ta, tb, tbp, tbq;   // owned rows (box 128); streamed rows with box 128 / 64 / 32 rows
+  CUtensorMap ta, tb, tbp;   // owned rows (box 128), streamed rows (box 128), streamed rows (box 64, multicast)
   const float* rs;           // sum-exp along the owned rows
   const float* cs;           // sum-exp along the streamed rows
   float* acc;                // [nseg][n_rows][d] partial accumulators
@@ -769,248 +791,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
 
 
 // =============================================================================================
-// backward, d <= 256, deep pipeline: 128 x 64 logits tiles, FOUR tile buffers in shared memory and
-// FOUR logits/G buffers in TMEM, two epilogue warp groups working on alternate tiles.  The tensor
-// pipe runs three S tiles ahead of the G.V of the oldest one, so the exp/pack latency of a tile
-// (~1.5-2 k cycles) overlaps the MMAs of its neighbours instead of stalling the issue stream
-// (the 2-buffer variant above spends half its time waiting on exactly that).
-//   MMA issue order: S(0) S(1) S(2) | GV(0) S(3) | GV(1) S(4) | ...
-// =============================================================================================
-template <int KD>
-struct Grad3Cfg {
-  static constexpr int kResident = KD * kChunkBytes;          // owned rows: [128 x 64] chunks
-  static constexpr int kYChunk = 64 * kChunkK * 2;            // streamed [64 x 64] chunk = 8 KiB
-  static constexpr int kTileBuf = KD * kYChunk;
-  static constexpr int kNB = 4;
-  static constexpr int kSmem = 1024 + kResident + kNB * kTileBuf + kAuxBytes;
-  static_assert(kSmem <= kMaxSmem, "deep-pipeline backward needs d <= 256");
-};
-
-template <int KD, int CS, bool F16>
-__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc3(
-    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
-    int64_t d, int64_t bs, int tiles_per_seg /* in 64-column tiles */, const float* __restrict__ ls) {
-  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
-  using Cfg = Grad3Cfg<KD>;
-  constexpr int DN = KD * 64;
-  constexpr int NB = Cfg::kNB;
-  constexpr int TN = 64;          // logits tile width
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sm_a = smem;
-  uint8_t* sm_y = smem + Cfg::kResident;                  // [NB][KD chunks of 8 KiB]
-  uint8_t* aux = sm_y + NB * Cfg::kTileBuf;
-  uint64_t* bar_a = reinterpret_cast<uint64_t*>(aux);     // [1]
-  uint64_t* bar_yfull = bar_a + 1;                        // [NB]
-  uint64_t* bar_yempty = bar_yfull + NB;                  // [NB]
-  uint64_t* bar_sfull = bar_yempty + NB;                  // [NB]
-  uint64_t* bar_gfull = bar_sfull + NB;                   // [NB]
-  uint64_t* bar_accfull = bar_gfull + NB;                 // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
-  float* rcs_s = reinterpret_cast<float*>(aux + 512);     // [2 groups][2][64]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
-  int64_t jlo = 0, jhi = n_cols;
-  if constexpr (CS == 1) row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
-  const int total_tiles = (int)((jhi - jlo + TN - 1) / TN);
-  const int t_begin = blockIdx.x * tiles_per_seg;
-  int t_end = t_begin + tiles_per_seg;
-  if (t_end > total_tiles) t_end = total_tiles;
-  const int T = t_end > t_begin ? t_end - t_begin : 0;
-  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
-  float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
-  if (T == 0) {
-    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DN; e += kNumThreads) {
-      const int64_t rr = i0 + e / DN, col = e % DN;
-      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
-    }
-    return;
-  }
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&g.ta);
-    tma_prefetch_desc(&g.tbp);
-    tma_prefetch_desc(&g.tbq);
-    mbar_init(bar_a, 1);
-    for (int b = 0; b < NB; ++b) {
-      mbar_init(bar_yfull + b, 1);
-      mbar_init(bar_yempty + b, CS);
-      mbar_init(bar_sfull + b, 1);
-      mbar_init(bar_gfull + b, kEpiThreads / 2);
-    }
-    mbar_init(bar_accfull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kAccCol = 256;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(bar_a, Cfg::kResident);
-      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &g.ta, bar_a, c * kChunkK, (int)i0);
-      for (int t = 0; t < T; ++t) {
-        const int b = t & (NB - 1);
-        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * TN);
-        mbar_wait(bar_yempty + b, ((t / NB) & 1) ^ 1);
-        mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
-        for (int c = 0; c < KD; ++c) {
-          uint8_t* slot = sm_y + (b * KD + c) * Cfg::kYChunk;
-          if constexpr (CS == 1) {
-            tma_load_2d(slot, &g.tbp, bar_yfull + b, c * kChunkK, j0);
-          } else {   // each CTA of the pair fetches 32 of the 64 rows and multicasts them to both
-            tma_load_2d_mc(slot + cta_rank * (Cfg::kYChunk / 2), &g.tbq, bar_yfull + b, c * kChunkK,
-                           j0 + (int)cta_rank * 32, (uint16_t)3);
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_16(128, TN, 0, 0, F16);
-      constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A from TMEM (K-major), B MN-major
-      mbar_wait(bar_a, 0);
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
-      const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);                  // K-major view (S)
-      const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), Cfg::kYChunk);       // MN-major view, LBO = chunk
-      auto issue_s = [&](int t) {
-        const int b = t & (NB - 1);
-        mbar_wait(bar_yfull + b, (t / NB) & 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + b * TN;
-#pragma unroll
-        for (int c = 0; c < KD; ++c) {
-          const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
-          const uint32_t b_lo = y_lo0 + (b * KD + c) * (Cfg::kYChunk >> 4);
-#pragma unroll
-          for (int k = 0; k < kChunkK / kUmmaK; ++k)
-            umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
-        }
-        umma_commit(bar_sfull + b);
-      };
-      auto issue_gv = [&](int t) {
-        const int b = t & (NB - 1);
-        mbar_wait(bar_gfull + b, (t / NB) & 1);
-        tc_fence_after();
-        const uint32_t b_lo = y2_lo0 + b * KD * (Cfg::kYChunk >> 4);
-#pragma unroll
-        for (int k = 0; k < TN / kUmmaK; ++k) {
-          // A: packed G; K elements 32h..32h+31 live in columns 32h .. 32h+15 of logits buffer b
-          const uint32_t a_tmem = tmem_base + b * TN + (k >> 1) * 32 + (k & 1) * 8;
-          umma_bf16_ts(tmem_base + kAccCol, a_tmem, b_lo + k * (2048 >> 4), idesc_g, (t | k) != 0);
-        }
-        ring_release<CS>(bar_yempty + b);   // tile buffer b + logits buffer b are free once these retire
-      };
-      for (int t = 0; t < NB - 1 && t < T; ++t) issue_s(t);
-      for (int t = 0; t < T; ++t) {
-        issue_gv(t);
-        if (t + NB - 1 < T) issue_s(t + NB - 1);
-      }
-      umma_commit(bar_accfull);
-    }
-    __syncwarp();
-  } else {
-    // two epilogue groups of 8 warps (256 threads): group gq handles tiles t = gq, gq+2, ...
-    const int ew = warp - 2;
-    const int grp = ew >> 3;
-    const int q = warp & 3;                  // TMEM lane quadrant
-    const int half = (ew & 7) >> 2;          // which 32 of the tile's 64 columns
-    const int r = q * 32 + lane;
-    const int64_t i = i0 + r;
-    const int64_t gi = row_offset + i;
-    int64_t lo = 0, hi = 0;
-    float rrs = 0.f;
-    if (i < n_rows) {
-      bucket_range(gi, bs, n_cols, lo, hi);
-      rrs = 1.0f / g.rs[i];
-    }
-    const float s = expf(*ls);
-    const float c1 = s * kLog2e, c0 = -c1;
-    const bool want_gs = g.gs != nullptr;
-    float gs_local = 0.f;
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    float* my_rcs = rcs_s + grp * 2 * TN;
-    const bool loader = (half == 0) && (r < TN);   // 64 threads per group stage 1/cs of a tile
-    float rc_next = 0.f;
-    if (loader && grp < T) {
-      const int64_t jc = jlo + (int64_t)(t_begin + grp) * TN + r;
-      my_rcs[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
-    }
-    int it = 0;
-    for (int t = grp; t < T; t += 2, ++it) {
-      const int buf = t & (NB - 1);
-      const int pp = it & 1;
-      const int64_t j0 = jlo + (int64_t)(t_begin + t) * TN;
-      named_barrier_sync(1 + grp, kEpiThreads / 2);   // my_rcs[pp] visible; group is done with its previous tile
-      if (loader && t + 2 < T) {
-        const int64_t jc = j0 + 2 * TN + r;
-        rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
-      }
-      mbar_wait(bar_sfull + buf, (t / NB) & 1);
-      tc_fence_after();
-      const int64_t jc0 = j0 + half * 32;
-      const bool full = (jc0 >= lo) && (jc0 + 32 <= hi);
-      const bool warp_full = __all_sync(0xffffffffu, full);
-      const uint32_t col0 = tmem_base + lane_addr + buf * TN + half * 32;
-      uint32_t raw[32];
-      tmem_ld32(col0, raw);
-      tmem_ld_wait();
-      uint32_t packed[16];
-      grad_chunk_dispatch<F16>(raw, packed, my_rcs + pp * TN + half * 32, rrs, c1, c0, lo, hi, gi, jc0, want_gs,
-                               gs_local);
-      // G overwrites the first 16 of this warp's own 32 logits columns (all 32 were read above)
-      tmem_st16(col0, packed);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(bar_gfull + buf);
-      if (loader && t + 2 < T) my_rcs[(pp ^ 1) * TN + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
-    }
-    mbar_wait(bar_accfull, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int ch = grp * 2 + half; ch < 2 * KD; ch += 4) {
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
-      tmem_ld_wait();
-      const int64_t col0 = (int64_t)ch * 32;
-      if (i < n_rows) {
-        float* dst = acc_out + i * d + col0;
-        if (col0 + 32 <= d && (d & 3) == 0) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<float4*>(dst + e) =
-                make_float4(__uint_as_float(raw[e]), __uint_as_float(raw[e + 1]),
-                            __uint_as_float(raw[e + 2]), __uint_as_float(raw[e + 3]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (col0 + e < d) dst[e] = __uint_as_float(raw[e]);
-        }
-      }
-    }
-    if (want_gs) {
-      gs_local *= s;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
-      if (lane == 0) atomicAdd(g.gs, gs_local);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
-
-// =============================================================================================
 // host launchers
 // =============================================================================================
 // widest column range [jlo, jhi) a 128-row block can need: the union of the buckets its rows touch
@@ -1043,7 +823,7 @@ static int pick_cluster(int64_t row_blocks, int64_t bs, int64_t n_cols) {
 }
 
 template <int KD, int CS>
-static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
+static int launch_fwd(const void* a_op, int64_t lda, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
                       int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tps,
                       const float* ls, float* rsum, float* csum, float* diag, int f16, cudaStream_t st) {
   auto kern = infonce_fwd_tc<KD, CS>;
@@ -1052,7 +832,7 @@ static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<KD>::kSmem));
     configured = true;
   }
-  int rc = launch_kernel(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, ta, tb, tbp, n_rows,
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, (const uint16_t*)a_op, lda, tb, tbp, n_rows,
                          row_offset, n_cols, bs, tps, ls, rsum, csum, diag, f16);
   if (rc) return rc;
   PLK_LAUNCHED(1);
@@ -1066,8 +846,8 @@ int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t 
   if (rc) return rc;
   int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int cs = pick_cluster(row_blocks, bs, n_cols);
-  CUtensorMap ta, tb, tbp;
-  if ((rc = make_tmap_bf16(&ta, u, n_rows, ld, ld, kTileRows))) return rc;
+  PLK_REQUIRE(((uintptr_t)u & 15) == 0, PLK_ERR_INVALID, "operand must be 16-byte aligned");
+  CUtensorMap tb, tbp;
   if ((rc = make_tmap_bf16(&tb, v, n_cols, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tbp, v, n_cols, ld, ld, kTileRows / 2))) return rc;
   // sums are accumulated with atomics -> zero first; diag needs no init (every owned row has its
@@ -1081,8 +861,8 @@ int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t 
   switch (ld / kChunkK) {
 #define PLK_CASE(KD)                                                                                         \
   case KD:                                                                                                   \
-    return cs == 2 ? launch_fwd<KD, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st) \
-                   : launch_fwd<KD, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st);
+    return cs == 2 ? launch_fwd<KD, 2>(u, ld, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st) \
+                   : launch_fwd<KD, 1>(u, ld, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st);
     PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
   }
@@ -1122,22 +902,6 @@ static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
   return PLK_OK;
 }
 
-template <int KD, int CS, bool F16>
-static int launch_grad3(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
-                        int64_t d, int64_t bs, int tps64, const float* ls, cudaStream_t st) {
-  auto kern = infonce_grad_tc3<KD, CS, F16>;
-  static bool configured = false;
-  if (!configured) {
-    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad3Cfg<KD>::kSmem));
-    configured = true;
-  }
-  int rc = launch_kernel(kern, grid, dim3(kNumThreads), Grad3Cfg<KD>::kSmem, st, CS, ga, n_rows, row_offset,
-                         n_cols, d, bs, tps64, ls);
-  if (rc) return rc;
-  PLK_LAUNCHED(1);
-  return PLK_OK;
-}
-
 // number of partial accumulators per direction for this shape (bf16 path); ndir = 1 or 2 directions per launch
 int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir) {
   const int64_t ld = ceil_div(d, kChunkK) * kChunkK;
@@ -1153,7 +917,6 @@ static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_
   if ((rc = make_tmap_bf16(&g.ta, a, n_rows, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&g.tb, b, n_cols, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&g.tbp, b, n_cols, ld, ld, kTileRows / 2))) return rc;
-  if ((rc = make_tmap_bf16(&g.tbq, b, n_cols, ld, ld, kTileRows / 4))) return rc;
   g.rs = rs; g.cs = cs; g.acc = acc; g.gs = gs;
   return PLK_OK;
 }
@@ -1170,23 +933,12 @@ static int grad_launch_16(const GradArgs& ga, int64_t ld, int64_t n_rows, int64_
   const int tps = (int)ceil_div(max_tiles, nseg);
   row_blocks = ceil_div(row_blocks, csz) * csz;
   dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
-  static const int variant = [] { const char* e = getenv("PLK_GRAD_VARIANT"); return e ? atoi(e) : 3; }();
-  if (kd <= 4 && variant == 2) {   // 128-column tiles, two buffers
+  if (kd <= 4) {   // the streamed tile fits next to the resident rows: tile-buffer kernel, G in TMEM
     switch (kd) {
 #define PLK_CASE2(KD)                                                                                   \
   case KD:                                                                                              \
     return csz == 2 ? launch_grad2<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st) \
                     : launch_grad2<KD, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
-      PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
-#undef PLK_CASE2
-    }
-  }
-  if (kd <= 4) {   // the streamed tile fits next to the resident rows: deep-pipeline kernel, G in TMEM
-    switch (kd) {
-#define PLK_CASE2(KD)                                                                                   \
-  case KD:                                                                                              \
-    return csz == 2 ? launch_grad3<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps * 2, ls, st) \
-                    : launch_grad3<KD, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps * 2, ls, st);
       PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
 #undef PLK_CASE2
     }

@@ -1,6 +1,11 @@
 // tcgen05 (sm_100a) path of the k-nearest candidate search.
-// Same mainloop as the InfoNCE forward (128 resident query rows, gallery streamed as [128 x 64]
-// bf16 TMA chunks, double-buffered 128x128 fp32 score tiles in TMEM); the epilogue keeps, per
+// The 128 query rows of a CTA live in TENSOR MEMORY (packed 16-bit pairs, written once by the
+// epilogue warps with tcgen05.st) and are the A operand of a TS-mode tcgen05.mma: an SS-mode
+// 128x128x16 MMA reads 8 KiB of operands from shared memory per 64 cycles, i.e. all of the
+// shared-memory bandwidth, and the TMA refill of the ring on top of that capped the mainloop at
+// ~65 % of tensor peak; with A in TMEM only the streamed gallery chunks touch shared memory.
+// Gallery streamed as [128 x 64] TMA chunks through a deep ring (cluster-multicast), double-
+// buffered 128x128 fp32 score tiles in TMEM; the epilogue keeps, per
 // thread (= per query row x 64 of the tile's 128 columns), a sorted list of the KC smallest keys
 // |g|^2 - 2 q.g.  The common case is one FFMA + one FMNMX per score and a single compare of the
 // 32-column minimum against the current KC-th best; the insertion code exists once (not inlined,
@@ -17,10 +22,12 @@ constexpr int kTkAux = 4096;
 
 template <int KD>
 struct TopkCfg {
-  static constexpr int kResident = KD * kChunkBytes;
-  static constexpr int kStagesMax = (kMaxSmem - 1024 - kTkAux - kResident) / kChunkBytes;
+  static constexpr int kCPS = (KD % 2 == 0) ? 2 : 1;             // 64-wide K chunks per ring stage
+  static constexpr int kStageBytes = kCPS * kChunkBytes;         // one barrier round trip per 8 (or 4) MMAs
+  static constexpr int kStagesMax = (kMaxSmem - 1024 - kTkAux) / kStageBytes;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
-  static constexpr int kSmem = 1024 + kResident + kStages * kChunkBytes + kTkAux;
+  static constexpr int kSmem = 1024 + kStages * kStageBytes + kTkAux;
+  static constexpr int kACols = KD * 32;   // packed query rows: 64 elements = 32 TMEM columns per chunk
   static_assert(kStages >= 2, "not enough shared memory for the ring");
 };
 
@@ -43,16 +50,16 @@ __device__ __forceinline__ void list_insert(float (&bk)[KC], int32_t (&bi)[KC], 
 
 template <int KD, int KC, int CS>
 __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
-    const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+    const uint16_t* __restrict__ q_op, int64_t ldq, const __grid_constant__ CUtensorMap tmap_g,
     const __grid_constant__ CUtensorMap tmap_gp, const float* __restrict__ g_sqn, int64_t nq, int64_t ng, int64_t goff, int tiles_per_chunk,
     int nchunks, int kc_out, int32_t* __restrict__ out_idx, float* __restrict__ out_key, int f16) {
   using Cfg = TopkCfg<KD>;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sm_a = smem;
-  uint8_t* sm_ring = smem + Cfg::kResident;
-  uint8_t* aux = sm_ring + NST * kChunkBytes;
+  uint8_t* sm_ring = smem;
+  constexpr int CPS = Cfg::kCPS;
+  uint8_t* aux = sm_ring + NST * Cfg::kStageBytes;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);
   uint64_t* bar_empty = bar_full + NST;
   uint64_t* bar_a = bar_empty + NST;
@@ -82,14 +89,13 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   }
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_g);
     for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
-    mbar_init(bar_a, 1);
+    mbar_init(bar_a, kTkEpi);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kTkEpi); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();
@@ -99,14 +105,16 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_a, Cfg::kResident);
-      for (int c = 0; c < KD; ++c) tma_load_2d(sm_a + c * kChunkBytes, &tmap_q, bar_a, c * kChunkK, (int)q0);
       int st = 0; uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         const int j0 = (t_begin + t) * kTileRows;
-        for (int c = 0; c < KD; ++c) {
+        for (int c = 0; c < KD; c += CPS) {
           mbar_wait(bar_empty + st, ph ^ 1);
-          ring_load<CS>(sm_ring + st * kChunkBytes, &tmap_g, &tmap_gp, bar_full + st, c * kChunkK, j0, cta_rank);
+          mbar_expect_tx(bar_full + st, Cfg::kStageBytes);
+#pragma unroll
+          for (int cs = 0; cs < CPS; ++cs)
+            chunk_load<CS>(sm_ring + st * Cfg::kStageBytes + cs * kChunkBytes, &tmap_g, &tmap_gp, bar_full + st,
+                           (c + cs) * kChunkK, j0, cta_rank);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
@@ -115,22 +123,26 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
-      mbar_wait(bar_a, 0);
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
+      mbar_wait(bar_a, 0);     // the epilogue warps have parked the query rows in TMEM
+      tc_fence_after();
+      const uint32_t a_tmem0 = tmem_base + 256;
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         const int buf = t & 1;
         mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * 128;
-        for (int c = 0; c < KD; ++c) {
+        for (int c = 0; c < KD; c += CPS) {
           mbar_wait(bar_full + st, ph);
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
-          const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
+          const uint32_t b_lo = b_lo0 + st * (Cfg::kStageBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kChunkK / kUmmaK; ++k)   // 32 bytes (>>4 = 2) per K step inside the swizzle row
-            umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (c | k) != 0);
+          for (int cs = 0; cs < CPS; ++cs)
+#pragma unroll
+            for (int k = 0; k < kChunkK / kUmmaK; ++k)   // A: 8 packed columns per K step; B: 32 bytes (>>4 = 2)
+              umma_bf16_ts(d_tmem, a_tmem0 + (c + cs) * 32 + k * 8, b_lo + cs * (kChunkBytes >> 4) + 2 * k, idesc,
+                           (c | cs | k) != 0);
           ring_release<CS>(bar_empty + st);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
@@ -149,6 +161,23 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     for (int e = 0; e < KC; ++e) { bk[e] = CUDART_INF_F; bi[e] = -1; }
     float thresh = CUDART_INF_F;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    {  // park this thread's query row (16-bit operand, padded to KD*64) in TMEM columns 256.. as packed pairs;
+       // the two warps of a lane quadrant take alternate 64-element chunks
+      const uint4* qrow = reinterpret_cast<const uint4*>(q_op + qi * ldq);
+      for (int c = half; c < KD; c += 2) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) {
+          uint4 w = make_uint4(0u, 0u, 0u, 0u);
+          if (qi < nq) w = qrow[c * 8 + v4];
+          pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
+        }
+        tmem_st32(tmem_base + lane_addr + 256 + c * 32, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+    }
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = (int64_t)(t_begin + t) * kTileRows;
@@ -213,7 +242,7 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   if constexpr (CS > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -242,7 +271,7 @@ size_t topk_ws_tc16(int64_t nq, int64_t ng, int64_t d, int kc) {
 }
 
 template <int KD, int KC, int CS>
-static int launch_topk(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tgp, dim3 grid,
+static int launch_topk(const void* q, int64_t ldq, const CUtensorMap& tg, const CUtensorMap& tgp, dim3 grid,
                        const float* g_sqn, int64_t nq, int64_t ng, int64_t goff, int tpc, int nchunks,
                        int kc, int32_t* o_idx, float* o_key, int f16, cudaStream_t st) {
   auto kern = topk_tc_kernel<KD, KC, CS>;
@@ -251,7 +280,7 @@ static int launch_topk(const CUtensorMap& tq, const CUtensorMap& tg, const CUten
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TopkCfg<KD>::kSmem));
     configured = true;
   }
-  int rc = launch_kernel(kern, grid, dim3(kTkThreads), TopkCfg<KD>::kSmem, st, CS, tq, tg, tgp, g_sqn, nq, ng,
+  int rc = launch_kernel(kern, grid, dim3(kTkThreads), TopkCfg<KD>::kSmem, st, CS, (const uint16_t*)q, ldq, tg, tgp, g_sqn, nq, ng,
                          goff, tpc, nchunks, kc, o_idx, o_key, f16);
   if (rc) return rc;
   PLK_LAUNCHED(1);
@@ -268,8 +297,8 @@ int topk_candidates_tc16(const void* q, const void* g, int f16, int64_t ld,
   PLK_REQUIRE(kc <= 32, PLK_ERR_UNSUPPORTED, "tensor-core path keeps at most 32 candidates per query (got %d)", kc);
   PLK_REQUIRE(plk_device_supports_tc(), PLK_ERR_ARCH, "the tensor-core path needs an sm_100 device");
   int rc;
-  CUtensorMap tq, tg, tgp;
-  if ((rc = make_tmap_bf16(&tq, q, nq, ld, ld, kTileRows))) return rc;
+  PLK_REQUIRE(((uintptr_t)q & 15) == 0, PLK_ERR_INVALID, "query operand must be 16-byte aligned");
+  CUtensorMap tg, tgp;
   if ((rc = make_tmap_bf16(&tg, g, ng, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tgp, g, ng, ld, ld, kTileRows / 2))) return rc;
   const int nchunks = topk_bf16_chunks(nq, ng);
@@ -282,7 +311,7 @@ int topk_candidates_tc16(const void* q, const void* g, int f16, int64_t ld,
   dim3 grid((unsigned)nchunks, (unsigned)qblocks, 1);
   const int kd = (int)(ld / kChunkK);
   rc = PLK_ERR_UNSUPPORTED;
-#define PLK_TK(KD, KC, CS) launch_topk<KD, KC, CS>(tq, tg, tgp, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, f16, st)
+#define PLK_TK(KD, KC, CS) launch_topk<KD, KC, CS>(q, ld, tg, tgp, grid, g_sqn, nq, ng, goff, tpc, nchunks, kc, o_idx, o_key, f16, st)
 #define PLK_CASE(KD)                                                              \
   case KD:                                                                        \
     rc = kc <= 16 ? (cs == 2 ? PLK_TK(KD, 16, 2) : PLK_TK(KD, 16, 1))              \
