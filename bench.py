@@ -212,16 +212,25 @@ def main():
     go = torch.ones(1, device=dev)
 
     # ---- value: the whole fwd+bwd step, inputs resident in HBM, captured in a CUDA graph ----
+    xg = None
     if world == 1:
         def raw_step():
             loss, u, v, stats, dsum = ops.clip_loss_fwd(img, pro, ls, 1, mode)
             return (loss,) + tuple(ops.clip_loss_bwd(go, img, pro, ls, u, v, stats, dsum, 1, mode))
     else:
-        # bucket-aligned sharding: the data path has no exchange; the two scalar all-reduces (loss,
-        # d logit_scale) are issued eagerly right after the replayed graph, inside the timed region
+        # bucket-aligned sharding: the data path has no exchange; the two per-rank scalars (loss,
+        # d logit_scale) are summed over the ranks INSIDE the gradient-tail kernel through NVLink peer
+        # memory (plk_infonce_grad_finish_pair_xgpu), so the replayed graph is the whole step.
+        if os.environ.get("PLK_BENCH_NCCL_SCALARS", "0") != "1":
+            try:
+                xg = pdist.XGpuScalars(dev)
+            except Exception as e:      # no symmetric memory on this box: fall back to one NCCL all-reduce
+                if rank == 0:
+                    print(f"bench: symmetric memory unavailable ({e!r}); using NCCL for the scalars", file=sys.stderr)
+
         def raw_step():
             loss, state = pdist.sharded_fwd(img, pro, ls, world, mode, None, reduce_scalars=False)
-            return (state[-2],) + tuple(pdist.sharded_bwd(state, go, "ddp", reduce_scalars=False))
+            return (state[-2],) + tuple(pdist.sharded_bwd(state, go, "ddp", reduce_scalars=False, xgpu=xg))
 
     raw_step()
     torch.cuda.synchronize()
@@ -238,7 +247,7 @@ def main():
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
         outs = raw_step()
-    if world == 1:
+    if world == 1 or xg is not None:
         step_fn = graph.replay
     else:
         def step_fn():
@@ -308,7 +317,9 @@ def main():
             "global_batch": Bg, "d": d, "buckets": world, "logit_scale": 1.0,
             "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
             "timed_path": "CUDA-graph replay of clip_loss_fwd + clip_loss_bwd" if world == 1
-                          else "CUDA-graph replay of dist.sharded_fwd + dist.sharded_bwd, then one NCCL all-reduce of (loss, d logit_scale) (eager)",
+                          else ("CUDA-graph replay of dist.sharded_fwd + dist.sharded_bwd; the (loss, d logit_scale) sum over ranks is "
+                                "fused into the gradient-tail kernel (NVLink peer memory)" if xg is not None else
+                                "CUDA-graph replay of dist.sharded_fwd + dist.sharded_bwd, then one NCCL all-reduce of (loss, d logit_scale)"),
             "parallelism": f"dp{world}"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 2 * n * d * 4, "d2h_bytes_per_step": 4},

@@ -166,6 +166,26 @@ int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int par
                                  const float* diag_sum, float* dx, float* dy, float* dls_out,
                                  void* stream);
 
+/* Same, for a rank of a sharded step, with the cross-GPU sum of (loss partial, d logit_scale
+ * partial) fused into the kernel: the ranks exchange the two scalars through peer-mapped symmetric
+ * memory over NVLink (release/acquire flags), replacing a separate NCCL all-reduce launch.
+ *   loss_partial  this rank's loss partial (from plk_infonce_loss)
+ *   peer_bufs     DEVICE array [world] of peer-mapped base pointers of one >= 128-byte,
+ *                 zero-initialised symmetric buffer per rank (same order on every rank)
+ *   epoch         local device counter (zero-initialised once; incremented per launch)
+ *   out2          OUT (global loss, global d logit_scale), bitwise identical on every rank
+ * All ranks must launch it the same number of times (it waits for every peer, bounded by a trap). */
+int plk_infonce_grad_finish_pair_xgpu(const float* acc_x, const float* acc_y, int parts,
+                                      const float* x, const float* y, int64_t n, int64_t d, int64_t ldx,
+                                      const float* inv_den_x, const float* nrm_x,
+                                      const float* inv_den_y, const float* nrm_y,
+                                      const float* diag, const float* rs, const float* cs,
+                                      const float* logit_scale, const float* grad_out_emb,
+                                      const float* grad_out, int64_t batch_global, float* gs,
+                                      const float* diag_sum, float* dx, float* dy, float* dls_out,
+                                      const float* loss_partial, void* const* peer_bufs, int rank,
+                                      int world, unsigned* epoch, float* out2, void* stream);
+
 /* d logit_scale partial:  *dls_out = (*grad_out) / (2 B_global) * (*gs - 2 * *diag_sum) */
 int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_out,
                     int64_t batch_global, float* dls_out, void* stream);

@@ -91,6 +91,9 @@ SIGNATURES = {
     "plk_infonce_grad": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plk_infonce_grad_finish": (_int, [_vp, _int, _vp, _vp, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _vp, _i64, _vp, _int, _vp]),
+    "plk_infonce_grad_finish_pair_xgpu": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
+                                                 _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                 _int, _int, _vp, _vp, _vp]),
     "plk_infonce_dls": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "plk_topk_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "plk_topk_candidates": (_int, [_vp, _vp, _int, _i64, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp,

@@ -2,6 +2,7 @@
 // gradient tail (diag term + normalisation backward), candidate re-score / merge, k-NN vote.
 // One warp per row, coalesced 32-lane sweeps along d; grids are sized from the row count.
 #include <math_constants.h>
+#include <cstdio>
 #include "common.cuh"
 
 namespace plk {
@@ -378,17 +379,78 @@ struct FinishPairArgs {
   const float* nrm[2];
   float* dx[2];
 };
+// Cross-GPU sum of the two per-rank scalars of a sharded step (loss partial, d logit_scale
+// partial), fused into the gradient tail: the ranks exchange them through peer-mapped symmetric
+// memory over NVLink -- a release/acquire flag per (parity, rank) and one 8-byte slot per parity --
+// instead of a separate NCCL all-reduce launch (which costs ~25 us of a ~90 us step).
+//   peer[r] -> rank r's buffer: float data[2 parities][2], then at +64 bytes uint32 flags[2][8].
+// Every rank sums the slots in rank order, so the result is bitwise identical everywhere.
+struct XGpuArgs {
+  void* const* peer;          // device array [world] of peer-mapped base pointers (nullptr: single GPU)
+  int rank, world;
+  unsigned* epoch;            // local device counter, incremented once per launch (CUDA-graph safe)
+  const float* loss_partial;  // this rank's loss partial
+  float* out2;                // OUT: (global loss, global d logit_scale)
+};
+
+__device__ __forceinline__ void xgpu_scalar_allreduce(const XGpuArgs& xg, float loss_part, float dls_part) {
+  // executed by warp 0 of block (0,0); lane r talks to rank r
+  const int lane = threadIdx.x;
+  unsigned e = 0;
+  if (lane == 0) { e = *xg.epoch + 1; *xg.epoch = e; }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  const int p = e & 1;
+  if (lane == 0) {
+    volatile float* mine = reinterpret_cast<volatile float*>(xg.peer[xg.rank]) + 2 * p;
+    mine[0] = loss_part;
+    mine[1] = dls_part;
+    __threadfence_system();
+  }
+  __syncwarp();
+  float sl = 0.f, sd = 0.f;
+  if (lane < xg.world) {
+    unsigned* their_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(xg.peer[lane]) + 64) + p * 8;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(their_flags + xg.rank), "r"(e) : "memory");
+    const unsigned* my_flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(xg.peer[xg.rank]) + 64) + p * 8;
+    unsigned seen = 0;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flags + lane) : "memory");
+      if (seen != e && clock64() - t0 > 4000000000LL) {
+        printf("plk: cross-GPU scalar exchange timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n",
+               xg.rank, lane, e, seen);
+        __trap();
+      }
+    } while (seen != e);
+    const volatile float* theirs = reinterpret_cast<const volatile float*>(xg.peer[lane]) + 2 * p;
+    sl = theirs[0];
+    sd = theirs[1];
+  }
+  // fixed-order sum (lane 0 adds ranks 0..world-1 in order): identical bits on every rank
+  float tl = 0.f, td = 0.f;
+  for (int r = 0; r < xg.world; ++r) {
+    tl += __shfl_sync(0xffffffffu, sl, r);
+    td += __shfl_sync(0xffffffffu, sd, r);
+  }
+  if (lane == 0) { xg.out2[0] = tl; xg.out2[1] = td; }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     FinishPairArgs a, int parts, int64_t n, int64_t ldx, const float* __restrict__ diag,
     const float* __restrict__ rs, const float* __restrict__ cs, const float* __restrict__ ls,
     const float* __restrict__ grad_out, const float* __restrict__ grad_out_dls, int64_t batch,
-    float* __restrict__ gs, const float* __restrict__ diag_sum, float* __restrict__ dls_out) {
+    float* __restrict__ gs, const float* __restrict__ diag_sum, float* __restrict__ dls_out, XGpuArgs xg) {
   constexpr int64_t d = NV * 128;
   const int m = blockIdx.y;
-  if (blockIdx.x == 0 && m == 0 && threadIdx.x == 0 && dls_out != nullptr) {
-    *dls_out = (float)((double)(*grad_out_dls) / (2.0 * (double)batch) * ((double)(*gs) - 2.0 * (double)(*diag_sum)));
-    *gs = 0.f;   // consumed: the accumulator is back to its zero-initialised state
+  if (blockIdx.x == 0 && m == 0 && threadIdx.x < 32 && dls_out != nullptr) {
+    float dls_local = 0.f;
+    if (threadIdx.x == 0) {
+      dls_local = (float)((double)(*grad_out_dls) / (2.0 * (double)batch) * ((double)(*gs) - 2.0 * (double)(*diag_sum)));
+      *dls_out = dls_local;
+      *gs = 0.f;   // consumed: the accumulator is back to its zero-initialised state
+    }
+    if (xg.peer != nullptr) xgpu_scalar_allreduce(xg, threadIdx.x == 0 ? *xg.loss_partial : 0.f, dls_local);
   }
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -687,14 +749,14 @@ int plk_infonce_grad_finish(const float* acc, int parts, const void* x, const vo
   return PLK_ERR_UNSUPPORTED;
 }
 
-int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int parts, const float* x,
+static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, const float* x,
                                  const float* y, int64_t n, int64_t d, int64_t ldx,
                                  const float* inv_den_x, const float* nrm_x, const float* inv_den_y,
                                  const float* nrm_y, const float* diag, const float* rs, const float* cs,
                                  const float* logit_scale, const float* grad_out_emb,
                                  const float* grad_out, int64_t batch_global, float* gs,
                                  const float* diag_sum, float* dx, float* dy, float* dls_out,
-                                 void* stream) {
+                                 const XGpuArgs& xg, void* stream) {
   PLK_REQUIRE(acc_x && acc_y && x && y && inv_den_x && nrm_x && inv_den_y && nrm_y && diag && rs && cs &&
                   logit_scale && grad_out_emb && grad_out && gs && diag_sum && dx && dy && dls_out,
               PLK_ERR_INVALID, "null pointer");
@@ -709,13 +771,15 @@ int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int par
     a.dx[0] = dx; a.dx[1] = dy;
     dim3 block(256), grid((unsigned)ceil_div(n, 8), 2);
     switch (d / 128) {
-#define PLK_CASE(NV) case NV: grad_finish_pair_vec_kernel<NV><<<grid, block, 0, st>>>(a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out); break;
+#define PLK_CASE(NV) case NV: grad_finish_pair_vec_kernel<NV><<<grid, block, 0, st>>>(a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out, xg); break;
       PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
     }
     PLK_LAUNCHED(1);
     return PLK_OK;
   }
+  PLK_REQUIRE(xg.peer == nullptr, PLK_ERR_UNSUPPORTED,
+              "the fused cross-GPU scalar exchange needs d % 128 == 0 (d <= 1024) and 16-byte aligned rows");
   int rc = plk_infonce_grad_finish(acc_x, parts, x, y, PLK_F32, n, d, ldx, inv_den_x, nrm_x, inv_den_y, diag, rs, cs,
                                    logit_scale, grad_out_emb, batch_global, dx, PLK_F32, stream);
   if (rc) return rc;
@@ -726,6 +790,40 @@ int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int par
   if (rc) return rc;
   PLK_CUDA(cudaMemsetAsync(gs, 0, sizeof(float), st));
   return PLK_OK;
+}
+
+int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int parts, const float* x,
+                                 const float* y, int64_t n, int64_t d, int64_t ldx,
+                                 const float* inv_den_x, const float* nrm_x, const float* inv_den_y,
+                                 const float* nrm_y, const float* diag, const float* rs, const float* cs,
+                                 const float* logit_scale, const float* grad_out_emb,
+                                 const float* grad_out, int64_t batch_global, float* gs,
+                                 const float* diag_sum, float* dx, float* dy, float* dls_out,
+                                 void* stream) {
+  XGpuArgs xg = {};
+  return finish_pair_impl(acc_x, acc_y, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, nrm_y, diag, rs, cs,
+                          logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dx, dy, dls_out, xg,
+                          stream);
+}
+
+int plk_infonce_grad_finish_pair_xgpu(const float* acc_x, const float* acc_y, int parts, const float* x,
+                                      const float* y, int64_t n, int64_t d, int64_t ldx,
+                                      const float* inv_den_x, const float* nrm_x, const float* inv_den_y,
+                                      const float* nrm_y, const float* diag, const float* rs, const float* cs,
+                                      const float* logit_scale, const float* grad_out_emb,
+                                      const float* grad_out, int64_t batch_global, float* gs,
+                                      const float* diag_sum, float* dx, float* dy, float* dls_out,
+                                      const float* loss_partial, void* const* peer_bufs, int rank, int world,
+                                      unsigned* epoch, float* out2, void* stream) {
+  PLK_REQUIRE(loss_partial && peer_bufs && epoch && out2, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, PLK_ERR_INVALID,
+              "world must be in [2, 8] (got rank %d of %d)", rank, world);
+  XGpuArgs xg;
+  xg.peer = peer_bufs; xg.rank = rank; xg.world = world; xg.epoch = epoch;
+  xg.loss_partial = loss_partial; xg.out2 = out2;
+  return finish_pair_impl(acc_x, acc_y, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, nrm_y, diag, rs, cs,
+                          logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dx, dy, dls_out, xg,
+                          stream);
 }
 
 int plk_topk_rescore(const float* q32, const float* g32, int64_t nq, int64_t ng, int64_t d,

@@ -35,6 +35,25 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
+class XGpuScalars:
+    """Peer-mapped symmetric buffer for the fused cross-GPU exchange of the two per-rank scalars
+    (loss partial, d logit_scale partial) inside plk_infonce_grad_finish_pair_xgpu -- torch's
+    symmetric-memory allocator is used only to allocate and exchange the IPC mappings."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty(64, dtype=torch.float32, device=device)   # 8 B x 2 parities + flags at +64 B
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, grp)
+        self.peer_ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.out2 = torch.zeros(2, dtype=torch.float32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)       # every rank's zero-fill is visible before anyone signals
+
+
 def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduce_scalars=True):
     """Forward of the row-block sharded loss without autograd: -> (global loss [], saved state).
     With reduce_scalars=False the returned loss is this rank's partial sum (the caller all-reduces
@@ -48,18 +67,22 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
     x, y = ops._as_f32_rows(image_emb), ops._as_f32_rows(profile_emb)
     ls = logit_scale.detach().float()
     st4 = torch.empty((4, n), device=x.device, dtype=torch.float32)
-    u, v = ops.l2norm_pair(x, y, mode, st4)
+    aligned = n % bs == 0
+    rs = torch.empty(n, device=x.device, dtype=torch.float32)
+    cs_all = torch.empty(n if aligned else B, device=x.device, dtype=torch.float32)
+    dg = torch.empty(n, device=x.device, dtype=torch.float32)
+    u, v = ops.l2norm_pair(x, y, mode, st4, rs, cs_all)      # also zero-fills the two sum-exp accumulators
     idx, nx, idy, ny = st4.unbind(0)
-    if n % bs == 0:
+    if aligned:
         # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange,
         # the local problem is complete; only the scalars are reduced.
         u_all, v_all, off = u, v, 0
-        rs, cs_all, dg = ops.infonce_fwd_local(u, v, mode, d, 0, bs, ls)
+        ops.infonce_fwd_local(u, v, mode, d, 0, bs, ls, rs, cs_all, dg, sums_zeroed=True)
         rs_all = rs
     else:
         u_all = _all_gather_rows(u, group)
         v_all = _all_gather_rows(v, group)
-        rs, cs_all, dg = ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls)
+        ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls, rs, cs_all, dg, sums_zeroed=True)
         dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
         rs_all = _all_gather_rows(rs, group)
     scal = torch.empty(2, device=x.device, dtype=torch.float32)   # (loss, d logit_scale) partials side by side
@@ -72,9 +95,12 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
 
 
 def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, torch.float32),
-                reduce_scalars=True):
+                reduce_scalars=True, xgpu=None):
     """Backward of `sharded_fwd`: -> (d image_emb [n,d], d profile_emb [n,d], d logit_scale []).
-    With reduce_scalars=False d logit_scale is this rank's partial (the caller all-reduces it)."""
+    With reduce_scalars=False d logit_scale is this rank's partial (the caller all-reduces it) --
+    unless `xgpu` (XGpuScalars) is given: then the gradient-tail kernel itself sums (loss partial,
+    d logit_scale partial) over the ranks through NVLink peer memory and xgpu.out2 holds the
+    global (loss, d logit_scale)."""
     x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal, meta = state
     n, d, B, bs, off, mode, group = meta
     R, _ = _world(group)
@@ -89,7 +115,8 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
     go_emb = go * R if grad_scale == "ddp" else go
     dx, dy, dls = ops.infonce_grad_finish_pair(acc_x, acc_y, x, y, (idx, nx), (idy, ny), dg, rs_own, cs_own, ls,
                                                go_emb, go, B, gs, aux[0:1],
-                                               scal[1] if not reduce_scalars else None)
+                                               scal[1] if not reduce_scalars else None,
+                                               xgpu=xgpu, loss_partial=scal[0:1] if xgpu is not None else None)
     dx, dy = dx.to(out_dtypes[0]), dy.to(out_dtypes[1])
     if reduce_scalars:
         dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards

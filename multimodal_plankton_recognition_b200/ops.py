@@ -148,21 +148,29 @@ def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own
 
 
 def infonce_grad_finish_pair(acc_x, acc_y, x, y, stats_x, stats_y, dg, rs_own, cs_own, logit_scale, go_emb, go,
-                             batch_global, gs, diag_sum, dls_out=None):
+                             batch_global, gs, diag_sum, dls_out=None, xgpu=None, loss_partial=None):
     """Both gradient tails + d logit_scale in one launch (fp32 rows).  stats_x / stats_y are
-    (1/den, |.|) pairs.  `gs` is consumed (reset to 0).  -> (dx, dy, dls)"""
+    (1/den, |.|) pairs.  `gs` is consumed (reset to 0).  -> (dx, dy, dls)
+    With `xgpu` (a dist.XGpuScalars) the kernel also sums (loss_partial, dls) over the ranks through
+    peer memory; the global pair lands in xgpu.out2."""
     lib = _lib.load()
     n, d = x.shape
     dx = torch.empty((n, d), device=x.device, dtype=torch.float32)
     dy = torch.empty((n, d), device=x.device, dtype=torch.float32)
     dls = torch.empty((), device=x.device, dtype=torch.float32) if dls_out is None else dls_out
+    common = (acc_x.data_ptr(), acc_y.data_ptr(), acc_x.shape[0], x.data_ptr(), y.data_ptr(), n, d, x.stride(0),
+              stats_x[0].data_ptr(), stats_x[1].data_ptr(), stats_y[0].data_ptr(), stats_y[1].data_ptr(),
+              dg.data_ptr(), rs_own.data_ptr(), cs_own.data_ptr(), logit_scale.data_ptr(), go_emb.data_ptr(),
+              go.data_ptr(), batch_global, gs.data_ptr(), diag_sum.data_ptr(), dx.data_ptr(), dy.data_ptr(),
+              dls.data_ptr())
     with torch.cuda.device(x.device):
-        lib.check(lib.plk_infonce_grad_finish_pair(
-            acc_x.data_ptr(), acc_y.data_ptr(), acc_x.shape[0], x.data_ptr(), y.data_ptr(), n, d, x.stride(0),
-            stats_x[0].data_ptr(), stats_x[1].data_ptr(), stats_y[0].data_ptr(), stats_y[1].data_ptr(),
-            dg.data_ptr(), rs_own.data_ptr(), cs_own.data_ptr(), logit_scale.data_ptr(), go_emb.data_ptr(),
-            go.data_ptr(), batch_global, gs.data_ptr(), diag_sum.data_ptr(), dx.data_ptr(), dy.data_ptr(),
-            dls.data_ptr(), _stream(x)), "plk_infonce_grad_finish_pair")
+        if xgpu is None:
+            lib.check(lib.plk_infonce_grad_finish_pair(*common, _stream(x)), "plk_infonce_grad_finish_pair")
+        else:
+            lib.check(lib.plk_infonce_grad_finish_pair_xgpu(*common, loss_partial.data_ptr(), xgpu.peer_ptrs_dev,
+                                                            xgpu.rank, xgpu.world, xgpu.epoch.data_ptr(),
+                                                            xgpu.out2.data_ptr(), _stream(x)),
+                      "plk_infonce_grad_finish_pair_xgpu")
     return dx, dy, dls
 
 

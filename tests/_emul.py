@@ -44,7 +44,11 @@ def _E(a, b, off, bs, ls):
 def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, ls, rs=None, cs=None, dg=None, sums_zeroed=False):
     E, S, _ = _E(u, v, row_offset, bucket_size, ls)
     n = u.shape[0]
-    return E.sum(1).float(), E.sum(0).float(), S[torch.arange(n), torch.arange(n) + row_offset].float()
+    out = (E.sum(1).float(), E.sum(0).float(), S[torch.arange(n), torch.arange(n) + row_offset].float())
+    for dst, src in zip((rs, cs, dg), out):
+        if dst is not None:
+            dst.copy_(src)
+    return tuple(o if dst is None else dst for dst, o in zip((rs, cs, dg), out))
 
 
 def infonce_loss_local(rs, cs_own, dg, ls, batch_global, loss_out=None):
@@ -83,7 +87,8 @@ def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own
 
 
 def infonce_grad_finish_pair(acc_x, acc_y, x, y, stats_x, stats_y, dg, rs_own, cs_own, ls, go_emb, go, batch_global,
-                             gs, diag_sum, dls_out=None):
+                             gs, diag_sum, dls_out=None, xgpu=None, loss_partial=None):
+    assert xgpu is None, "the fused cross-GPU exchange is CUDA-only"
     dx = infonce_grad_finish(acc_x, x, y, stats_x[0], stats_x[1], stats_y[0], dg, rs_own, cs_own, ls, go_emb,
                              batch_global, torch.float32)
     dy = infonce_grad_finish(acc_y, y, x, stats_y[0], stats_y[1], stats_x[0], dg, rs_own, cs_own, ls, go_emb,

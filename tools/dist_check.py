@@ -39,6 +39,29 @@ for prec, tol in (("fp32", 2e-5), ("bf16", 2e-3)):
         if rank == 0:
             print(f"loss[{prec}] B={B} d={d} bk={buckets}: loss {e_loss:.1e} dI {e_gx:.1e} dls {e_ls:.1e} {'OK' if good else 'FAIL'}", flush=True)
 
+# fused cross-GPU scalar exchange (NVLink peer memory inside the gradient-tail kernel) vs NCCL
+try:
+    from multimodal_plankton_recognition_b200 import dist as pdist, ops
+    xg = pdist.XGpuScalars(dev)
+    img, pro, _ = synth.pairs(512 * world, 256, 5 + rank, dev)
+    ls = torch.ones((), device=dev)
+    go = torch.ones(1, device=dev)
+    for rep in range(5):   # several epochs: parity slots are reused
+        loss_p, state = pdist.sharded_fwd(img, pro, ls, world, ops.MODES["bf16"], None, reduce_scalars=False)
+        want_loss = loss_p.clone()
+        dx, dy, dls_p = pdist.sharded_bwd(state, go, "none", reduce_scalars=False, xgpu=xg)
+        want = torch.stack((want_loss, dls_p.clone()))
+        dist.all_reduce(want)
+        torch.cuda.synchronize()
+        err = float((xg.out2 - want).abs().max() / want.abs().max())
+        good = err < 1e-6
+        ok &= good
+    if rank == 0:
+        print(f"fused xgpu scalars: out2={xg.out2.tolist()} nccl={want.tolist()} {'OK' if good else 'FAIL'}", flush=True)
+except Exception as e:
+    ok = False
+    print(f"rank {rank}: fused xgpu exchange failed: {e!r}", flush=True)
+
 gal, lab = synth.unit_embeddings(40000, 256, 3, "cpu", 1)
 q, _ = synth.unit_embeddings(2000, 256, 4, "cpu", 0)
 shard = 40000 // world
