@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       mbar_init(bar_yfull + b, 1);
       mbar_init(bar_yempty + b, CS);
       mbar_init(bar_sfull + b, 1);
-      mbar_init(bar_gfull + b, kEpiThreads);
+      mbar_init(bar_gfull + b, kEpiThreads / 32);   // one elected arrival per epilogue warp
     }
     mbar_init(bar_accfull, 1);
     fence_barrier_init();
@@ -667,8 +667,31 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
       const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);               // K-major view (S)
       const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), kChunkBytes);     // MN-major view (G.V), LBO = chunk
-      for (int t = 0; t <= T; ++t) {
-        if (t < T) {
+      // Issue order: S(0) S(1) | GV(0) GV(1) S(2) S(3) | GV(2) GV(3) S(4) S(5) | ...
+      // Tile buffer t&1 is released when GV(t) retires; issuing the two GVs back to back lets the
+      // TMA refill of buffer 0 (~1000 cycles) overlap GV(2p+1) and the refill of buffer 1 overlap
+      // S(2p+2), instead of stalling the in-order issue stream once per tile.
+      for (int t0 = 0; t0 < T + 2; t0 += 2) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {          // GV of the previous pair
+          const int u = t0 - 2 + h2;
+          if (u < 0 || u >= T) continue;
+          const int b = u & 1;
+          mbar_wait(bar_gfull + b, (u >> 1) & 1);
+          tc_fence_after();
+          const uint32_t b_lo = y2_lo0 + b * KD * (kChunkBytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kTileRows / kUmmaK; ++k) {
+            // A: packed G, K elements 32c..32c+31 live in columns 32c .. 32c+15 of logits buffer b
+            const uint32_t a_tmem = tmem_base + b * 128 + (k >> 1) * 32 + (k & 1) * 8;
+            umma_bf16_ts(tmem_base + kAccCol, a_tmem, b_lo + k * (2048 >> 4), idesc_g, (u | k) != 0);
+          }
+          ring_release<CS>(bar_yempty + b);   // tile buffer b (and logits buffer b) free once these retire
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {          // S of this pair
+          const int t = t0 + h2;
+          if (t >= T) continue;
           const int b = t & 1;
           mbar_wait(bar_yfull + b, (t >> 1) & 1);
           tc_fence_after();
@@ -682,19 +705,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
               umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
           }
           umma_commit(bar_sfull + b);
-        }
-        if (t >= 1) {
-          const int u = t - 1, b = u & 1;
-          mbar_wait(bar_gfull + b, (u >> 1) & 1);
-          tc_fence_after();
-          const uint32_t b_lo = y2_lo0 + b * KD * (kChunkBytes >> 4);
-#pragma unroll
-          for (int k = 0; k < kTileRows / kUmmaK; ++k) {
-            // A: packed G, K elements 32c..32c+31 live in columns 32c .. 32c+15 of logits buffer b
-            const uint32_t a_tmem = tmem_base + b * 128 + (k >> 1) * 32 + (k & 1) * 8;
-            umma_bf16_ts(tmem_base + kAccCol, a_tmem, b_lo + k * (2048 >> 4), idesc_g, (u | k) != 0);
-          }
-          ring_release<CS>(bar_yempty + b);   // tile buffer b (and logits buffer b) free once these retire
         }
       }
       umma_commit(bar_accfull);
@@ -747,7 +757,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       tmem_st16(col0, packed);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_gfull + buf);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_gfull + buf);   // 16 arrivals per tile instead of 512 serialized smem atomics
       if (cc == 0 && t + 1 < T) rcs_s[(buf ^ 1) * 128 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
     }
     mbar_wait(bar_accfull, 0);
