@@ -191,6 +191,51 @@ int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_ou
                     int64_t batch_global, float* dls_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a1-a11 in two calls: the whole single-GPU loss step, what `CLIPLoss.forward` and the autograd
+ * backward of its result do.                                reference src/coordination.py:26-47
+ *   x, y [B, d] raw fp32 embeddings (row stride ldx); logit_scale the learnable scalar (device).
+ *   state      plk_clip_loss_state_bytes() bytes of device memory written by the forward and
+ *              consumed by the backward (normalised 16-bit/fp32 operands, the per-row statistics,
+ *              two scalars); 256-byte aligned.  One allocation instead of five.
+ *   workspace  plk_clip_loss_workspace_bytes() bytes of scratch for the backward (the partial
+ *              gradient slabs); contents are dead after the call.
+ *   forward : *loss_out = loss.     Launches: normalise(both) -> fused similarity/sum-exp -> loss.
+ *   backward: dx, dy [B, d] fp32, *dls = d loss / d logit_scale, all scaled by *grad_out.
+ *             Launches: recompute backward (both directions) -> gradient tail (both + dls).
+ *   The backward may be called more than once on one state (it restores what it consumes).
+ * ------------------------------------------------------------------------------------------ */
+size_t plk_clip_loss_state_bytes(int op_dtype, int64_t batch, int64_t d);
+size_t plk_clip_loss_workspace_bytes(int op_dtype, int64_t batch, int64_t d, int64_t bucket_size);
+int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
+                          int op_dtype, int64_t bucket_size, const float* logit_scale, void* state,
+                          float* loss_out, void* stream);
+int plk_clip_loss_backward(const float* grad_out, const float* x, const float* y, int64_t batch,
+                           int64_t d, int64_t ldx, int op_dtype, int64_t bucket_size,
+                           const float* logit_scale, void* state, void* workspace, float* dx,
+                           float* dy, float* dls, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Staging host-resident batches into HBM under the running step (no reference counterpart: the
+ * reference hands each batch to the device serially through Lightning's loop,
+ * reference scripts/train_multi.py:78-85).  A stager owns a copy stream and per-slot events:
+ *   issue(slot)             copy stream: wait until `slot` was released, copy x (and y) host->device,
+ *                           mark the slot ready.  Host buffers must be page-locked to overlap.
+ *   acquire(slot, release)  consumer stream: mark `release` (>= 0) reusable after everything queued
+ *                           so far, then wait until `slot` is ready.
+ *   read_async / read_wait  device->host copy of a result on the consumer stream + an event the
+ *                           host can wait on alone (reading a loss does not drain the queue).
+ * Handles are bound to the device current at creation.  NULL from create => plk_last_error().
+ * ------------------------------------------------------------------------------------------ */
+void* plk_stager_create(int depth, int read_slots);
+void plk_stager_destroy(void* stager);
+int plk_stager_issue(void* stager, int slot, void* dst_x, const void* src_x, size_t bytes_x,
+                     void* dst_y, const void* src_y, size_t bytes_y);
+int plk_stager_acquire(void* stager, int slot, int release_slot, void* consumer_stream);
+int plk_stager_read_async(void* stager, int read_slot, void* dst_host, const void* src_dev,
+                          size_t bytes, void* consumer_stream);
+int plk_stager_read_wait(void* stager, int read_slot);
+
+/* ------------------------------------------------------------------------------------------
  * a12. k-nearest candidates by euclidean distance (ranking key |g|^2 - 2 q.g).
  *      replaces pynndescent NNDescent.query                        reference src/ann.py:15-16
  *   q [nq, ld], g [ng, ld] in op_dtype; g_sqn [ng] = ||g_j||^2 (from plk_l2norm_fwd).

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libplk.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "elementwise.cu", "infonce_simt.cu", "topk_simt.cu", "tc_host.cu",
+SOURCES = ["api.cu", "elementwise.cu", "infonce_simt.cu", "topk_simt.cu", "tc_host.cu", "stager.cu",
            "infonce_tc.cu", "topk_tc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
@@ -95,6 +95,17 @@ SIGNATURES = {
                                                  _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                                  _int, _int, _vp, _vp, _vp]),
     "plk_infonce_dls": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "plk_clip_loss_state_bytes": (_sz, [_int, _i64, _i64]),
+    "plk_clip_loss_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
+    "plk_clip_loss_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
+    "plk_clip_loss_backward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp]),
+    "plk_stager_create": (_vp, [_int, _int]),
+    "plk_stager_destroy": (None, [_vp]),
+    "plk_stager_issue": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp, _sz]),
+    "plk_stager_acquire": (_int, [_vp, _int, _int, _vp]),
+    "plk_stager_read_async": (_int, [_vp, _int, _vp, _vp, _sz, _vp]),
+    "plk_stager_read_wait": (_int, [_vp, _int]),
     "plk_topk_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "plk_topk_candidates": (_int, [_vp, _vp, _int, _i64, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp,
                                    _sz, _vp]),

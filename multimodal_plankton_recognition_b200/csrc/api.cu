@@ -113,6 +113,86 @@ int plk_infonce_grad_pair(const void* a0, const void* b0, const void* a1, const 
                                 bucket_size, logit_scale, rs0, cs0, rs1, cs1, acc0, acc1, gs, st);
 }
 
+// ---- the whole single-GPU loss step: layout of the saved state + the two composite calls ----
+namespace {
+struct ClipState {
+  size_t u, v, stats, aux, bytes;
+  int64_t ld;
+  ClipState(int op_dtype, int64_t B, int64_t d) {
+    const size_t esz = op_dtype == PLK_F32 ? 4 : 2;
+    ld = op_dtype == PLK_F32 ? d : (d + 63) / 64 * 64;
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    u = 0;
+    v = up((size_t)B * ld * esz);
+    stats = v + up((size_t)B * ld * esz);
+    aux = stats + up((size_t)7 * B * 4);
+    bytes = aux + 256;
+  }
+};
+int clip_parts(int op_dtype, int64_t B, int64_t d, int64_t bs) {
+  return plk_infonce_grad_pair_parts(op_dtype, B, B, d, bs);
+}
+}  // namespace
+
+size_t plk_clip_loss_state_bytes(int op_dtype, int64_t batch, int64_t d) {
+  if (batch <= 0 || d <= 0) return 0;
+  return ClipState(op_dtype, batch, d).bytes;
+}
+
+size_t plk_clip_loss_workspace_bytes(int op_dtype, int64_t batch, int64_t d, int64_t bucket_size) {
+  if (batch <= 0 || d <= 0 || bucket_size <= 0) return 0;
+  return (size_t)2 * clip_parts(op_dtype, batch, d, bucket_size) * batch * d * sizeof(float);
+}
+
+int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
+                          int op_dtype, int64_t bucket_size, const float* logit_scale, void* state,
+                          float* loss_out, void* stream) {
+  PLK_REQUIRE(x && y && logit_scale && state && loss_out, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(op_dtype >= PLK_F32 && op_dtype <= PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
+  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0,
+              PLK_ERR_INVALID, "bad shape batch=%lld d=%lld ldx=%lld bucket_size=%lld", (long long)batch,
+              (long long)d, (long long)ldx, (long long)bucket_size);
+  PLK_REQUIRE(((uintptr_t)state & 255) == 0, PLK_ERR_INVALID, "state must be 256-byte aligned");
+  const ClipState L(op_dtype, batch, d);
+  char* base = (char*)state;
+  float* st = (float*)(base + L.stats);     // rows: 1/den_x, |x|, 1/den_y, |y|, row sum-exp, col sum-exp, diag
+  float* aux = (float*)(base + L.aux);      // (sum of diagonal logits, gs accumulator)
+  const int64_t B = batch;
+  int rc = plk_l2norm_pair_fwd(x, y, B, d, ldx, base + L.u, base + L.v, op_dtype, L.ld, st, st + B, st + 2 * B,
+                               st + 3 * B, st + 4 * B, B, st + 5 * B, B, stream);
+  if (rc) return rc;
+  rc = plk_infonce_fwd(base + L.u, base + L.v, op_dtype, L.ld, B, 0, B, d, bucket_size, logit_scale, st + 4 * B,
+                       st + 5 * B, st + 6 * B, 1, stream);
+  if (rc) return rc;
+  return plk_infonce_loss(st + 4 * B, st + 5 * B, st + 6 * B, logit_scale, B, B, loss_out, aux, aux + 1, stream);
+}
+
+int plk_clip_loss_backward(const float* grad_out, const float* x, const float* y, int64_t batch,
+                           int64_t d, int64_t ldx, int op_dtype, int64_t bucket_size,
+                           const float* logit_scale, void* state, void* workspace, float* dx,
+                           float* dy, float* dls, void* stream) {
+  PLK_REQUIRE(grad_out && x && y && logit_scale && state && workspace && dx && dy && dls, PLK_ERR_INVALID,
+              "null pointer");
+  PLK_REQUIRE(op_dtype >= PLK_F32 && op_dtype <= PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
+  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0,
+              PLK_ERR_INVALID, "bad shape");
+  const ClipState L(op_dtype, batch, d);
+  char* base = (char*)state;
+  float* st = (float*)(base + L.stats);
+  float* aux = (float*)(base + L.aux);
+  const int64_t B = batch;
+  const int parts = clip_parts(op_dtype, B, d, bucket_size);
+  float* acc_x = (float*)workspace;
+  float* acc_y = acc_x + (size_t)parts * B * d;
+  const float *rs = st + 4 * B, *cs = st + 5 * B;
+  int rc = plk_infonce_grad_pair(base + L.u, base + L.v, base + L.v, base + L.u, op_dtype, L.ld, B, 0, B, d,
+                                 bucket_size, logit_scale, rs, cs, cs, rs, acc_x, acc_y, aux + 1, stream);
+  if (rc) return rc;
+  return plk_infonce_grad_finish_pair(acc_x, acc_y, parts, x, y, B, d, ldx, st, st + B, st + 2 * B, st + 3 * B,
+                                      st + 6 * B, rs, cs, logit_scale, grad_out, grad_out, B, aux + 1, aux, dx,
+                                      dy, dls, stream);
+}
+
 size_t plk_topk_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int kc, int op_dtype) {
   return op_dtype == PLK_F32 ? topk_ws_f32(nq, ng, d, kc) : topk_ws_tc16(nq, ng, d, kc);
 }

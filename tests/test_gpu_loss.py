@@ -167,3 +167,73 @@ def test_clip_plus_matches_reference_formula():
     assert float(loss) == pytest.approx(ref["loss"] + 0.25 * mse, rel=1e-5)
     gref = ref["d_image"] + 0.25 * 2 * (img.astype(np.float64) - pro) / img.size
     assert _rel(x.grad.cpu().numpy(), gref) < 1e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_custom_op_path_matches_eager_path(precision):
+    """`plk::clip_loss_fwd/bwd` (traceable custom ops) and the eager composite calls
+    (plk_clip_loss_forward / plk_clip_loss_backward) launch the same kernels."""
+    from multimodal_plankton_recognition_b200 import ops
+    r = np.random.default_rng(11)
+    dev = torch.device("cuda:0")
+    B, d, buckets = 384, 192, 3
+    x = torch.tensor(r.standard_normal((B, d)), device=dev, dtype=torch.float32)
+    y = torch.tensor(r.standard_normal((B, d)), device=dev, dtype=torch.float32)
+    ls = torch.tensor(1.3, device=dev)
+    go = torch.tensor(0.7, device=dev)
+    mode = ops.MODES[precision]
+    loss_a, u, v, stats, aux = ops.clip_loss_fwd(x, y, ls, buckets, mode)
+    da = ops.clip_loss_bwd(go, x, y, ls, u, v, stats, aux, buckets, mode)
+    loss_b, state = ops.clip_loss_forward_state(x, y, ls, B // buckets, mode)
+    db = ops.clip_loss_backward_state(go, x, y, ls, state, B // buckets, mode)
+    db2 = ops.clip_loss_backward_state(go, x, y, ls, state, B // buckets, mode)   # state survives a backward
+    torch.cuda.synchronize()
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-6 * abs(float(loss_a))
+    for a, b, b2 in zip(da, db, db2):
+        a, b, b2 = a.cpu().numpy(), b.cpu().numpy(), b2.cpu().numpy()
+        scale = max(np.abs(a).max(), 1e-30)
+        assert np.abs(a - b).max() <= 1e-5 * scale
+        assert np.abs(b - b2).max() <= 1e-5 * scale
+
+
+def test_retain_graph_and_two_backwards():
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    dev = torch.device("cuda:0")
+    mod = CLIPLoss(precision="fp32").to(dev)
+    x = torch.randn(64, 32, device=dev, requires_grad=True)
+    y = torch.randn(64, 32, device=dev, requires_grad=True)
+    loss = mod(image_emb=x, profile_emb=y)
+    loss.backward(retain_graph=True)
+    g1 = x.grad.clone()
+    x.grad = None
+    (2 * loss).backward()
+    assert torch.allclose(x.grad, 2 * g1, rtol=1e-5, atol=1e-9)
+
+
+def test_prefetcher_streams_batches_in_order():
+    """prefetch.HostPairPrefetcher: every batch arrives intact and in order while later copies are in
+    flight; losses read through read_async equal the synchronous ones."""
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    from multimodal_plankton_recognition_b200.prefetch import HostPairPrefetcher
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    host = [(torch.randn(256, 128, generator=g).pin_memory(), torch.randn(256, 128, generator=g).pin_memory())
+            for _ in range(7)]
+    mod = CLIPLoss(precision="fp32").to(dev)
+    want = [float(mod(image_emb=hx.to(dev), profile_emb=hy.to(dev))) for hx, hy in host]
+    for depth in (2, 3, 4):
+        pf = HostPairPrefetcher(iter(host), dev, depth=depth)
+        reads = []
+        for i, (x, y) in enumerate(pf):
+            assert torch.equal(x.cpu(), host[i][0]) and torch.equal(y.cpu(), host[i][1])
+            x.requires_grad_()
+            loss = mod(image_emb=x, profile_emb=y)
+            loss.backward()
+            assert x.grad is not None and torch.isfinite(x.grad).all()
+            reads.append(pf.read_async(loss))
+            if len(reads) >= 2:
+                assert reads[-2]() == pytest.approx(want[i - 1], rel=1e-6)
+        assert len(reads) == len(host)
+        assert reads[-1]() == pytest.approx(want[-1], rel=1e-6)
+    with pytest.raises(ValueError):
+        HostPairPrefetcher(iter(host), dev, depth=1)

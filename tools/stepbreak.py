@@ -62,8 +62,8 @@ print(f"sum of parts (2x l2norm, 2x grad, 2x finish): {tot:8.2f} us")
 
 
 def step():
-    l, uu, vv, st, ds = ops.clip_loss_fwd(img, pro, ls, 1, mode)
-    ops.clip_loss_bwd(go, img, pro, ls, uu, vv, st, ds, 1, mode)
+    l, st = ops.clip_loss_forward_state(img, pro, ls, img.shape[0], mode)
+    ops.clip_loss_backward_state(go, img, pro, ls, st, img.shape[0], mode)
 
 
 gtime(step, "whole step (custom ops)")
