@@ -20,6 +20,20 @@
 namespace plk {
 using namespace tc;
 
+// Development aid (-DPLK_TRACE, see tools/trace_tc.py): per-CTA clock stamps of the pipeline events.
+#ifdef PLK_TRACE
+constexpr int kTraceSlots = 128;
+static __device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(int slot) {
+  if (g_trace == nullptr) return;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  g_trace[(size_t)cta * kTraceSlots + slot] = clock64();
+}
+#define TR(slot) trace_stamp(slot)
+#else
+#define TR(slot) ((void)0)
+#endif
+
 constexpr int kNumThreads = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int kEpiThreads = 512;   // four warps per SM sub-partition (latency hiding): each takes one
                                    // 32-column chunk of a tile's 128 columns
@@ -163,6 +177,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   if (t_begin >= t_end) return;  // uniform across the CTA (and across the cluster)
   const int T = t_end - t_begin;
   const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
+  if (threadIdx.x == 0) TR(0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_b);
@@ -177,6 +192,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TR(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -192,6 +208,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
                            (c + cs) * kChunkK, j0, cta_rank);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
+        if (t < 16) TR(48 + t);
       }
     }
     __syncwarp();
@@ -200,6 +217,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
       mbar_wait(bar_a, 0);     // the epilogue warps have parked the owned rows in TMEM (columns 256..)
       tc_fence_after();
+      TR(3);
       const uint32_t a_tmem0 = tmem_base + 256;
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
       int st = 0; uint32_t ph = 0;
@@ -218,10 +236,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
             for (int k = 0; k < kChunkK / kUmmaK; ++k)   // A: 8 packed TMEM columns per K step; B: 32 bytes
               umma_bf16_ts(d_tmem, a_tmem0 + (c + cs) * 32 + k * 8, b_lo + cs * (kChunkBytes >> 4) + 2 * k, idesc,
                            (c | cs | k) != 0);
+          if (t == 0 && c == 0) TR(4);
           ring_release<CS>(bar_empty + st);
           if (++st == NST) { st = 0; ph ^= 1; }
         }
         umma_commit(bar_sfull + buf);
+        if (t < 16) TR(64 + t);
       }
     }
     __syncwarp();
@@ -253,12 +273,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar_a);
+      if (threadIdx.x == 64) TR(2);
     }
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows + cc * 32;   // first column of this chunk
       mbar_wait(bar_sfull + buf, (t >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64 && t < 16) TR(80 + t);
       uint32_t raw[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cc * 32, raw);
       tmem_ld_wait();
@@ -299,16 +321,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       warp_transpose_reduce(v, lane);
       const int64_t j = j0 + lane;
       if (j < n_cols && v[0] != 0.f) atomicAdd(col_sumexp + j, v[0]);
+      if (threadIdx.x == 64 && t < 16) TR(96 + t);
     }
     if (i < n_rows) atomicAdd(row_sumexp + i, rsum);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TR(5);
   if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
+  if (threadIdx.x == 0) TR(6);
 }
 
 // =============================================================================================
@@ -318,6 +343,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 // =============================================================================================
 struct GradDir {
   CUtensorMap ta, tb, tbp;   // owned rows (box 128), streamed rows (box 128), streamed rows (box 64, multicast)
+  CUtensorMap tacc;          // acc as fp32 [nseg][n_rows][d], box 128 x 32 (valid when use_tacc)
+  int use_tacc;
   const float* rs;           // sum-exp along the owned rows
   const float* cs;           // sum-exp along the streamed rows
   float* acc;                // [nseg][n_rows][d] partial accumulators
@@ -622,6 +649,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     }
     return;
   }
+  if (threadIdx.x == 0) TR(0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&g.ta);
@@ -644,6 +672,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kAccCol = 256;
+  if (threadIdx.x == 0) TR(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -656,6 +685,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
         mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
         for (int c = 0; c < KD; ++c)
           chunk_load<CS>(sm_y + (b * KD + c) * kChunkBytes, &g.tb, &g.tbp, bar_yfull + b, c * kChunkK, j0, cta_rank);
+        if (t < 16) TR(48 + t);
       }
     }
     __syncwarp();
@@ -664,6 +694,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
       constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A from TMEM (K-major), B MN-major
       mbar_wait(bar_a, 0);
+      TR(3);
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
       const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);               // K-major view (S)
       const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), kChunkBytes);     // MN-major view (G.V), LBO = chunk
@@ -687,6 +718,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
             umma_bf16_ts(tmem_base + kAccCol, a_tmem, b_lo + k * (2048 >> 4), idesc_g, (u | k) != 0);
           }
           ring_release<CS>(bar_yempty + b);   // tile buffer b (and logits buffer b) free once these retire
+          if (u < 16) TR(112 + u);
         }
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {          // S of this pair
@@ -705,6 +737,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
               umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
           }
           umma_commit(bar_sfull + b);
+          if (t < 16) TR(64 + t);
         }
       }
       umma_commit(bar_accfull);
@@ -744,6 +777,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       }
       mbar_wait(bar_sfull + buf, (t >> 1) & 1);
       tc_fence_after();
+      if (threadIdx.x == 64 && t < 16) TR(80 + t);
       const bool full = (j0 + cc * 32 >= lo) && (j0 + cc * 32 + 32 <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full);
       const uint32_t col0 = tmem_base + lane_addr + buf * 128 + cc * 32;
@@ -759,10 +793,37 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfull + buf);   // 16 arrivals per tile instead of 512 serialized smem atomics
+      if (threadIdx.x == 64 && t < 16) TR(96 + t);
       if (cc == 0 && t + 1 < T) rcs_s[(buf ^ 1) * 128 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
     }
     mbar_wait(bar_accfull, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) TR(2);
+    if (g.use_tacc) {
+      // Drain through shared memory + TMA stores: a thread owns a row, so direct stores would touch 32
+      // different lines per warp instruction (8192 sixteen-byte requests per CTA); staged as 128-byte
+      // swizzled rows in the (now idle) tile buffers, each 32-column chunk leaves as ONE bulk store of
+      // full lines.  The four warps of a chunk (lane quadrants 0..3) synchronise on a named barrier.
+#pragma unroll 1
+      for (int ch = cc; ch < 2 * KD; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        uint8_t* stage = sm_y + ch * kChunkBytes;     // 128 rows x 128 B
+        uint8_t* rowp = stage + r * 128;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
+              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+        fence_proxy_async_smem();
+        named_barrier_sync(2 + cc, 128);
+        if (q == 0 && lane == 0 && i0 < n_rows) {
+          tma_store_3d(&g.tacc, stage, ch * 32, (int)i0, (int)blockIdx.x);
+          tma_store_commit();
+        }
+      }
+      if (q == 0 && lane == 0) tma_store_wait_all();
+    } else {
 #pragma unroll 1
     for (int ch = cc; ch < 2 * KD; ch += 4) {
       uint32_t raw[32];
@@ -784,6 +845,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
         }
       }
     }
+    }
     if (want_gs) {
       gs_local *= s;
 #pragma unroll
@@ -793,11 +855,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TR(5);
   if constexpr (CS > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
+  if (threadIdx.x == 0) TR(6);
 }
 
 
@@ -929,12 +993,14 @@ static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_
   if ((rc = make_tmap_bf16(&g.tb, b, n_cols, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&g.tbp, b, n_cols, ld, ld, kTileRows / 2))) return rc;
   g.rs = rs; g.cs = cs; g.acc = acc; g.gs = gs;
+  g.use_tacc = 0;
   return PLK_OK;
 }
 
 template <bool F16>
-static int grad_launch_16(const GradArgs& ga, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
                           int64_t d, int64_t bs, const float* ls, cudaStream_t st) {
+  GradArgs ga = ga_in;
   int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int csz = pick_cluster(row_blocks, bs, n_cols);
   const int kd = (int)(ld / kChunkK);
@@ -945,6 +1011,15 @@ static int grad_launch_16(const GradArgs& ga, int64_t ld, int64_t n_rows, int64_
   row_blocks = ceil_div(row_blocks, csz) * csz;
   dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
   if (kd <= 4) {   // the streamed tile fits next to the resident rows: tile-buffer kernel, G in TMEM
+    if (d % 32 == 0) {   // accumulator drain by TMA store (full 128-byte lines)
+      for (int k = 0; k < ga.ndir; ++k) {
+        if (((uintptr_t)ga.dir[k].acc & 15) != 0) continue;
+        int rc = make_tmap_f32_slabs(&ga.dir[k].tacc, ga.dir[k].acc, nseg, n_rows, d);
+        if (rc) return rc;
+        ga.dir[k].use_tacc = 1;
+      }
+      if (ga.ndir == 1) ga.dir[1] = ga.dir[0];
+    }
     switch (kd) {
 #define PLK_CASE2(KD)                                                                                   \
   case KD:                                                                                              \
@@ -995,3 +1070,9 @@ int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1,
 }
 
 }  // namespace plk
+
+#ifdef PLK_TRACE
+extern "C" int plk_debug_set_trace(long long* buf) {
+  return cudaMemcpyToSymbol(plk::g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -83,6 +83,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// 3-D tiled store shared -> global (bulk async group), and the fences around it
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Multicast variant: the box is written at the same CTA-relative offset in every CTA of `mask`
 // and complete_tx is signalled on the mbarrier at the same offset in each of them.
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
@@ -330,6 +339,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // 128-byte swizzle, out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld,
                    int box_rows);
+int make_tmap_f32_slabs(CUtensorMap* out, const void* base, int64_t slabs, int64_t rows, int64_t cols);
 
 // launch with an optional {1, cluster_y, 1} thread-block cluster
 template <typename... KArgs, typename... Args>

@@ -17,7 +17,8 @@ _DT = {torch.float32: PLK_F32, torch.bfloat16: PLK_BF16, torch.float16: PLK_F16}
 
 
 def _stream(t: torch.Tensor) -> int:
-    return torch.cuda.current_stream(t.device).cuda_stream
+    idx = t.device.index
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device() if idx is None else idx)
 
 
 def _require_cuda(*ts):
