@@ -148,7 +148,7 @@ struct FwdCfg {
 
 template <int KD, int CS>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
-    const uint16_t* __restrict__ a_op, int64_t lda, const __grid_constant__ CUtensorMap tmap_b,
+    const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_bp, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tiles_per_seg,
     const float* __restrict__ ls, float* __restrict__ row_sumexp, float* __restrict__ col_sumexp,
     float* __restrict__ diag, int f16) {
@@ -164,7 +164,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   uint64_t* bar_a = bar_empty + NST;                      // [1]
   uint64_t* bar_sfull = bar_a + 1;                        // [2]
   uint64_t* bar_sempty = bar_sfull + 2;                   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sempty + 2);
+  uint64_t* bar_afull = bar_sempty + 2;                   // [1] owned rows landed in their staging slots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_afull + 1);
+  // The owned rows arrive by TMA in the LAST KD chunk slots of the ring, are moved to TMEM by the
+  // epilogue warps, and only then does the producer let streamed chunks into those slots.
+  constexpr int kASlot0 = NST * CPS - KD;
+  constexpr int kAStage0 = kASlot0 / CPS;
+  static_assert(kASlot0 >= 0, "ring too small to stage the owned rows");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
@@ -180,9 +186,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   if (threadIdx.x == 0) TR(0);
 
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
     mbar_init(bar_a, kEpiThreads);
+    mbar_init(bar_afull, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
     fence_barrier_init();
   }
@@ -196,10 +204,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 
   if (warp == 0) {
     if (lane == 0) {
+      mbar_expect_tx(bar_afull, KD * kChunkBytes);
+      for (int c = 0; c < KD; ++c)
+        tma_load_2d(sm_ring + (kASlot0 + c) * kChunkBytes, &tmap_a, bar_afull, c * kChunkK, (int)i0);
+      bool a_parked = false;
       int st = 0; uint32_t ph = 0;
       for (int t = 0; t < T; ++t) {
         const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
         for (int c = 0; c < KD; c += CPS) {
+          if (!a_parked && st >= kAStage0) {   // first use of a stage that overlaps the staging slots
+            mbar_wait(bar_a, 0);
+            a_parked = true;
+          }
           mbar_wait(bar_empty + st, ph ^ 1);
           mbar_expect_tx(bar_full + st, Cfg::kStageBytes);
 #pragma unroll
@@ -258,14 +274,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     const float c1 = s * kLog2e, c0 = -c1;
     float rsum = 0.f;
     {  // park this thread's owned row (16-bit operand, padded to KD*64) in TMEM columns 256.. as packed
-       // pairs -- the A operand of the TS-mode MMA; the four warps of a lane quadrant take alternate chunks
-      const uint4* arow = reinterpret_cast<const uint4*>(a_op + i * lda);
+       // pairs -- the A operand of the TS-mode MMA; the four warps of a lane quadrant take alternate chunks.
+       // Source: the swizzled staging slots (rows past n_rows were zero-filled by the TMA unit).
+      mbar_wait(bar_afull, 0);
       for (int c = cc; c < KD; c += 4) {
+        const uint8_t* rowp = sm_ring + (kASlot0 + c) * kChunkBytes + r * 128;
         uint32_t pk[32];
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4) {
-          uint4 w = make_uint4(0u, 0u, 0u, 0u);
-          if (i < n_rows) w = arow[c * 8 + v4];
+          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
           pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
         }
         tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + 256 + c * 32, pk);
@@ -898,7 +915,7 @@ static int pick_cluster(int64_t row_blocks, int64_t bs, int64_t n_cols) {
 }
 
 template <int KD, int CS>
-static int launch_fwd(const void* a_op, int64_t lda, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
+static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
                       int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tps,
                       const float* ls, float* rsum, float* csum, float* diag, int f16, cudaStream_t st) {
   auto kern = infonce_fwd_tc<KD, CS>;
@@ -907,7 +924,7 @@ static int launch_fwd(const void* a_op, int64_t lda, const CUtensorMap& tb, cons
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<KD>::kSmem));
     configured = true;
   }
-  int rc = launch_kernel(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, (const uint16_t*)a_op, lda, tb, tbp, n_rows,
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, ta, tb, tbp, n_rows,
                          row_offset, n_cols, bs, tps, ls, rsum, csum, diag, f16);
   if (rc) return rc;
   PLK_LAUNCHED(1);
@@ -922,7 +939,8 @@ int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t 
   int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int cs = pick_cluster(row_blocks, bs, n_cols);
   PLK_REQUIRE(((uintptr_t)u & 15) == 0, PLK_ERR_INVALID, "operand must be 16-byte aligned");
-  CUtensorMap tb, tbp;
+  CUtensorMap ta, tb, tbp;
+  if ((rc = make_tmap_bf16(&ta, u, n_rows, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tb, v, n_cols, ld, ld, kTileRows))) return rc;
   if ((rc = make_tmap_bf16(&tbp, v, n_cols, ld, ld, kTileRows / 2))) return rc;
   // sums are accumulated with atomics -> zero first; diag needs no init (every owned row has its
@@ -936,8 +954,8 @@ int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t 
   switch (ld / kChunkK) {
 #define PLK_CASE(KD)                                                                                         \
   case KD:                                                                                                   \
-    return cs == 2 ? launch_fwd<KD, 2>(u, ld, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st) \
-                   : launch_fwd<KD, 1>(u, ld, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st);
+    return cs == 2 ? launch_fwd<KD, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st) \
+                   : launch_fwd<KD, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st);
     PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
   }
