@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace plk {
@@ -185,8 +186,19 @@ int plk_clip_loss_backward(const float* grad_out, const float* x, const float* y
   float* acc_x = (float*)workspace;
   float* acc_y = acc_x + (size_t)parts * B * d;
   const float *rs = st + 4 * B, *cs = st + 5 * B;
-  int rc = plk_infonce_grad_pair(base + L.u, base + L.v, base + L.v, base + L.u, op_dtype, L.ld, B, 0, B, d,
-                                 bucket_size, logit_scale, rs, cs, cs, rs, acc_x, acc_y, aux + 1, stream);
+  int rc;
+  static const bool overlap = getenv("PLK_PDL") == nullptr || getenv("PLK_PDL")[0] != '0';
+  if (op_dtype != PLK_F32) {
+    // Everything this launch reads was produced by the forward call, at least one kernel back in the
+    // stream; only the sum G*S accumulator is zeroed by the forward's last kernel.  The grid may
+    // therefore start under that kernel (or whatever ran in between) -- programmatic serialization.
+    rc = infonce_grad_pair_tc16(base + L.u, base + L.v, base + L.v, base + L.u, op_dtype == PLK_F16, L.ld, B, 0, B,
+                                d, bucket_size, logit_scale, rs, cs, cs, rs, acc_x, acc_y, aux + 1,
+                                (cudaStream_t)stream, overlap ? 1 : 0);
+  } else {
+    rc = plk_infonce_grad_pair(base + L.u, base + L.v, base + L.v, base + L.u, op_dtype, L.ld, B, 0, B, d,
+                               bucket_size, logit_scale, rs, cs, cs, rs, acc_x, acc_y, aux + 1, stream);
+  }
   if (rc) return rc;
   return plk_infonce_grad_finish_pair(acc_x, acc_y, parts, x, y, B, d, ldx, st, st + B, st + 2 * B, st + 3 * B,
                                       st + 6 * B, rs, cs, logit_scale, grad_out, grad_out, B, aux + 1, aux, dx,

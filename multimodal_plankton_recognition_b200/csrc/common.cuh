@@ -33,6 +33,30 @@ constexpr float kLog2e = 1.4426950408889634f;
     }                                 \
   } while (0)
 
+// ---- programmatic dependent launch (sm_90+) ---------------------------------------------------
+// A grid launched with launch_overlapped() may become resident while the previous kernel in the
+// stream is still running: once every thread block of that kernel has executed pdl_trigger() (or
+// exited).  It must execute pdl_wait() -- the previous kernel has completed and its writes are
+// visible -- before touching anything that kernel produces or still reads.  Both are no-ops for
+// normally launched grids / grids without dependents.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+cudaError_t launch_overlapped(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define PLK_LAUNCHED(n)                     \
   do {                                      \
     ::plk::count_launch(n);                 \
@@ -65,7 +89,7 @@ int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1, const
                            int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
                            int64_t bs, const float* ls, const float* rs0, const float* cs0,
                            const float* rs1, const float* cs1, float* acc0, float* acc1, float* gs,
-                           cudaStream_t st);
+                           cudaStream_t st, int overlap_prev = 0);
 int topk_candidates_tc16(const void* q, const void* g, int f16, int64_t ld, const float* g_sqn,
                          int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff, int32_t* cand_idx,
                          float* cand_key, void* ws, size_t ws_bytes, cudaStream_t st);

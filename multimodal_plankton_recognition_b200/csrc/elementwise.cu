@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) l2norm_pair_vec_kernel(NormPairArgs a, in
   const int m = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_trigger();   // the forward kernel may set itself up; it waits for this grid before reading
   {  // zero fill: thread-linear over this modality's accumulator
     const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a.zero[m] != nullptr && z < a.nzero[m]) a.zero[m][z] = 0.f;
@@ -244,6 +245,10 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ rs
                                                     float* __restrict__ diag_sum_out,
                                                     float* __restrict__ gs_zero) {
   __shared__ double sh[2][32];
+  pdl_wait();      // the forward kernel is complete
+  // A kernel queued behind this one with programmatic serialization (the recompute backward) may
+  // start now: the forward's results are final and it consumes nothing of ours before its own wait.
+  pdl_trigger();
   if (threadIdx.x == 0 && gs_zero != nullptr) *gs_zero = 0.f;
   const double s = (double)expf(*ls);
   double a = 0.0, dsum = 0.0;
@@ -443,6 +448,7 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     float* __restrict__ gs, const float* __restrict__ diag_sum, float* __restrict__ dls_out, XGpuArgs xg) {
   constexpr int64_t d = NV * 128;
   const int m = blockIdx.y;
+  pdl_wait();   // launched under the tail of the recompute backward
   if (blockIdx.x == 0 && m == 0 && threadIdx.x < 32 && dls_out != nullptr) {
     float dls_local = 0.f;
     if (threadIdx.x == 0) {
@@ -717,7 +723,8 @@ int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const
                      float* diag_sum_out, float* gs_zero, void* stream) {
   PLK_REQUIRE(row_sumexp && col_sumexp_own && diag && logit_scale && loss_out, PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(n_rows > 0 && batch_global >= n_rows, PLK_ERR_INVALID, "bad sizes");
-  loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(row_sumexp, col_sumexp_own, diag, logit_scale, n_rows, batch_global, loss_out, diag_sum_out, gs_zero);
+  PLK_CUDA(launch_overlapped(loss_kernel, dim3(1), dim3(1024), (cudaStream_t)stream, row_sumexp, col_sumexp_own, diag,
+                             logit_scale, n_rows, batch_global, loss_out, diag_sum_out, gs_zero));
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
@@ -771,7 +778,7 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
     a.dx[0] = dx; a.dx[1] = dy;
     dim3 block(256), grid((unsigned)ceil_div(n, 8), 2);
     switch (d / 128) {
-#define PLK_CASE(NV) case NV: grad_finish_pair_vec_kernel<NV><<<grid, block, 0, st>>>(a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out, xg); break;
+#define PLK_CASE(NV) case NV: PLK_CUDA(launch_overlapped(grad_finish_pair_vec_kernel<NV>, grid, block, st, a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out, xg)); break;
       PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
     }

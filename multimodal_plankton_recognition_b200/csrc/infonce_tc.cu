@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   const int T = t_end - t_begin;
   const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
   if (threadIdx.x == 0) TR(0);
+  pdl_trigger();   // the loss kernel may become resident; it waits for this grid's completion
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -200,6 +201,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // set-up (barriers, tensor memory, descriptor prefetch) may have run under the tail of the
+  // normalisation kernel; the operands and the zero-filled accumulators are its products
+  pdl_wait();
   if (threadIdx.x == 0) TR(1);
 
   if (warp == 0) {
@@ -660,6 +664,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
   const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
   float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
   if (T == 0) {
+    griddep_wait();   // global writes only after the kernel queued before this one is done
     for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DN; e += kNumThreads) {
       const int64_t rr = i0 + e / DN, col = e % DN;
       if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
@@ -667,6 +672,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     return;
   }
   if (threadIdx.x == 0) TR(0);
+  pdl_trigger();   // the gradient-tail kernel may become resident; it waits for this grid's completion
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&g.ta);
@@ -816,6 +822,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     mbar_wait(bar_accfull, 0);
     tc_fence_after();
     if (threadIdx.x == 64) TR(2);
+    // With an overlapped launch (launch_kernel_ex) everything above only read what the forward left
+    // behind; global writes start here, after the kernel queued before this one has completed.
+    griddep_wait();
     if (g.use_tacc) {
       // Drain through shared memory + TMA stores: a thread owns a row, so direct stores would touch 32
       // different lines per warp instruction (8192 sixteen-byte requests per CTA); staged as 128-byte
@@ -867,9 +876,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       gs_local *= s;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
-      if (lane == 0) atomicAdd(g.gs, gs_local);
+      if (lane == 0) atomicAdd(g.gs, gs_local);   // zeroed by plk_infonce_loss (waited for above)
     }
   }
+  griddep_wait();   // no thread block outlives the kernel queued before it (see launch_kernel_ex)
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TR(5);
@@ -924,7 +934,7 @@ static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<KD>::kSmem));
     configured = true;
   }
-  int rc = launch_kernel(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, ta, tb, tbp, n_rows,
+  int rc = launch_kernel_ex(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, true, ta, tb, tbp, n_rows,
                          row_offset, n_cols, bs, tps, ls, rsum, csum, diag, f16);
   if (rc) return rc;
   PLK_LAUNCHED(1);
@@ -981,15 +991,15 @@ static int launch_grad(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t ro
 
 template <int KD, int CS, bool F16>
 static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
-                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st) {
+                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
   auto kern = infonce_grad_tc2<KD, CS, F16>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad2Cfg<KD>::kSmem));
     configured = true;
   }
-  int rc = launch_kernel(kern, grid, dim3(kNumThreads), Grad2Cfg<KD>::kSmem, st, CS, ga, n_rows, row_offset,
-                         n_cols, d, bs, tps, ls);
+  int rc = launch_kernel_ex(kern, grid, dim3(kNumThreads), Grad2Cfg<KD>::kSmem, st, CS, overlap_prev, ga, n_rows,
+                            row_offset, n_cols, d, bs, tps, ls);
   if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
@@ -1017,7 +1027,7 @@ static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_
 
 template <bool F16>
 static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
-                          int64_t d, int64_t bs, const float* ls, cudaStream_t st) {
+                          int64_t d, int64_t bs, const float* ls, cudaStream_t st, bool overlap_prev = false) {
   GradArgs ga = ga_in;
   int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int csz = pick_cluster(row_blocks, bs, n_cols);
@@ -1041,8 +1051,8 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
     switch (kd) {
 #define PLK_CASE2(KD)                                                                                   \
   case KD:                                                                                              \
-    return csz == 2 ? launch_grad2<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st) \
-                    : launch_grad2<KD, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
+    return csz == 2 ? launch_grad2<KD, 2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev) \
+                    : launch_grad2<KD, 1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
       PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
 #undef PLK_CASE2
     }
@@ -1076,15 +1086,15 @@ int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1,
                            const void* b1, int f16, int64_t ld, int64_t n_rows, int64_t row_offset,
                            int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs0,
                            const float* cs0, const float* rs1, const float* cs1, float* acc0, float* acc1,
-                           float* gs, cudaStream_t st) {
+                           float* gs, cudaStream_t st, int overlap_prev) {
   int rc = check_tc_shape(ld, d);
   if (rc) return rc;
   GradArgs ga;
   ga.ndir = 2;
   if ((rc = fill_dir(ga.dir[0], a0, b0, ld, n_rows, n_cols, rs0, cs0, acc0, gs))) return rc;
   if ((rc = fill_dir(ga.dir[1], a1, b1, ld, n_rows, n_cols, rs1, cs1, acc1, nullptr))) return rc;
-  return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st)
-             : grad_launch_16<false>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
+  return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st, overlap_prev != 0)
+             : grad_launch_16<false>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st, overlap_prev != 0);
 }
 
 }  // namespace plk

@@ -105,6 +105,11 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, 
 }
 
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { pdl_wait(); }   // see common.cuh
+
+// ------------------------------------------------------------------------------------------
 // thread-block clusters
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -341,24 +346,41 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t col
                    int box_rows);
 int make_tmap_f32_slabs(CUtensorMap* out, const void* base, int64_t slabs, int64_t rows, int64_t cols);
 
-// launch with an optional {1, cluster_y, 1} thread-block cluster
+// launch with an optional {1, cluster_y, 1} thread-block cluster; `overlap_prev` adds programmatic
+// stream serialization: the grid may start while the previous kernel in the stream is still
+// running (once that kernel has executed griddepcontrol.launch_dependents, or finished), and must
+// execute griddep_wait() before touching anything the previous kernel produces.
 template <typename... KArgs, typename... Args>
-int launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                  int cluster_y, Args... args) {
+int launch_kernel_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     int cluster_y, bool overlap_prev, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = (unsigned)cluster_y;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_y > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = (unsigned)cluster_y;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (overlap_prev) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = cluster_y > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   PLK_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
   return PLK_OK;
+}
+template <typename... KArgs, typename... Args>
+int launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                  int cluster_y, Args... args) {
+  return launch_kernel_ex(kern, grid, block, smem, st, cluster_y, false, args...);
 }
 
 }  // namespace tc
