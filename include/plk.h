@@ -172,7 +172,9 @@ int plk_infonce_grad_finish_pair(const float* acc_x, const float* acc_y, int par
  *   loss_partial  this rank's loss partial (from plk_infonce_loss)
  *   peer_bufs     DEVICE array [world] of peer-mapped base pointers of one >= 128-byte,
  *                 zero-initialised symmetric buffer per rank (same order on every rank)
- *   epoch         local device counter (zero-initialised once; incremented per launch)
+ *   epoch         TWO local device counters (uint32[2], zero-initialised once; each is incremented
+ *                 per launch: the first block publishes, the last block collects, so rank skew is
+ *                 absorbed by the kernel's row work)
  *   out2          OUT (global loss, global d logit_scale), bitwise identical on every rank
  * All ranks must launch it the same number of times (it waits for every peer, bounded by a trap). */
 int plk_infonce_grad_finish_pair_xgpu(const float* acc_x, const float* acc_y, int parts,
@@ -200,19 +202,34 @@ int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_ou
  *   workspace  plk_clip_loss_workspace_bytes() bytes of scratch for the backward (the partial
  *              gradient slabs); contents are dead after the call.
  *   forward : *loss_out = loss.     Launches: normalise(both) -> fused similarity/sum-exp -> loss.
- *   backward: dx, dy [B, d] fp32, *dls = d loss / d logit_scale, all scaled by *grad_out.
- *             Launches: recompute backward (both directions) -> gradient tail (both + dls).
+ *   backward: dx, dy [B, d] fp32 scaled by *grad_out_emb, *dls = d loss / d logit_scale scaled by
+ *             *grad_out.  Launches: recompute backward (both directions, started under the tail of
+ *             the preceding kernel -- programmatic serialization) -> gradient tail (both + dls).
  *   The backward may be called more than once on one state (it restores what it consumes).
+ *   batch_global: the 1/(2 B) of the loss.  batch_global == batch on one GPU.  A rank of a
+ *   bucket-aligned sharded step (every bucket entirely on one rank: the local problem is
+ *   complete) passes the global batch: loss / dls are then this rank's PARTIAL sums.  The embedding
+ *   gradients are scaled by (*grad_out_emb) * emb_scale; under DDP gradient averaging pass
+ *   grad_out_emb = grad_out and emb_scale = world (emb_scale != 1 needs d % 128 == 0, d <= 1024).
+ *   plk_clip_loss_backward_xgpu additionally sums (loss partial, dls partial) over the ranks inside
+ *   the gradient-tail kernel (arguments as plk_infonce_grad_finish_pair_xgpu).
  * ------------------------------------------------------------------------------------------ */
 size_t plk_clip_loss_state_bytes(int op_dtype, int64_t batch, int64_t d);
 size_t plk_clip_loss_workspace_bytes(int op_dtype, int64_t batch, int64_t d, int64_t bucket_size);
 int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
-                          int op_dtype, int64_t bucket_size, const float* logit_scale, void* state,
-                          float* loss_out, void* stream);
-int plk_clip_loss_backward(const float* grad_out, const float* x, const float* y, int64_t batch,
-                           int64_t d, int64_t ldx, int op_dtype, int64_t bucket_size,
-                           const float* logit_scale, void* state, void* workspace, float* dx,
-                           float* dy, float* dls, void* stream);
+                          int op_dtype, int64_t bucket_size, int64_t batch_global,
+                          const float* logit_scale, void* state, float* loss_out, void* stream);
+int plk_clip_loss_backward(const float* grad_out, const float* grad_out_emb, float emb_scale,
+                           const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx, int op_dtype,
+                           int64_t bucket_size, int64_t batch_global, const float* logit_scale,
+                           void* state, void* workspace, float* dx, float* dy, float* dls,
+                           void* stream);
+int plk_clip_loss_backward_xgpu(const float* grad_out, const float* grad_out_emb, float emb_scale,
+                                const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx, int op_dtype,
+                                int64_t bucket_size, int64_t batch_global, const float* logit_scale,
+                                void* state, void* workspace, float* dx, float* dy, float* dls,
+                                const float* loss_partial, void* const* peer_bufs, int rank,
+                                int world, unsigned* epoch, float* out2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Staging host-resident batches into HBM under the running step (no reference counterpart: the

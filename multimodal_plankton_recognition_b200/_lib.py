@@ -99,9 +99,11 @@ SIGNATURES = {
     "plk_infonce_dls": (_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "plk_clip_loss_state_bytes": (_sz, [_int, _i64, _i64]),
     "plk_clip_loss_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
-    "plk_clip_loss_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp]),
-    "plk_clip_loss_backward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                                      _vp]),
+    "plk_clip_loss_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "plk_clip_loss_backward": (_int, [_vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _vp]),
+    "plk_clip_loss_backward_xgpu": (_int, [_vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp,
+                                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "plk_stager_create": (_vp, [_int, _int]),
     "plk_stager_destroy": (None, [_vp]),
     "plk_stager_issue": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp, _sz]),

@@ -146,13 +146,13 @@ size_t plk_clip_loss_workspace_bytes(int op_dtype, int64_t batch, int64_t d, int
 }
 
 int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
-                          int op_dtype, int64_t bucket_size, const float* logit_scale, void* state,
-                          float* loss_out, void* stream) {
+                          int op_dtype, int64_t bucket_size, int64_t batch_global,
+                          const float* logit_scale, void* state, float* loss_out, void* stream) {
   PLK_REQUIRE(x && y && logit_scale && state && loss_out, PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(op_dtype >= PLK_F32 && op_dtype <= PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
-  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0,
-              PLK_ERR_INVALID, "bad shape batch=%lld d=%lld ldx=%lld bucket_size=%lld", (long long)batch,
-              (long long)d, (long long)ldx, (long long)bucket_size);
+  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0 && batch_global >= batch,
+              PLK_ERR_INVALID, "bad shape batch=%lld d=%lld ldx=%lld bucket_size=%lld batch_global=%lld",
+              (long long)batch, (long long)d, (long long)ldx, (long long)bucket_size, (long long)batch_global);
   PLK_REQUIRE(((uintptr_t)state & 255) == 0, PLK_ERR_INVALID, "state must be 256-byte aligned");
   const ClipState L(op_dtype, batch, d);
   char* base = (char*)state;
@@ -165,17 +165,19 @@ int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t
   rc = plk_infonce_fwd(base + L.u, base + L.v, op_dtype, L.ld, B, 0, B, d, bucket_size, logit_scale, st + 4 * B,
                        st + 5 * B, st + 6 * B, 1, stream);
   if (rc) return rc;
-  return plk_infonce_loss(st + 4 * B, st + 5 * B, st + 6 * B, logit_scale, B, B, loss_out, aux, aux + 1, stream);
+  return plk_infonce_loss(st + 4 * B, st + 5 * B, st + 6 * B, logit_scale, B, batch_global, loss_out, aux, aux + 1,
+                          stream);
 }
 
-int plk_clip_loss_backward(const float* grad_out, const float* x, const float* y, int64_t batch,
-                           int64_t d, int64_t ldx, int op_dtype, int64_t bucket_size,
-                           const float* logit_scale, void* state, void* workspace, float* dx,
-                           float* dy, float* dls, void* stream) {
-  PLK_REQUIRE(grad_out && x && y && logit_scale && state && workspace && dx && dy && dls, PLK_ERR_INVALID,
-              "null pointer");
+static int clip_backward_impl(const float* grad_out, const float* grad_out_emb, float emb_scale, const float* x, const float* y,
+                              int64_t batch, int64_t d, int64_t ldx, int op_dtype, int64_t bucket_size,
+                              int64_t batch_global, const float* logit_scale, void* state, void* workspace,
+                              float* dx, float* dy, float* dls, const float* loss_partial, void* const* peer_bufs,
+                              int rank, int world, unsigned* epoch, float* out2, void* stream) {
+  PLK_REQUIRE(grad_out && grad_out_emb && x && y && logit_scale && state && workspace && dx && dy && dls,
+              PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(op_dtype >= PLK_F32 && op_dtype <= PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
-  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0,
+  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0 && batch_global >= batch,
               PLK_ERR_INVALID, "bad shape");
   const ClipState L(op_dtype, batch, d);
   char* base = (char*)state;
@@ -200,9 +202,30 @@ int plk_clip_loss_backward(const float* grad_out, const float* x, const float* y
                                bucket_size, logit_scale, rs, cs, cs, rs, acc_x, acc_y, aux + 1, stream);
   }
   if (rc) return rc;
-  return plk_infonce_grad_finish_pair(acc_x, acc_y, parts, x, y, B, d, ldx, st, st + B, st + 2 * B, st + 3 * B,
-                                      st + 6 * B, rs, cs, logit_scale, grad_out, grad_out, B, aux + 1, aux, dx,
-                                      dy, dls, stream);
+  return finish_pair_scaled(acc_x, acc_y, parts, x, y, B, d, ldx, st, st + B, st + 2 * B, st + 3 * B, st + 6 * B, rs,
+                            cs, logit_scale, grad_out_emb, emb_scale, grad_out, batch_global, aux + 1, aux, dx, dy,
+                            dls, loss_partial, peer_bufs, rank, world, epoch, out2, stream);
+}
+
+int plk_clip_loss_backward(const float* grad_out, const float* grad_out_emb, float emb_scale, const float* x,
+                           const float* y, int64_t batch, int64_t d, int64_t ldx, int op_dtype,
+                           int64_t bucket_size, int64_t batch_global, const float* logit_scale, void* state,
+                           void* workspace, float* dx, float* dy, float* dls, void* stream) {
+  return clip_backward_impl(grad_out, grad_out_emb, emb_scale, x, y, batch, d, ldx, op_dtype, bucket_size, batch_global,
+                            logit_scale, state, workspace, dx, dy, dls, nullptr, nullptr, 0, 1, nullptr, nullptr,
+                            stream);
+}
+
+int plk_clip_loss_backward_xgpu(const float* grad_out, const float* grad_out_emb, float emb_scale, const float* x,
+                                const float* y, int64_t batch, int64_t d, int64_t ldx, int op_dtype, int64_t bucket_size,
+                                int64_t batch_global, const float* logit_scale, void* state, void* workspace,
+                                float* dx, float* dy, float* dls, const float* loss_partial,
+                                void* const* peer_bufs, int rank, int world, unsigned* epoch, float* out2,
+                                void* stream) {
+  PLK_REQUIRE(loss_partial && peer_bufs && epoch && out2, PLK_ERR_INVALID, "null pointer");
+  return clip_backward_impl(grad_out, grad_out_emb, emb_scale, x, y, batch, d, ldx, op_dtype, bucket_size, batch_global,
+                            logit_scale, state, workspace, dx, dy, dls, loss_partial, peer_bufs, rank, world, epoch,
+                            out2, stream);
 }
 
 size_t plk_topk_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int kc, int op_dtype) {

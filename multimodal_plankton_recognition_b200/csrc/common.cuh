@@ -85,6 +85,13 @@ int infonce_grad_tc16(const void* a, const void* b, int f16, int64_t ld, int64_t
                       int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
                       const float* rs, const float* cs, float* acc, float* gs, cudaStream_t st);
 int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir);
+int finish_pair_scaled(const float* acc_x, const float* acc_y, int parts, const float* x, const float* y, int64_t n,
+                       int64_t d, int64_t ldx, const float* inv_den_x, const float* nrm_x, const float* inv_den_y,
+                       const float* nrm_y, const float* diag, const float* rs, const float* cs,
+                       const float* logit_scale, const float* grad_out_emb, float emb_scale, const float* grad_out,
+                       int64_t batch_global, float* gs, const float* diag_sum, float* dx, float* dy, float* dls_out,
+                       const float* loss_partial, void* const* peer_bufs, int rank, int world, unsigned* epoch,
+                       float* out2, void* stream);
 int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1, const void* b1, int f16,
                            int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
                            int64_t bs, const float* ls, const float* rs0, const float* cs0,

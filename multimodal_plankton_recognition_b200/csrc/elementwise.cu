@@ -383,6 +383,7 @@ struct FinishPairArgs {
   const float* inv_den[2];
   const float* nrm[2];
   float* dx[2];
+  float emb_scale;          // extra factor on the embedding gradients (world size under DDP averaging)
 };
 // Cross-GPU sum of the two per-rank scalars of a sharded step (loss partial, d logit_scale
 // partial), fused into the gradient tail: the ranks exchange them through peer-mapped symmetric
@@ -393,16 +394,20 @@ struct FinishPairArgs {
 struct XGpuArgs {
   void* const* peer;          // device array [world] of peer-mapped base pointers (nullptr: single GPU)
   int rank, world;
-  unsigned* epoch;            // local device counter, incremented once per launch (CUDA-graph safe)
+  unsigned* epoch;            // two local device counters, incremented once per launch (CUDA-graph safe)
   const float* loss_partial;  // this rank's loss partial
   float* out2;                // OUT: (global loss, global d logit_scale)
 };
 
-__device__ __forceinline__ void xgpu_scalar_allreduce(const XGpuArgs& xg, float loss_part, float dls_part) {
-  // executed by warp 0 of block (0,0); lane r talks to rank r
+// Publish (first thread block of the kernel) and collect (LAST thread block, which is scheduled near the
+// end of the kernel) are separate, so the time the ranks are out of step with each other is
+// absorbed by the kernel's own row work instead of stalling it.  epoch[0] / epoch[1] count the
+// launches seen by the publisher / the collector.
+__device__ __forceinline__ void xgpu_publish(const XGpuArgs& xg, float loss_part, float dls_part) {
+  // executed by warp 0 of block (0,0); lane r signals rank r
   const int lane = threadIdx.x;
   unsigned e = 0;
-  if (lane == 0) { e = *xg.epoch + 1; *xg.epoch = e; }
+  if (lane == 0) { e = xg.epoch[0] + 1; xg.epoch[0] = e; }
   e = __shfl_sync(0xffffffffu, e, 0);
   const int p = e & 1;
   if (lane == 0) {
@@ -412,10 +417,20 @@ __device__ __forceinline__ void xgpu_scalar_allreduce(const XGpuArgs& xg, float 
     __threadfence_system();
   }
   __syncwarp();
-  float sl = 0.f, sd = 0.f;
   if (lane < xg.world) {
     unsigned* their_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(xg.peer[lane]) + 64) + p * 8;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(their_flags + xg.rank), "r"(e) : "memory");
+  }
+}
+__device__ __forceinline__ void xgpu_collect(const XGpuArgs& xg) {
+  // executed by warp 0 of the last block; lane r waits for rank r (its own rank included)
+  const int lane = threadIdx.x;
+  unsigned e = 0;
+  if (lane == 0) { e = xg.epoch[1] + 1; xg.epoch[1] = e; }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  const int p = e & 1;
+  float sl = 0.f, sd = 0.f;
+  if (lane < xg.world) {
     const unsigned* my_flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(xg.peer[xg.rank]) + 64) + p * 8;
     unsigned seen = 0;
     const long long t0 = clock64();
@@ -456,8 +471,11 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
       *dls_out = dls_local;
       *gs = 0.f;   // consumed: the accumulator is back to its zero-initialised state
     }
-    if (xg.peer != nullptr) xgpu_scalar_allreduce(xg, threadIdx.x == 0 ? *xg.loss_partial : 0.f, dls_local);
+    if (xg.peer != nullptr) xgpu_publish(xg, threadIdx.x == 0 ? *xg.loss_partial : 0.f, dls_local);
   }
+  if (xg.peer != nullptr && blockIdx.x == gridDim.x - 1 && m == (int)gridDim.y - 1 && threadIdx.x < 32 &&
+      dls_out != nullptr)
+    xgpu_collect(xg);
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -480,7 +498,7 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     }
   }
   const float s = expf(*ls);
-  const float coef = (*grad_out) * s / (2.0f * (float)batch);
+  const float coef = (*grad_out) * a.emb_scale * s / (2.0f * (float)batch);
   const float idx_ = a.inv_den[m][row], idp = a.inv_den[1 - m][row];
   const bool clamped = !(a.nrm[m][row] > kNormEps);
   const float dterm = expf(diag[row] - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
@@ -763,7 +781,7 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
                                  const float* logit_scale, const float* grad_out_emb,
                                  const float* grad_out, int64_t batch_global, float* gs,
                                  const float* diag_sum, float* dx, float* dy, float* dls_out,
-                                 const XGpuArgs& xg, void* stream) {
+                                 const XGpuArgs& xg, void* stream, float emb_scale = 1.0f) {
   PLK_REQUIRE(acc_x && acc_y && x && y && inv_den_x && nrm_x && inv_den_y && nrm_y && diag && rs && cs &&
                   logit_scale && grad_out_emb && grad_out && gs && diag_sum && dx && dy && dls_out,
               PLK_ERR_INVALID, "null pointer");
@@ -776,6 +794,7 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
     a.acc[0] = acc_x; a.acc[1] = acc_y; a.x[0] = x; a.x[1] = y;
     a.inv_den[0] = inv_den_x; a.inv_den[1] = inv_den_y; a.nrm[0] = nrm_x; a.nrm[1] = nrm_y;
     a.dx[0] = dx; a.dx[1] = dy;
+    a.emb_scale = emb_scale;
     dim3 block(256), grid((unsigned)ceil_div(n, 8), 2);
     switch (d / 128) {
 #define PLK_CASE(NV) case NV: PLK_CUDA(launch_overlapped(grad_finish_pair_vec_kernel<NV>, grid, block, st, a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out, xg)); break;
@@ -785,8 +804,8 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
     PLK_LAUNCHED(1);
     return PLK_OK;
   }
-  PLK_REQUIRE(xg.peer == nullptr, PLK_ERR_UNSUPPORTED,
-              "the fused cross-GPU scalar exchange needs d % 128 == 0 (d <= 1024) and 16-byte aligned rows");
+  PLK_REQUIRE(xg.peer == nullptr && emb_scale == 1.0f, PLK_ERR_UNSUPPORTED,
+              "the fused cross-GPU scalar exchange / emb_scale need d % 128 == 0 (d <= 1024) and 16-byte aligned rows");
   int rc = plk_infonce_grad_finish(acc_x, parts, x, y, PLK_F32, n, d, ldx, inv_den_x, nrm_x, inv_den_y, diag, rs, cs,
                                    logit_scale, grad_out_emb, batch_global, dx, PLK_F32, stream);
   if (rc) return rc;
@@ -832,6 +851,34 @@ int plk_infonce_grad_finish_pair_xgpu(const float* acc_x, const float* acc_y, in
                           logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dx, dy, dls_out, xg,
                           stream);
 }
+
+}  // extern "C"
+
+namespace plk {
+// plk_infonce_grad_finish_pair(_xgpu) with an extra host-side factor on the embedding gradients
+// (peer_bufs == nullptr: no cross-GPU exchange).  Used by the composite backward (api.cu).
+int finish_pair_scaled(const float* acc_x, const float* acc_y, int parts, const float* x, const float* y, int64_t n,
+                       int64_t d, int64_t ldx, const float* inv_den_x, const float* nrm_x, const float* inv_den_y,
+                       const float* nrm_y, const float* diag, const float* rs, const float* cs,
+                       const float* logit_scale, const float* grad_out_emb, float emb_scale, const float* grad_out,
+                       int64_t batch_global, float* gs, const float* diag_sum, float* dx, float* dy, float* dls_out,
+                       const float* loss_partial, void* const* peer_bufs, int rank, int world, unsigned* epoch,
+                       float* out2, void* stream) {
+  XGpuArgs xg = {};
+  if (peer_bufs != nullptr) {
+    PLK_REQUIRE(loss_partial && epoch && out2, PLK_ERR_INVALID, "null pointer");
+    PLK_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, PLK_ERR_INVALID,
+                "world must be in [2, 8] (got rank %d of %d)", rank, world);
+    xg.peer = peer_bufs; xg.rank = rank; xg.world = world; xg.epoch = epoch;
+    xg.loss_partial = loss_partial; xg.out2 = out2;
+  }
+  return finish_pair_impl(acc_x, acc_y, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, nrm_y, diag, rs, cs,
+                          logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dx, dy, dls_out, xg, stream,
+                          emb_scale);
+}
+}  // namespace plk
+
+extern "C" {
 
 int plk_topk_rescore(const float* q32, const float* g32, int64_t nq, int64_t ng, int64_t d,
                      const int32_t* cand_idx, int m, int64_t gallery_offset, int k, float* scratch,

@@ -48,7 +48,7 @@ class XGpuScalars:
         self.hdl = symm_mem.rendezvous(self.buf, grp)
         self.peer_ptrs_dev = int(self.hdl.buffer_ptrs_dev)
         self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)   # publisher / collector launch counters
         self.out2 = torch.zeros(2, dtype=torch.float32, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group=group)       # every rank's zero-fill is visible before anyone signals
@@ -66,31 +66,31 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
     off = r * n
     x, y = ops._as_f32_rows(image_emb), ops._as_f32_rows(profile_emb)
     ls = logit_scale.detach().float()
+    scal = torch.empty(2, device=x.device, dtype=torch.float32)   # (loss, d logit_scale) partials side by side
+    if n % bs == 0:
+        # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange, the
+        # local problem is complete -- the single-GPU composite step with the global 1/(2B); only the
+        # two scalars are reduced.
+        loss, st = ops.clip_loss_forward_state(x, y, ls, bs, mode, batch_global=B, loss_out=scal[0])
+        if reduce_scalars:
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        return loss, (x, y, ls, st, scal, (True, n, d, B, bs, off, mode, group))
     st4 = torch.empty((4, n), device=x.device, dtype=torch.float32)
-    aligned = n % bs == 0
     rs = torch.empty(n, device=x.device, dtype=torch.float32)
-    cs_all = torch.empty(n if aligned else B, device=x.device, dtype=torch.float32)
+    cs_all = torch.empty(B, device=x.device, dtype=torch.float32)
     dg = torch.empty(n, device=x.device, dtype=torch.float32)
     u, v = ops.l2norm_pair(x, y, mode, st4, rs, cs_all)      # also zero-fills the two sum-exp accumulators
     idx, nx, idy, ny = st4.unbind(0)
-    if aligned:
-        # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange,
-        # the local problem is complete; only the scalars are reduced.
-        u_all, v_all, off = u, v, 0
-        ops.infonce_fwd_local(u, v, mode, d, 0, bs, ls, rs, cs_all, dg, sums_zeroed=True)
-        rs_all = rs
-    else:
-        u_all = _all_gather_rows(u, group)
-        v_all = _all_gather_rows(v, group)
-        ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls, rs, cs_all, dg, sums_zeroed=True)
-        dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
-        rs_all = _all_gather_rows(rs, group)
-    scal = torch.empty(2, device=x.device, dtype=torch.float32)   # (loss, d logit_scale) partials side by side
+    u_all = _all_gather_rows(u, group)
+    v_all = _all_gather_rows(v, group)
+    ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls, rs, cs_all, dg, sums_zeroed=True)
+    dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
+    rs_all = _all_gather_rows(rs, group)
     loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B, scal[0])
     if reduce_scalars:
         dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
     state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal,
-             (n, d, B, bs, off, mode, group))
+             (False, n, d, B, bs, off, mode, group))
     return loss, state
 
 
@@ -101,22 +101,33 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
     unless `xgpu` (XGpuScalars) is given: then the gradient-tail kernel itself sums (loss partial,
     d logit_scale partial) over the ranks through NVLink peer memory and xgpu.out2 holds the
     global (loss, d logit_scale)."""
-    x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal, meta = state
-    n, d, B, bs, off, mode, group = meta
+    meta = state[-1]
+    aligned, n, d, B, bs, off, mode, group = meta
     R, _ = _world(group)
     go = grad_out.detach().float().reshape(1).contiguous()
-    rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
-    gs = aux[1:]
-    acc_x, acc_y = ops.infonce_grad_pair_local(u, v_all, v, u_all, mode, d, off, bs, ls, rs_own, cs_all,
-                                               cs_own, rs_all, gs)
     # grad_scale == "ddp": DistributedDataParallel AVERAGES parameter gradients over ranks, while
     # each rank holds the exact d(global loss)/d(local rows); pre-multiplying by the world size
     # makes the averaged encoder gradients equal the true global-batch gradients.
-    go_emb = go * R if grad_scale == "ddp" else go
-    dx, dy, dls = ops.infonce_grad_finish_pair(acc_x, acc_y, x, y, (idx, nx), (idy, ny), dg, rs_own, cs_own, ls,
-                                               go_emb, go, B, gs, aux[0:1],
-                                               scal[1] if not reduce_scalars else None,
-                                               xgpu=xgpu, loss_partial=scal[0:1] if xgpu is not None else None)
+    scale = float(R) if grad_scale == "ddp" else 1.0
+    if aligned:
+        x, y, ls, st, scal = state[:-1]
+        in_kernel = d % 128 == 0 and d <= 1024      # the vectorised gradient tail applies the factor itself
+        dx, dy, dls = ops.clip_loss_backward_state(go, x, y, ls, st, bs, mode, batch_global=B,
+                                                   go_emb=None if in_kernel or scale == 1.0 else go * scale,
+                                                   emb_scale=scale if in_kernel else 1.0,
+                                                   dls_out=scal[1] if not reduce_scalars else None, xgpu=xgpu,
+                                                   loss_partial=scal[0:1] if xgpu is not None else None)
+    else:
+        go_emb = go * scale if scale != 1.0 else go
+        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal = state[:-1]
+        rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
+        gs = aux[1:]
+        acc_x, acc_y = ops.infonce_grad_pair_local(u, v_all, v, u_all, mode, d, off, bs, ls, rs_own, cs_all,
+                                                   cs_own, rs_all, gs)
+        dx, dy, dls = ops.infonce_grad_finish_pair(acc_x, acc_y, x, y, (idx, nx), (idy, ny), dg, rs_own, cs_own, ls,
+                                                   go_emb, go, B, gs, aux[0:1],
+                                                   scal[1] if not reduce_scalars else None,
+                                                   xgpu=xgpu, loss_partial=scal[0:1] if xgpu is not None else None)
     dx, dy = dx.to(out_dtypes[0]), dy.to(out_dtypes[1])
     if reduce_scalars:
         dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
@@ -128,14 +139,15 @@ class _ShardedClipLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_emb, profile_emb, logit_scale, buckets, mode, group, grad_scale):
         loss, state = sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group)
-        ctx.save_for_backward(*state[:-1])
-        ctx.meta = (state[-1], grad_scale, image_emb.dtype, profile_emb.dtype, logit_scale.dtype)
+        ctx.plk_state = state    # intermediates only (detached fp32 rows, opaque buffers): no graph edges
+        ctx.meta = (grad_scale, image_emb.dtype, profile_emb.dtype, logit_scale.dtype)
         return loss
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        meta, grad_scale, dt_x, dt_y, dt_ls = ctx.meta
-        dx, dy, dls = sharded_bwd(tuple(ctx.saved_tensors) + (meta,), g, grad_scale, (dt_x, dt_y))
+        grad_scale, dt_x, dt_y, dt_ls = ctx.meta
+        dx, dy, dls = sharded_bwd(ctx.plk_state, g, grad_scale, (dt_x, dt_y))
         return dx, dy, dls.to(dt_ls), None, None, None, None
 
 

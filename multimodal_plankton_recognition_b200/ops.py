@@ -288,30 +288,38 @@ def _f32_rows(t: torch.Tensor) -> torch.Tensor:
     return t if t.stride(1) == 1 else t.contiguous()
 
 
-def clip_loss_forward_state(x: torch.Tensor, y: torch.Tensor, ls: torch.Tensor, bs: int, mode: int):
+def clip_loss_forward_state(x: torch.Tensor, y: torch.Tensor, ls: torch.Tensor, bs: int, mode: int,
+                            batch_global: int | None = None, loss_out: torch.Tensor | None = None):
     """x, y: fp32 [B, d] rows (unit inner stride, equal row stride); ls: fp32 scalar on the device.
-    -> (loss [], state) where `state` is the opaque buffer plk_clip_loss_backward consumes."""
+    -> (loss [], state) where `state` is the opaque buffer plk_clip_loss_backward consumes.
+    `batch_global` > B: the rows are one rank's share of a bucket-aligned global batch and `loss`
+    is that rank's partial sum."""
     lib = _lib.load()
     B, d = x.shape
     dev = x.device
     state_bytes, _ = _clip_sizes(lib, mode, B, d, bs)
     state = torch.empty(state_bytes, device=dev, dtype=torch.uint8)
-    loss = torch.empty((), device=dev, dtype=torch.float32)
+    loss = torch.empty((), device=dev, dtype=torch.float32) if loss_out is None else loss_out
     if y.stride(0) != x.stride(0):
         x, y = x.contiguous(), y.contiguous()
     idx = dev.index
     if torch.cuda.current_device() != idx:
         with torch.cuda.device(idx):
-            return clip_loss_forward_state(x, y, ls, bs, mode)
-    lib.check(lib.plk_clip_loss_forward(x.data_ptr(), y.data_ptr(), B, d, x.stride(0), mode, bs, ls.data_ptr(),
+            return clip_loss_forward_state(x, y, ls, bs, mode, batch_global, loss)
+    lib.check(lib.plk_clip_loss_forward(x.data_ptr(), y.data_ptr(), B, d, x.stride(0), mode, bs,
+                                        B if batch_global is None else batch_global, ls.data_ptr(),
                                         state.data_ptr(), loss.data_ptr(),
                                         torch._C._cuda_getCurrentRawStream(idx)), "plk_clip_loss_forward")
     return loss, state
 
 
 def clip_loss_backward_state(go: torch.Tensor, x: torch.Tensor, y: torch.Tensor, ls: torch.Tensor, state, bs: int,
-                             mode: int):
-    """-> (dx, dy, dls) fp32, scaled by the scalar `go` (fp32, on the device)."""
+                             mode: int, batch_global: int | None = None, go_emb: torch.Tensor | None = None,
+                             dls_out: torch.Tensor | None = None, xgpu=None, loss_partial=None,
+                             emb_scale: float = 1.0):
+    """-> (dx, dy, dls) fp32: dx, dy scaled by the scalar `go_emb` (default `go`) times the host float
+    `emb_scale` (needs d % 128 == 0 when != 1), dls by `go` (fp32, on the device).  With `xgpu` (dist.XGpuScalars) the gradient-tail kernel also sums (loss_partial, dls)
+    over the ranks through peer memory; the global pair lands in xgpu.out2."""
     lib = _lib.load()
     B, d = x.shape
     dev = x.device
@@ -320,16 +328,24 @@ def clip_loss_backward_state(go: torch.Tensor, x: torch.Tensor, y: torch.Tensor,
     idx = dev.index
     if torch.cuda.current_device() != idx:
         with torch.cuda.device(idx):
-            return clip_loss_backward_state(go, x, y, ls, state, bs, mode)
+            return clip_loss_backward_state(go, x, y, ls, state, bs, mode, batch_global, go_emb, dls_out, xgpu,
+                                            loss_partial, emb_scale)
     _, ws_bytes = _clip_sizes(lib, mode, B, d, bs)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     dx = torch.empty((B, d), device=dev, dtype=torch.float32)
     dy = torch.empty((B, d), device=dev, dtype=torch.float32)
-    dls = torch.empty((), device=dev, dtype=torch.float32)
-    lib.check(lib.plk_clip_loss_backward(go.data_ptr(), x.data_ptr(), y.data_ptr(), B, d, x.stride(0), mode, bs,
-                                         ls.data_ptr(), state.data_ptr(), ws.data_ptr(), dx.data_ptr(),
-                                         dy.data_ptr(), dls.data_ptr(),
-                                         torch._C._cuda_getCurrentRawStream(idx)), "plk_clip_loss_backward")
+    dls = torch.empty((), device=dev, dtype=torch.float32) if dls_out is None else dls_out
+    common = (go.data_ptr(), (go if go_emb is None else go_emb).data_ptr(), float(emb_scale), x.data_ptr(),
+              y.data_ptr(), B, d,
+              x.stride(0), mode, bs, B if batch_global is None else batch_global, ls.data_ptr(), state.data_ptr(),
+              ws.data_ptr(), dx.data_ptr(), dy.data_ptr(), dls.data_ptr())
+    stream = torch._C._cuda_getCurrentRawStream(idx)
+    if xgpu is None:
+        lib.check(lib.plk_clip_loss_backward(*common, stream), "plk_clip_loss_backward")
+    else:
+        lib.check(lib.plk_clip_loss_backward_xgpu(*common, loss_partial.data_ptr(), xgpu.peer_ptrs_dev, xgpu.rank,
+                                                  xgpu.world, xgpu.epoch.data_ptr(), xgpu.out2.data_ptr(), stream),
+                  "plk_clip_loss_backward_xgpu")
     return dx, dy, dls
 
 

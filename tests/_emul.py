@@ -106,6 +106,29 @@ def infonce_dls(gs, diag_sum, go, batch_global, out=None):
     return val
 
 
+def clip_loss_forward_state(x, y, ls, bs, mode, batch_global=None, loss_out=None):
+    """plk_clip_loss_forward: the complete local problem with the global 1/(2B)."""
+    n, d = x.shape
+    stats = torch.empty((4, n))
+    u, v = l2norm_pair(x, y, mode, stats)
+    rs, cs, dg = infonce_fwd_local(u, v, mode, d, 0, bs, ls)
+    loss, aux = infonce_loss_local(rs, cs, dg, ls, n if batch_global is None else batch_global, loss_out)
+    return loss, (u, v, stats, rs, cs, dg, aux)
+
+
+def clip_loss_backward_state(go, x, y, ls, state, bs, mode, batch_global=None, go_emb=None, dls_out=None, xgpu=None,
+                             loss_partial=None, emb_scale=1.0):
+    """plk_clip_loss_backward."""
+    u, v, stats, rs, cs, dg, aux = state
+    n, d = x.shape
+    Bg = n if batch_global is None else batch_global
+    gs = aux[1:]
+    acc_x, acc_y = infonce_grad_pair_local(u, v, v, u, mode, d, 0, bs, ls, rs, cs, cs, rs, gs)
+    return infonce_grad_finish_pair(acc_x, acc_y, x, y, stats[0:2], stats[2:4], dg, rs, cs, ls,
+                                    (go if go_emb is None else go_emb) * emb_scale, go, Bg, gs, aux[0:1], dls_out, xgpu,
+                                    loss_partial)
+
+
 class CpuExactIndex:
     """Stand-in for ann.GpuExactIndex over the oracle's exact index (global indices via offset)."""
 

@@ -24,7 +24,8 @@ def _patch():
     import _emul
     from multimodal_plankton_recognition_b200 import ann, ops
     for name in ("l2norm", "l2norm_pair", "infonce_fwd_local", "infonce_loss_local", "infonce_grad_pair_local",
-                 "infonce_grad_finish", "infonce_grad_finish_pair", "infonce_dls"):
+                 "infonce_grad_finish", "infonce_grad_finish_pair", "infonce_dls", "clip_loss_forward_state",
+                 "clip_loss_backward_state"):
         setattr(ops, name, getattr(_emul, name))
     ann.GpuExactIndex = _emul.CpuExactIndex
     ann.topk_merge_device = _emul.topk_merge_device
