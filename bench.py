@@ -366,7 +366,11 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "infonce_grad_tc2 (recompute backward, both directions in one launch)", "achieved": achieved,
                      "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                      "peak_source": f"{peaks['source']} burst", "kernel_ms": k_ms,
-                     "algorithmic_flops_per_launch": algo_flops, "traffic": None,
+                     "algorithmic_flops_per_launch": algo_flops,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one
+                     # `ncu --set full` capture (profiles/r1_ncu_full_summary.txt): the 4 MiB of 16-bit
+                     # operands; the partial-gradient slabs stay in L2
+                     "traffic": 4287232 if (n, d, args.precision) == (4096, 256, "bf16") else None,
                      "executed_flops_per_launch": 2.0 * algo_flops,
                      "executed_tflops": 2.0 * achieved,
                      "note": "the recompute backward executes S = a.b^T once per direction on top of the two "
