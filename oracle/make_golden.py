@@ -8,6 +8,8 @@ exist on the GPU box):
 * loss_*.npz      inputs + outputs of the reference's own ``CLIPLoss``
                   (reference src/coordination.py:17-47), fp64 and fp32, incl. autograd
                   gradients w.r.t. both embeddings and ``logit_scale``.
+* siglip_*.npz    the same for the reference's ``SigLIPLoss`` (reference src/coordination.py:67-95),
+                  incl. the gradient w.r.t. ``bias``.
 * ann_*.npz       inputs + outputs of the reference's own ``ANNClassifier``
                   (reference src/ann.py:6-34) executed with ``oracle.ann.ExactIndex``
                   injected as the module ``pynndescent`` (the real package is not
@@ -32,7 +34,7 @@ stub = types.ModuleType("pynndescent")
 stub.NNDescent = ExactIndex
 sys.modules["pynndescent"] = stub
 
-from src.coordination import CLIPLoss  # noqa: E402  (the reference)
+from src.coordination import CLIPLoss, SigLIPLoss  # noqa: E402  (the reference)
 from src.ann import ANNClassifier      # noqa: E402  (the reference)
 
 
@@ -65,6 +67,30 @@ def loss_case(name, B, d, buckets, ls, seed, tweak=None):
         out[f"d_logit_scale_{tag}"] = mod.logit_scale.grad.numpy()
     np.savez_compressed(os.path.join(OUT, f"loss_{name}.npz"), **out)
     print("wrote", name, float(out["loss_f64"]))
+
+
+def siglip_case(name, B, d, buckets, ls, bias, seed, tweak=None):
+    """inputs + outputs of the reference's own ``SigLIPLoss`` (reference src/coordination.py:67-95)."""
+    img, pro, _ = synth_pairs(B, d, seed)
+    if tweak:
+        tweak(img, pro)
+    out = {"image": img, "profile": pro, "buckets": buckets, "logit_scale": np.float64(ls), "bias": np.float64(bias)}
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        mod = SigLIPLoss().to(dt)
+        with torch.no_grad():
+            mod.logit_scale.fill_(ls)
+            mod.bias.fill_(bias)
+        x = torch.tensor(img, dtype=dt, requires_grad=True)
+        y = torch.tensor(pro, dtype=dt, requires_grad=True)
+        loss = mod(image_emb=x, profile_emb=y, buckets=buckets)
+        loss.backward()
+        out[f"loss_{tag}"] = loss.detach().numpy()
+        out[f"d_image_{tag}"] = x.grad.numpy()
+        out[f"d_profile_{tag}"] = y.grad.numpy()
+        out[f"d_logit_scale_{tag}"] = mod.logit_scale.grad.numpy()
+        out[f"d_bias_{tag}"] = mod.bias.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, f"siglip_{name}.npz"), **out)
+    print("wrote siglip", name, float(out["loss_f64"]))
 
 
 def ann_case(name, ng, nq, d, k, seed, n_classes=9, dup=False, two_mod=False):
@@ -111,6 +137,12 @@ def main():
         img[7] = img[8]
         pro[7] = pro[8]
     loss_case("b64_d64_edge", 64, 64, 2, 1.0, 6, tweak=tiny)
+
+    siglip_case("b64_d128_k1", 64, 128, 1, 1.0, -10.0, 21)           # the reference's initial parameters
+    siglip_case("b256_d256_k4", 256, 256, 4, 1.0, -10.0, 22)
+    siglip_case("b192_d256_k3_ls2.3_b-4", 192, 256, 3, 2.3, -4.0, 23)  # a trained-looking temperature / bias
+    siglip_case("b100_d72_k1_ls0_b0", 100, 72, 1, 0.0, 0.0, 24)      # ragged B and d, logits around 0
+    siglip_case("b64_d64_edge", 64, 64, 2, 1.0, -10.0, 25, tweak=tiny)
 
     ann_case("g432_q300_d512_k9", 432, 300, 512, 9, 11, n_classes=27)
     ann_case("g96_q64_d64_k5_dup", 96, 64, 64, 5, 12, dup=True)

@@ -8,6 +8,7 @@ import pytest
 from conftest import golden_files
 from oracle import ann as oann
 from oracle import infonce as oinf
+from oracle import siglip as osig
 
 
 @pytest.mark.parametrize("path", golden_files("loss_"), ids=os.path.basename)
@@ -36,6 +37,37 @@ def test_loss_torch_port_matches_reference_fp32(path):
     np.testing.assert_allclose(x.grad.numpy(), g["d_image_f32"], rtol=1e-4, atol=1e-7)
     np.testing.assert_allclose(y.grad.numpy(), g["d_profile_f32"], rtol=1e-4, atol=1e-7)
     assert float(ls.grad) == pytest.approx(float(g["d_logit_scale_f32"]), rel=1e-3, abs=1e-6)
+
+
+@pytest.mark.parametrize("path", golden_files("siglip_"), ids=os.path.basename)
+def test_siglip_closed_form_matches_reference_fp64(path):
+    g = np.load(path)
+    out = osig.siglip_loss_closed_form(g["image"], g["profile"], float(g["logit_scale"]), float(g["bias"]),
+                                       int(g["buckets"]))
+    assert out["loss"] == pytest.approx(float(g["loss_f64"]), rel=1e-12)
+    for k_o, k_g in (("d_image", "d_image_f64"), ("d_profile", "d_profile_f64")):
+        ref = g[k_g]
+        err = np.abs(out[k_o] - ref).max() / max(np.abs(ref).max(), 1e-300)
+        assert err < 1e-10, (k_o, err)
+    assert out["d_logit_scale"] == pytest.approx(float(g["d_logit_scale_f64"]), rel=1e-9, abs=1e-13)
+    assert out["d_bias"] == pytest.approx(float(g["d_bias_f64"]), rel=1e-9, abs=1e-13)
+
+
+@pytest.mark.parametrize("path", golden_files("siglip_"), ids=os.path.basename)
+def test_siglip_torch_port_matches_reference_fp32(path):
+    import torch
+    g = np.load(path)
+    x = torch.tensor(g["image"], requires_grad=True)
+    y = torch.tensor(g["profile"], requires_grad=True)
+    ls = torch.tensor(float(g["logit_scale"]), dtype=torch.float32, requires_grad=True)
+    b = torch.tensor(float(g["bias"]), dtype=torch.float32, requires_grad=True)
+    loss = osig.siglip_loss_materialised(x, y, ls, b, int(g["buckets"]))
+    loss.backward()
+    assert float(loss) == pytest.approx(float(g["loss_f32"]), rel=2e-6)
+    np.testing.assert_allclose(x.grad.numpy(), g["d_image_f32"], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(y.grad.numpy(), g["d_profile_f32"], rtol=1e-4, atol=1e-7)
+    assert float(ls.grad) == pytest.approx(float(g["d_logit_scale_f32"]), rel=1e-3, abs=1e-6)
+    assert float(b.grad) == pytest.approx(float(g["d_bias_f32"]), rel=1e-3, abs=1e-6)
 
 
 @pytest.mark.parametrize("path", golden_files("ann_"), ids=os.path.basename)
