@@ -398,6 +398,12 @@ def main():
         except Exception as e:
             line["retrieval"] = {"error": repr(e)}
 
+        if world == 1:
+            try:
+                line["siglip"] = bench_siglip(args, dev, mode, flush, sync_all, peaks)
+            except Exception as e:
+                line["siglip"] = {"error": repr(e)}
+
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -426,6 +432,57 @@ def bench_c3(args, world, rank, dev, mode, flush, sync_all, max_over_ranks, peak
             "value": B_C3 / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "scaling": "strong",
             "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
             "frac_of_peak_all_gpus": flops / (ms * 1e-3) / 1e12 / (peaks["bf16_sustained"] * world)}
+
+
+def bench_siglip(args, dev, mode, flush, sync_all, peaks):
+    """SigLIP fwd+bwd at the primary shape (B=4096, d=256), CUDA-graph replay of
+    plk_siglip_loss_forward + plk_siglip_loss_backward, L2 flushed between steps; CPU port timed beside it."""
+    import torch
+    from multimodal_plankton_recognition_b200 import ops, synth
+    n, d = B_C2, D_C2
+    img, pro, _ = synth.pairs(n, d, 1234, dev)
+    ls = torch.ones((), device=dev)
+    bias = torch.full((), -10.0, device=dev)
+    go = torch.ones(1, device=dev)
+
+    def raw_step():
+        loss, state = ops.siglip_loss_forward_state(img, pro, ls, bias, n, mode)
+        return (loss,) + tuple(ops.siglip_loss_backward_state(go, img, pro, ls, bias, state, n, mode))
+
+    raw_step()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            raw_step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = raw_step()
+    steps = min(args.steps, 100)
+    ms = timed_steps(graph.replay, steps, 3, flush, sync_all) / steps
+    out = {"workload": f"SigLIP fwd+bwd, batch {n} x d={d}, {args.precision}", "value": n / (ms * 1e-3),
+           "unit": "pairs/s", "ms_per_step": ms,
+           "algorithmic_tflops": 6.0 * n * n * d / (ms * 1e-3) / 1e12,
+           "frac_of_peak": 6.0 * n * n * d / (ms * 1e-3) / 1e12 / peaks["bf16"]}
+    del keep
+    try:
+        from oracle import siglip as osig
+        torch.set_num_threads(os.cpu_count() or 1)
+        xc, yc = img.cpu().requires_grad_(), pro.cpu().requires_grad_()
+        lc, bc = torch.ones((), requires_grad=True), torch.full((), -10.0, requires_grad=True)
+        times = []
+        for _ in range(3):
+            xc.grad = yc.grad = lc.grad = bc.grad = None
+            t0 = time.perf_counter()
+            osig.siglip_loss_materialised(xc, yc, lc, bc, 1).backward()
+            times.append(time.perf_counter() - t0)
+        out["cpu_baseline"] = {"value": n / min(times), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"3 fwd+bwd steps of the same workload, best {1e3 * min(times):.1f} ms"}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
 
 
 def bench_retrieval(args, world, rank, dev, sync_all, max_over_ranks, peaks):

@@ -232,6 +232,36 @@ int plk_clip_loss_backward_xgpu(const float* grad_out, const float* grad_out_emb
                                 int world, unsigned* epoch, float* out2, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * N2. SigLIP pairwise-sigmoid loss on the same similarity mainloop.
+ *      replaces SigLIPLoss.forward and its autograd backward       reference src/coordination.py:67-95
+ *   z_ij = exp(*logit_scale) u_i.v_j + *bias  within the bucket of row i;
+ *   loss = (1/B) [ sum_{i != j} softplus(z_ij) + sum_i softplus(-z_ii) ]
+ *   state / workspace: plk_clip_loss_state_bytes() / plk_clip_loss_workspace_bytes() (same layout).
+ *   forward : normalise(both) -> fused similarity + softplus sum (no row/column statistics) -> loss.
+ *   backward: recompute backward with G = sigmoid(z) off the diagonal -> gradient tail (diagonal term
+ *             -sigmoid(-z_ii) in fp32) -> dx, dy [B, d] fp32, *dls, *dbias, all scaled by *grad_out.
+ *   Building blocks: plk_siglip_loss (loss = sums[0] / B) and plk_siglip_grad_finish_pair
+ *   (sums = double[3] from the forward: loss terms, sum_i G_ii S_ii, sum_i G_ii; gs2 = float[2] from the
+ *   recompute backward: sum G*S, sum G over the off-diagonal; consumed = reset to 0).
+ * ------------------------------------------------------------------------------------------ */
+int plk_siglip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
+                            int op_dtype, int64_t bucket_size, const float* logit_scale,
+                            const float* bias, void* state, float* loss_out, void* stream);
+int plk_siglip_loss_backward(const float* grad_out, const float* x, const float* y, int64_t batch,
+                             int64_t d, int64_t ldx, int op_dtype, int64_t bucket_size,
+                             const float* logit_scale, const float* bias, void* state,
+                             void* workspace, float* dx, float* dy, float* dls, float* dbias,
+                             void* stream);
+int plk_siglip_loss(const double* sums, int64_t batch, float* loss_out, void* stream);
+int plk_siglip_grad_finish_pair(const float* acc_x, const float* acc_y, int parts, const float* x,
+                                const float* y, int64_t n, int64_t d, int64_t ldx,
+                                const float* inv_den_x, const float* nrm_x, const float* inv_den_y,
+                                const float* nrm_y, const float* diag, const float* logit_scale,
+                                const float* bias, const float* grad_out, int64_t batch, float* gs2,
+                                const double* sums, float* dx, float* dy, float* dls_out,
+                                float* dbias_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Staging host-resident batches into HBM under the running step (no reference counterpart: the
  * reference hands each batch to the device serially through Lightning's loop,
  * reference scripts/train_multi.py:78-85).  A stager owns a copy stream and per-slot events:

@@ -5,7 +5,7 @@ with the inverse-distance k-NN vote (``ANNClassifier``, drop-in for reference sr
 
 All arithmetic runs in ``libplk.so`` (hand-written CUDA, C ABI in ``include/plk.h``).
 """
-from .coordination import CLIPLoss, CLIPPlus  # noqa: F401
+from .coordination import CLIPLoss, CLIPPlus, SigLIPLoss, SigLIPPlus  # noqa: F401
 from .ann import ANNClassifier  # noqa: F401
 
-__all__ = ["CLIPLoss", "CLIPPlus", "ANNClassifier"]
+__all__ = ["CLIPLoss", "CLIPPlus", "SigLIPLoss", "SigLIPPlus", "ANNClassifier"]

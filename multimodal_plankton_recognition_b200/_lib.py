@@ -104,6 +104,12 @@ SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp]),
     "plk_clip_loss_backward_xgpu": (_int, [_vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp,
                                            _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp]),
+    "plk_siglip_loss_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "plk_siglip_loss_backward": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _int, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp]),
+    "plk_siglip_loss": (_int, [_vp, _i64, _vp, _vp]),
+    "plk_siglip_grad_finish_pair": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "plk_stager_create": (_vp, [_int, _int]),
     "plk_stager_destroy": (None, [_vp]),
     "plk_stager_issue": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp, _sz]),

@@ -58,6 +58,49 @@ class CLIPLoss(Module):
         return f"precision={self.precision}, sharded={self.sharded}"
 
 
+class SigLIPLoss(Module):
+    """Pairwise-sigmoid coordination loss (https://arxiv.org/abs/2303.15343), drop-in for reference
+    src/coordination.py:67-95: parameters ``logit_scale`` (init 1.0) and ``bias`` (init -10.0), both
+    0-dim fp32; ``loss(image_emb=..., profile_emb=..., buckets=...)``.  Same similarity mainloop as
+    `CLIPLoss` with a softplus epilogue -- no row / column statistics, so the forward is one pass and
+    the recompute backward needs nothing from it.  Single GPU."""
+
+    def __init__(self, *, precision: str | None = None) -> None:
+        super().__init__()
+        self.logit_scale = Parameter(torch.ones([]))
+        self.bias = Parameter(-10 * torch.ones([]))
+        precision = precision or os.environ.get("PLK_PRECISION", "bf16")
+        if precision not in ops.MODES:
+            raise ValueError(f"precision must be one of {sorted(ops.MODES)}, got {precision!r}")
+        self.precision = precision
+
+    def forward(self, image_emb: Tensor, profile_emb: Tensor, buckets: int = 1) -> Tensor:
+        assert image_emb.size(0) % buckets == 0, \
+            "Batch size must be divisible by number of buckets!"
+        if image_emb.dim() != 2 or image_emb.shape != profile_emb.shape:
+            raise ValueError(f"expected two [B, d] embeddings of equal shape, got "
+                             f"{tuple(image_emb.shape)} and {tuple(profile_emb.shape)}")
+        return ops.siglip_loss(image_emb, profile_emb, self.logit_scale, self.bias, int(buckets),
+                               ops.MODES[self.precision])
+
+    def extra_repr(self) -> str:
+        return f"precision={self.precision}"
+
+
+class SigLIPPlus(Module):
+    """Drop-in for reference src/coordination.py:98-112: the fused SigLIP term plus ``beta`` times the MSE
+    between the RAW embeddings; parameter paths ``siglip.logit_scale`` / ``siglip.bias``."""
+
+    def __init__(self, beta: float = 0.25, *, precision: str | None = None) -> None:
+        super().__init__()
+        self.siglip = SigLIPLoss(precision=precision)
+        self.l2 = MSELoss()
+        self.beta = beta
+
+    def forward(self, image_emb: Tensor, profile_emb: Tensor, buckets: int = 1) -> Tensor:
+        return self.siglip(image_emb, profile_emb, buckets) + self.beta * self.l2(image_emb, profile_emb)
+
+
 class CLIPPlus(Module):
     """Drop-in for reference src/coordination.py:50-64: the fused InfoNCE term
     plus ``beta`` times the MSE between the RAW embeddings.  The MSE term is one elementwise pass and

@@ -228,6 +228,74 @@ int plk_clip_loss_backward_xgpu(const float* grad_out, const float* grad_out_emb
                             out2, stream);
 }
 
+// ---- N2: SigLIP loss (reference src/coordination.py:67-95) on the same state layout ----
+//   aux region: double sums[3] (loss terms, sum_i G_ii S_ii, sum_i G_ii) at +0, float gs2[2] at +32
+int plk_siglip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx, int op_dtype,
+                            int64_t bucket_size, const float* logit_scale, const float* bias, void* state,
+                            float* loss_out, void* stream) {
+  PLK_REQUIRE(x && y && logit_scale && bias && state && loss_out, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(op_dtype >= PLK_F32 && op_dtype <= PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
+  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0, PLK_ERR_INVALID,
+              "bad shape batch=%lld d=%lld ldx=%lld bucket_size=%lld", (long long)batch, (long long)d,
+              (long long)ldx, (long long)bucket_size);
+  PLK_REQUIRE(((uintptr_t)state & 255) == 0, PLK_ERR_INVALID, "state must be 256-byte aligned");
+  const ClipState L(op_dtype, batch, d);
+  char* base = (char*)state;
+  float* st = (float*)(base + L.stats);
+  double* sums = (double*)(base + L.aux);
+  const int64_t B = batch;
+  cudaStream_t cst = (cudaStream_t)stream;
+  int rc = plk_l2norm_pair_fwd(x, y, B, d, ldx, base + L.u, base + L.v, op_dtype, L.ld, st, st + B, st + 2 * B,
+                               st + 3 * B, nullptr, 0, (float*)(base + L.aux), 16, stream);
+  if (rc) return rc;
+  if (op_dtype == PLK_F32)
+    rc = siglip_fwd_f32((const float*)(base + L.u), (const float*)(base + L.v), L.ld, B, 0, B, d, bucket_size,
+                        logit_scale, bias, st + 6 * B, sums, cst);
+  else
+    rc = siglip_fwd_tc16(base + L.u, base + L.v, op_dtype == PLK_F16, L.ld, B, 0, B, d, bucket_size, logit_scale, bias,
+                         st + 6 * B, sums, cst);
+  if (rc) return rc;
+  return plk_siglip_loss(sums, B, loss_out, stream);
+}
+
+int plk_siglip_loss_backward(const float* grad_out, const float* x, const float* y, int64_t batch, int64_t d,
+                             int64_t ldx, int op_dtype, int64_t bucket_size, const float* logit_scale,
+                             const float* bias, void* state, void* workspace, float* dx, float* dy, float* dls,
+                             float* dbias, void* stream) {
+  PLK_REQUIRE(grad_out && x && y && logit_scale && bias && state && workspace && dx && dy && dls && dbias,
+              PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(op_dtype >= PLK_F32 && op_dtype <= PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
+  PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0, PLK_ERR_INVALID,
+              "bad shape");
+  const ClipState L(op_dtype, batch, d);
+  char* base = (char*)state;
+  float* st = (float*)(base + L.stats);
+  const double* sums = (const double*)(base + L.aux);
+  float* gs2 = (float*)(base + L.aux + 32);
+  const int64_t B = batch;
+  const int parts = clip_parts(op_dtype, B, d, bucket_size);
+  float* acc_x = (float*)workspace;
+  float* acc_y = acc_x + (size_t)parts * B * d;
+  cudaStream_t cst = (cudaStream_t)stream;
+  int rc;
+  if (op_dtype == PLK_F32) {
+    rc = siglip_grad_f32((const float*)(base + L.u), (const float*)(base + L.v), L.ld, B, 0, B, d, bucket_size,
+                         logit_scale, bias, acc_x, gs2, cst);
+    if (rc) return rc;
+    rc = siglip_grad_f32((const float*)(base + L.v), (const float*)(base + L.u), L.ld, B, 0, B, d, bucket_size,
+                         logit_scale, bias, acc_y, nullptr, cst);
+  } else {
+    static const bool overlap = getenv("PLK_PDL") == nullptr || getenv("PLK_PDL")[0] != '0';
+    rc = infonce_grad_pair_tc16(base + L.u, base + L.v, base + L.v, base + L.u, op_dtype == PLK_F16, L.ld, B, 0, B,
+                                d, bucket_size, logit_scale, nullptr, nullptr, nullptr, nullptr, acc_x, acc_y, gs2,
+                                cst, overlap ? 1 : 0, bias);
+  }
+  if (rc) return rc;
+  return plk_siglip_grad_finish_pair(acc_x, acc_y, parts, x, y, B, d, ldx, st, st + B, st + 2 * B, st + 3 * B,
+                                     st + 6 * B, logit_scale, bias, grad_out, B, gs2, sums, dx, dy, dls, dbias,
+                                     stream);
+}
+
 size_t plk_topk_workspace_bytes(int64_t nq, int64_t ng, int64_t d, int kc, int op_dtype) {
   return op_dtype == PLK_F32 ? topk_ws_f32(nq, ng, d, kc) : topk_ws_tc16(nq, ng, d, kc);
 }

@@ -33,6 +33,29 @@ constexpr float kLog2e = 1.4426950408889634f;
     }                                 \
   } while (0)
 
+// ---- accurate fp32 logistic helpers (SigLIP epilogues of the fp32 path and the gradient tails) ----
+#ifdef __CUDACC__
+__device__ __forceinline__ float sigmoid_f(float z) {
+  const float e = expf(-fabsf(z));
+  return z >= 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+}
+__device__ __forceinline__ float softplus_f(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
+// Scale and diagonal term of the gradient tail (plk_infonce_grad_finish*):
+//   InfoNCE (bias == nullptr): coef = g s / (2B), dterm = E_ii (1/rs_i + 1/cs_i) - 2
+//   SigLIP  (bias != nullptr): coef = g s / B,    dterm = -sigmoid(-(S_ii + bias))
+__device__ __forceinline__ void tail_terms(const float* bias, float diag_i, const float* rs, const float* cs,
+                                           int64_t row, float s, float go, int64_t batch, float& coef,
+                                           float& dterm) {
+  if (bias != nullptr) {
+    dterm = -sigmoid_f(-(diag_i + *bias));
+    coef = go * s / (float)batch;
+  } else {
+    dterm = expf(diag_i - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
+    coef = go * s / (2.0f * (float)batch);
+  }
+}
+#endif
+
 // ---- programmatic dependent launch (sm_90+) ---------------------------------------------------
 // A grid launched with launch_overlapped() may become resident while the previous kernel in the
 // stream is still running: once every thread block of that kernel has executed pdl_trigger() (or
@@ -96,7 +119,17 @@ int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1, const
                            int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d,
                            int64_t bs, const float* ls, const float* rs0, const float* cs0,
                            const float* rs1, const float* cs1, float* acc0, float* acc1, float* gs,
-                           cudaStream_t st, int overlap_prev = 0);
+                           cudaStream_t st, int overlap_prev = 0, const float* siglip_bias = nullptr);
+// SigLIP variants (reference src/coordination.py:67-95): fp32 CUDA-core path / tensor-core forward
+int siglip_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                   int64_t d, int64_t bs, const float* ls, const float* bias, float* diag, double* sums,
+                   cudaStream_t st);
+int siglip_grad_f32(const float* a, const float* b, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                    int64_t d, int64_t bs, const float* ls, const float* bias, float* acc, float* gs2,
+                    cudaStream_t st);
+int siglip_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows, int64_t row_offset,
+                    int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* bias, float* diag,
+                    double* sums, cudaStream_t st);
 int topk_candidates_tc16(const void* q, const void* g, int f16, int64_t ld, const float* g_sqn,
                          int64_t nq, int64_t ng, int64_t d, int kc, int64_t goff, int32_t* cand_idx,
                          float* cand_key, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -278,6 +278,21 @@ __global__ void dls_kernel(const float* gs, const float* diag_sum, const float* 
   *out = (float)((double)(*grad_out) / (2.0 * (double)batch) * ((double)(*gs) - 2.0 * (double)(*diag_sum)));
 }
 
+// SigLIP scalars.  loss = sums[0] / B;  d logit_scale = g/B (gs2[0] + sums[1]);  d bias = g/B (gs2[1] + sums[2])
+__global__ void siglip_loss_kernel(const double* __restrict__ sums, int64_t batch, float* __restrict__ loss_out) {
+  pdl_wait();
+  pdl_trigger();
+  *loss_out = (float)(sums[0] / (double)batch);
+}
+__global__ void siglip_scalars_kernel(float* gs2, const double* __restrict__ sums, const float* __restrict__ grad_out,
+                                      int64_t batch, float* dls_out, float* dbias_out) {
+  const double g_b = (double)(*grad_out) / (double)batch;
+  *dls_out = (float)(g_b * ((double)gs2[0] + sums[1]));
+  *dbias_out = (float)(g_b * ((double)gs2[1] + sums[2]));
+  gs2[0] = 0.f;
+  gs2[1] = 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // a9 tail: -2*delta term, g*s/(2B) scaling, normalisation backward.
 // ---------------------------------------------------------------------------------------------
@@ -288,14 +303,13 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(
     const float* __restrict__ nrm_x, const float* __restrict__ inv_den_p,
     const float* __restrict__ diag, const float* __restrict__ rs, const float* __restrict__ cs,
     const float* __restrict__ ls, const float* __restrict__ grad_out, int64_t batch,
-    TO* __restrict__ dx) {
+    TO* __restrict__ dx, const float* __restrict__ bias) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float s = expf(*ls);
-  const float coef = (*grad_out) * s / (2.0f * (float)batch);
-  // fp32 diagonal term: G_ii - 2 = E_ii (1/rs_i + 1/cs_i) - 2
-  const float dterm = expf(diag[row] - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
+  float coef, dterm;   // fp32 diagonal term (InfoNCE: G_ii - 2; SigLIP: G_ii)
+  tail_terms(bias, diag[row], rs, cs, row, s, *grad_out, batch, coef, dterm);
   const float idx_ = inv_den_x[row], idp = inv_den_p[row];
   const bool clamped = !(nrm_x[row] > kNormEps);
   const float* ar = acc + row * d;
@@ -329,7 +343,7 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(
     const float* __restrict__ nrm_x, const float* __restrict__ inv_den_p,
     const float* __restrict__ diag, const float* __restrict__ rs, const float* __restrict__ cs,
     const float* __restrict__ ls, const float* __restrict__ grad_out, int64_t batch,
-    float* __restrict__ dx) {
+    float* __restrict__ dx, const float* __restrict__ bias) {
   constexpr int64_t d = NV * 128;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -353,10 +367,10 @@ __global__ void __launch_bounds__(256) grad_finish_vec_kernel(
     }
   }
   const float s = expf(*ls);
-  const float coef = (*grad_out) * s / (2.0f * (float)batch);
+  float coef, dterm;
+  tail_terms(bias, diag[row], rs, cs, row, s, *grad_out, batch, coef, dterm);
   const float idx_ = inv_den_x[row], idp = inv_den_p[row];
   const bool clamped = !(nrm_x[row] > kNormEps);
-  const float dterm = expf(diag[row] - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
   float dot = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -384,6 +398,11 @@ struct FinishPairArgs {
   const float* nrm[2];
   float* dx[2];
   float emb_scale;          // extra factor on the embedding gradients (world size under DDP averaging)
+  // SigLIP mode (bias != nullptr): gs -> float[2] (sum G*S, sum G over the off-diagonal), sig_sums ->
+  // double[3] from the forward (sum of loss terms, sum_i G_ii S_ii, sum_i G_ii), dbias_out = d loss / d bias
+  const float* bias;
+  const double* sig_sums;
+  float* dbias_out;
 };
 // Cross-GPU sum of the two per-rank scalars of a sharded step (loss partial, d logit_scale
 // partial), fused into the gradient tail: the ranks exchange them through peer-mapped symmetric
@@ -467,7 +486,14 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
   if (blockIdx.x == 0 && m == 0 && threadIdx.x < 32 && dls_out != nullptr) {
     float dls_local = 0.f;
     if (threadIdx.x == 0) {
-      dls_local = (float)((double)(*grad_out_dls) / (2.0 * (double)batch) * ((double)(*gs) - 2.0 * (double)(*diag_sum)));
+      if (a.bias != nullptr) {
+        const double g_b = (double)(*grad_out_dls) / (double)batch;
+        dls_local = (float)(g_b * ((double)gs[0] + a.sig_sums[1]));
+        *a.dbias_out = (float)(g_b * ((double)gs[1] + a.sig_sums[2]));
+        gs[1] = 0.f;
+      } else {
+        dls_local = (float)((double)(*grad_out_dls) / (2.0 * (double)batch) * ((double)(*gs) - 2.0 * (double)(*diag_sum)));
+      }
       *dls_out = dls_local;
       *gs = 0.f;   // consumed: the accumulator is back to its zero-initialised state
     }
@@ -498,10 +524,10 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     }
   }
   const float s = expf(*ls);
-  const float coef = (*grad_out) * a.emb_scale * s / (2.0f * (float)batch);
+  float coef, dterm;
+  tail_terms(a.bias, diag[row], rs, cs, row, s, (*grad_out) * a.emb_scale, batch, coef, dterm);
   const float idx_ = a.inv_den[m][row], idp = a.inv_den[1 - m][row];
   const bool clamped = !(a.nrm[m][row] > kNormEps);
-  const float dterm = expf(diag[row] - s) * (1.0f / rs[row] + 1.0f / cs[row]) - 2.0f;
   float dot = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -525,12 +551,12 @@ template <typename TI>
 static int grad_finish_dispatch(const float* acc, int parts, const TI* x, const TI* p, int64_t n, int64_t d,
                                 int64_t ldx, const float* idx_, const float* nrm, const float* idp,
                                 const float* diag, const float* rs, const float* cs, const float* ls, const float* go, int64_t batch, void* dx,
-                                int dx_dtype, cudaStream_t st) {
+                                int dx_dtype, cudaStream_t st, const float* bias = nullptr) {
   dim3 block(256), grid((unsigned)ceil_div(n, 8));
   if constexpr (sizeof(TI) == 4) {
     if (dx_dtype == PLK_F32 && d % 128 == 0 && d <= 1024 && (ldx & 3) == 0 && (((uintptr_t)x | (uintptr_t)p | (uintptr_t)acc | (uintptr_t)dx) & 15) == 0) {
       switch (d / 128) {
-#define PLK_CASE(NV) case NV: grad_finish_vec_kernel<NV><<<grid, block, 0, st>>>(acc, parts, (const float*)x, (const float*)p, n, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (float*)dx); break;
+#define PLK_CASE(NV) case NV: grad_finish_vec_kernel<NV><<<grid, block, 0, st>>>(acc, parts, (const float*)x, (const float*)p, n, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (float*)dx, bias); break;
         PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
       }
@@ -539,11 +565,11 @@ static int grad_finish_dispatch(const float* acc, int parts, const TI* x, const 
     }
   }
   if (dx_dtype == PLK_F32)
-    grad_finish_kernel<TI, float><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (float*)dx);
+    grad_finish_kernel<TI, float><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (float*)dx, bias);
   else if (dx_dtype == PLK_BF16)
-    grad_finish_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (__nv_bfloat16*)dx);
+    grad_finish_kernel<TI, __nv_bfloat16><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (__nv_bfloat16*)dx, bias);
   else
-    grad_finish_kernel<TI, __half><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (__half*)dx);
+    grad_finish_kernel<TI, __half><<<grid, block, 0, st>>>(acc, parts, x, p, n, d, ldx, idx_, nrm, idp, diag, rs, cs, ls, go, batch, (__half*)dx, bias);
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
@@ -781,10 +807,14 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
                                  const float* logit_scale, const float* grad_out_emb,
                                  const float* grad_out, int64_t batch_global, float* gs,
                                  const float* diag_sum, float* dx, float* dy, float* dls_out,
-                                 const XGpuArgs& xg, void* stream, float emb_scale = 1.0f) {
-  PLK_REQUIRE(acc_x && acc_y && x && y && inv_den_x && nrm_x && inv_den_y && nrm_y && diag && rs && cs &&
-                  logit_scale && grad_out_emb && grad_out && gs && diag_sum && dx && dy && dls_out,
+                                 const XGpuArgs& xg, void* stream, float emb_scale = 1.0f,
+                                 const float* bias = nullptr, const double* sig_sums = nullptr,
+                                 float* dbias_out = nullptr) {
+  PLK_REQUIRE(acc_x && acc_y && x && y && inv_den_x && nrm_x && inv_den_y && nrm_y && diag &&
+                  logit_scale && grad_out_emb && grad_out && gs && dx && dy && dls_out,
               PLK_ERR_INVALID, "null pointer");
+  if (bias != nullptr) PLK_REQUIRE(sig_sums && dbias_out, PLK_ERR_INVALID, "null pointer");
+  else PLK_REQUIRE(rs && cs && diag_sum, PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(n > 0 && d > 0 && ldx >= d && batch_global >= n && parts >= 1, PLK_ERR_INVALID, "bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec_ok = d % 128 == 0 && d <= 1024 && (ldx & 3) == 0 &&
@@ -795,6 +825,7 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
     a.inv_den[0] = inv_den_x; a.inv_den[1] = inv_den_y; a.nrm[0] = nrm_x; a.nrm[1] = nrm_y;
     a.dx[0] = dx; a.dx[1] = dy;
     a.emb_scale = emb_scale;
+    a.bias = bias; a.sig_sums = sig_sums; a.dbias_out = dbias_out;
     dim3 block(256), grid((unsigned)ceil_div(n, 8), 2);
     switch (d / 128) {
 #define PLK_CASE(NV) case NV: PLK_CUDA(launch_overlapped(grad_finish_pair_vec_kernel<NV>, grid, block, st, a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out, xg)); break;
@@ -806,6 +837,17 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
   }
   PLK_REQUIRE(xg.peer == nullptr && emb_scale == 1.0f, PLK_ERR_UNSUPPORTED,
               "the fused cross-GPU scalar exchange / emb_scale need d % 128 == 0 (d <= 1024) and 16-byte aligned rows");
+  if (bias != nullptr) {   // SigLIP, ragged width: one tail per modality + the scalars
+    int rc = grad_finish_dispatch(acc_x, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, diag, rs, cs, logit_scale,
+                                  grad_out_emb, batch_global, dx, PLK_F32, st, bias);
+    if (rc) return rc;
+    rc = grad_finish_dispatch(acc_y, parts, y, x, n, d, ldx, inv_den_y, nrm_y, inv_den_x, diag, rs, cs, logit_scale,
+                              grad_out_emb, batch_global, dy, PLK_F32, st, bias);
+    if (rc) return rc;
+    siglip_scalars_kernel<<<1, 1, 0, st>>>(gs, sig_sums, grad_out, batch_global, dls_out, dbias_out);
+    PLK_LAUNCHED(1);
+    return PLK_OK;
+  }
   int rc = plk_infonce_grad_finish(acc_x, parts, x, y, PLK_F32, n, d, ldx, inv_den_x, nrm_x, inv_den_y, diag, rs, cs,
                                    logit_scale, grad_out_emb, batch_global, dx, PLK_F32, stream);
   if (rc) return rc;
@@ -850,6 +892,26 @@ int plk_infonce_grad_finish_pair_xgpu(const float* acc_x, const float* acc_y, in
   return finish_pair_impl(acc_x, acc_y, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, nrm_y, diag, rs, cs,
                           logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dx, dy, dls_out, xg,
                           stream);
+}
+
+int plk_siglip_loss(const double* sums, int64_t batch, float* loss_out, void* stream) {
+  PLK_REQUIRE(sums && loss_out && batch > 0, PLK_ERR_INVALID, "bad args");
+  PLK_CUDA(launch_overlapped(siglip_loss_kernel, dim3(1), dim3(1), (cudaStream_t)stream, sums, batch, loss_out));
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int plk_siglip_grad_finish_pair(const float* acc_x, const float* acc_y, int parts, const float* x, const float* y,
+                                int64_t n, int64_t d, int64_t ldx, const float* inv_den_x, const float* nrm_x,
+                                const float* inv_den_y, const float* nrm_y, const float* diag,
+                                const float* logit_scale, const float* bias, const float* grad_out,
+                                int64_t batch, float* gs2, const double* sums, float* dx, float* dy,
+                                float* dls_out, float* dbias_out, void* stream) {
+  PLK_REQUIRE(bias != nullptr, PLK_ERR_INVALID, "null pointer");
+  XGpuArgs xg = {};
+  return finish_pair_impl(acc_x, acc_y, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, nrm_y, diag, nullptr,
+                          nullptr, logit_scale, grad_out, grad_out, batch, gs2, nullptr, dx, dy, dls_out, xg, stream,
+                          1.0f, bias, sums, dbias_out);
 }
 
 }  // extern "C"

@@ -61,6 +61,63 @@ __device__ __forceinline__ void tile_col_range(int64_t i0, int64_t n_rows, int64
   jhi = hi2;
 }
 
+// SigLIP forward (reference src/coordination.py:85-93) on the same tiles: z = S + bias, the loss term is
+// softplus(z) off the diagonal and softplus(-z) on it; no row / column statistics.  Accumulates
+// sums[0] += loss terms, sums[1] += G_ii S_ii, sums[2] += G_ii with G_ii = -sigmoid(-z_ii).
+__global__ void __launch_bounds__(NT) siglip_fwd_simt(
+    const float* __restrict__ u, const float* __restrict__ v, int64_t ld, int64_t n_rows,
+    int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* __restrict__ ls,
+    const float* __restrict__ bias, float* __restrict__ diag, double* __restrict__ sums) {
+  __shared__ float As[BK][BM + 1];
+  __shared__ float Bs[BK][BN + 1];
+  __shared__ float red[3][NT / 32];
+  const int64_t i0 = (int64_t)blockIdx.y * BM;
+  const int64_t j0 = (int64_t)blockIdx.x * BN;
+  int64_t jlo, jhi;
+  tile_col_range(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  if (j0 + BN <= jlo || j0 >= jhi) return;
+  float acc[4][4];
+  tile_gemm_64x64(u, n_rows, i0, v, n_cols, j0, d, ld, As, Bs, acc);
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const float s = expf(*ls), b0 = *bias;
+  float part[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t i = i0 + ty * 4 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    if (i < n_rows) bucket_range(gi, bs, n_cols, lo, hi);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int64_t j = j0 + tx + 16 * c;
+      if (!(i < n_rows && j >= lo && j < hi)) continue;
+      const float S = s * acc[r][c];
+      const float z = S + b0;
+      if (j == gi) {
+        diag[i] = S;
+        part[0] += softplus_f(-z);
+        const float g = -sigmoid_f(-z);
+        part[1] = fmaf(g, S, part[1]);
+        part[2] += g;
+      } else {
+        part[0] += softplus_f(z);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part[k] += __shfl_xor_sync(0xffffffffu, part[k], o);
+    if ((t & 31) == 0) red[k][t >> 5] = part[k];
+  }
+  __syncthreads();
+  if (t < 3) {
+    double tot = 0.0;
+    for (int w = 0; w < NT / 32; ++w) tot += (double)red[t][w];
+    if (tot != 0.0) atomicAdd(sums + t, tot);
+  }
+}
+
 __global__ void __launch_bounds__(NT) infonce_fwd_simt(
     const float* __restrict__ u, const float* __restrict__ v, int64_t ld, int64_t n_rows,
     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* __restrict__ ls,
@@ -112,12 +169,15 @@ __global__ void __launch_bounds__(NT) infonce_fwd_simt(
 
 // One direction of the recompute backward.  CTA = (64 owned rows) x (128 output columns of d);
 // loops over the column tiles of the rows' buckets: S tile -> G tile in shared memory -> G.B.
+// SIG: SigLIP weights G = sigmoid(S + bias) off the diagonal (rs / cs unused); gs_out is then
+// float[2] = (sum G*S, sum G).
 constexpr int DC = 128;
+template <bool SIG>
 __global__ void __launch_bounds__(NT) infonce_grad_simt(
     const float* __restrict__ a, const float* __restrict__ b, int64_t ld, int64_t n_rows,
     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* __restrict__ ls,
     const float* __restrict__ rs, const float* __restrict__ cs, float* __restrict__ acc_out,
-    float* __restrict__ gs_out) {
+    float* __restrict__ gs_out, const float* __restrict__ bias) {
   __shared__ float As[BK][BM + 1];
   __shared__ float Bs[BK][BN + 1];
   __shared__ float Gs[BM][BN + 1];
@@ -140,9 +200,12 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
     rrs[r] = 0.f;
     if (i < n_rows) {
       bucket_range(row_offset + i, bs, n_cols, lo[r], hi[r]);
-      rrs[r] = 1.0f / rs[i];
+      if constexpr (!SIG) rrs[r] = 1.0f / rs[i];
     }
   }
+  float b0 = 0.f;
+  if constexpr (SIG) b0 = *bias;
+  float gsum_local = 0.f;
   float out[4][8];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -153,7 +216,9 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
   for (int64_t j0 = jlo; j0 < jhi; j0 += BN) {
     float acc[4][4];
     tile_gemm_64x64(a, n_rows, i0, b, n_cols, j0, d, ld, As, Bs, acc);
-    if (t < BN) rcs[t] = (j0 + t < n_cols) ? 1.0f / cs[j0 + t] : 0.f;
+    if constexpr (!SIG) {
+      if (t < BN) rcs[t] = (j0 + t < n_cols) ? 1.0f / cs[j0 + t] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -162,10 +227,17 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
         const int64_t j = j0 + tx + 16 * c;
         const bool valid = j >= lo[r] && j < hi[r];
         const float S = s * acc[r][c];
-        const float G = valid ? expf(S - s) * (rrs[r] + rcs[tx + 16 * c]) : 0.f;
+        const bool on_diag = j == row_offset + i0 + ty * 4 + r;
+        float G;
+        if constexpr (SIG) {
+          G = (valid && !on_diag) ? sigmoid_f(S + b0) : 0.f;
+          gsum_local += G;
+        } else {
+          G = valid ? expf(S - s) * (rrs[r] + rcs[tx + 16 * c]) : 0.f;
+        }
         gs_local = fmaf(G, S, gs_local);
         // the j == i term is added (in fp32, together with -2*delta) by plk_infonce_grad_finish
-        Gs[ty * 4 + r][tx + 16 * c] = (j == row_offset + i0 + ty * 4 + r) ? 0.f : G;
+        Gs[ty * 4 + r][tx + 16 * c] = on_diag ? 0.f : G;
       }
     __syncthreads();
     // out[64 x 128] += Gs[64 x 64] . b[j0:j0+64, dc0:dc0+128]
@@ -211,6 +283,18 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
       for (int w = 0; w < NT / 32; ++w) tot += red[w];
       atomicAdd(gs_out, tot);
     }
+    if constexpr (SIG) {
+      __syncthreads();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gsum_local += __shfl_xor_sync(0xffffffffu, gsum_local, o);
+      if ((t & 31) == 0) red[t >> 5] = gsum_local;
+      __syncthreads();
+      if (t == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < NT / 32; ++w) tot += red[w];
+        atomicAdd(gs_out + 1, tot);
+      }
+    }
   }
 }
 
@@ -232,7 +316,27 @@ int infonce_grad_f32(const float* a, const float* b, int64_t ld, int64_t n_rows,
                      int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs,
                      const float* cs, float* acc, float* gs, cudaStream_t st) {
   dim3 grid((unsigned)ceil_div(d, DC), (unsigned)ceil_div(n_rows, BM));
-  infonce_grad_simt<<<grid, NT, 0, st>>>(a, b, ld, n_rows, row_offset, n_cols, d, bs, ls, rs, cs, acc, gs);
+  infonce_grad_simt<false><<<grid, NT, 0, st>>>(a, b, ld, n_rows, row_offset, n_cols, d, bs, ls, rs, cs, acc, gs,
+                                                nullptr);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int siglip_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                   int64_t d, int64_t bs, const float* ls, const float* bias, float* diag, double* sums,
+                   cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(n_cols, BN), (unsigned)ceil_div(n_rows, BM));
+  siglip_fwd_simt<<<grid, NT, 0, st>>>(u, v, ld, n_rows, row_offset, n_cols, d, bs, ls, bias, diag, sums);
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int siglip_grad_f32(const float* a, const float* b, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                    int64_t d, int64_t bs, const float* ls, const float* bias, float* acc, float* gs2,
+                    cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(d, DC), (unsigned)ceil_div(n_rows, BM));
+  infonce_grad_simt<true><<<grid, NT, 0, st>>>(a, b, ld, n_rows, row_offset, n_cols, d, bs, ls, nullptr, nullptr, acc,
+                                               gs2, bias);
   PLK_LAUNCHED(1);
   return PLK_OK;
 }

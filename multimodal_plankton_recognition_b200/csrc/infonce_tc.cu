@@ -106,6 +106,31 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&raw)[32], uint32_t (
   }
 }
 
+// SigLIP variant (reference src/coordination.py:85-93): G = sigmoid(z) off the diagonal, z = s a + bias,
+// given as zl = a*c1 + c0 with c1 = s log2(e), c0 = bias log2(e).  No row / column statistics.
+// gs_local += G a (sum G*S after the final * s), gsum_local += G (for d bias).
+template <bool F16, bool EDGE, bool GS>
+__device__ __forceinline__ void sig_chunk(const uint32_t (&raw)[32], uint32_t (&packed)[16], float c1, float c0,
+                                          int lo_rel, int hi_rel, int dei, float& gs_local, float& gsum_local) {
+#pragma unroll
+  for (int e2 = 0; e2 < 16; ++e2) {
+    float gg[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int e = e2 * 2 + x;
+      const float a = __uint_as_float(raw[e]);
+      float G = sigmoid_l2(fmaf(a, c1, c0));
+      if constexpr (EDGE) G = (e >= lo_rel && e < hi_rel && e != dei) ? G : 0.f;
+      if constexpr (GS) {
+        gs_local = fmaf(G, a, gs_local);
+        gsum_local += G;
+      }
+      gg[x] = G;
+    }
+    packed[e2] = pack_16x2<F16>(gg[0], gg[1]);
+  }
+}
+
 // chunk-relative validity window [lo_rel, hi_rel) and diagonal position of a row for the 32 columns
 // starting at global column jc0 (all 32-bit)
 __device__ __forceinline__ void chunk_window(int64_t lo, int64_t hi, int64_t gi, int64_t jc0, int& lo_rel,
@@ -120,10 +145,21 @@ template <bool F16>
 __device__ __forceinline__ void grad_chunk_dispatch(const uint32_t (&raw)[32], uint32_t (&packed)[16],
                                                     const float* rc_smem, float rrs, float c1, float c0,
                                                     int64_t lo, int64_t hi, int64_t gi, int64_t jc0,
-                                                    bool want_gs, float& gs_local) {
+                                                    bool want_gs, float& gs_local, bool siglip,
+                                                    float& gsum_local) {
   int lo_rel, hi_rel, dei;
   chunk_window(lo, hi, gi, jc0, lo_rel, hi_rel, dei);
   const bool plain = __all_sync(0xffffffffu, lo_rel == 0 && hi_rel == 32 && dei < 0);
+  if (siglip) {   // warp-uniform (a launch parameter)
+    if (plain) {
+      if (want_gs) sig_chunk<F16, false, true>(raw, packed, c1, c0, 0, 32, -1, gs_local, gsum_local);
+      else sig_chunk<F16, false, false>(raw, packed, c1, c0, 0, 32, -1, gs_local, gsum_local);
+    } else {
+      if (want_gs) sig_chunk<F16, true, true>(raw, packed, c1, c0, lo_rel, hi_rel, dei, gs_local, gsum_local);
+      else sig_chunk<F16, true, false>(raw, packed, c1, c0, lo_rel, hi_rel, dei, gs_local, gsum_local);
+    }
+    return;
+  }
   if (plain) {
     if (want_gs) grad_chunk<F16, false, true>(raw, packed, rc_smem, rrs, c1, c0, 0, 32, -1, gs_local);
     else grad_chunk<F16, false, false>(raw, packed, rc_smem, rrs, c1, c0, 0, 32, -1, gs_local);
@@ -151,7 +187,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
     const __grid_constant__ CUtensorMap tmap_bp, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tiles_per_seg,
     const float* __restrict__ ls, float* __restrict__ row_sumexp, float* __restrict__ col_sumexp,
-    float* __restrict__ diag, int f16) {
+    float* __restrict__ diag, int f16, const float* __restrict__ sig_bias, double* __restrict__ sig_sums) {
+  // sig_bias != nullptr: SigLIP epilogue (reference src/coordination.py:85-93) on the same mainloop --
+  // no row / column statistics; sig_sums[0..2] += (loss terms, sum_i G_ii S_ii, sum_i G_ii)
   using Cfg = FwdCfg<KD>;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -275,8 +313,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     int64_t lo = 0, hi = 0;
     if (i < n_rows) bucket_range(gi, bs, n_cols, lo, hi);
     const float s = expf(*ls);
-    const float c1 = s * kLog2e, c0 = -c1;
+    const bool siglip = sig_bias != nullptr;
+    const float c1 = s * kLog2e, c0 = siglip ? *sig_bias * kLog2e : -c1;
     float rsum = 0.f;
+    float sg_loss = 0.f, sg_gs = 0.f, sg_g = 0.f;
     {  // park this thread's owned row (16-bit operand, padded to KD*64) in TMEM columns 256.. as packed
        // pairs -- the A operand of the TS-mode MMA; the four warps of a lane quadrant take alternate chunks.
        // Source: the swizzled staging slots (rows past n_rows were zero-filled by the TMA unit).
@@ -310,6 +350,40 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       const bool full = (j0 >= lo) && (j0 + 32 <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full);
       const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + 32 && i < n_rows);
+      if (siglip) {   // warp-uniform (a launch parameter)
+        float part = 0.f;
+        if (warp_full) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) part += softplus_l2(fmaf(__uint_as_float(raw[e]), c1, c0));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int64_t j = j0 + e;
+            const float sp = softplus_l2(fmaf(__uint_as_float(raw[e]), c1, c0));
+            part += (j >= lo && j < hi) ? sp : 0.f;
+          }
+        }
+        if (has_diag) {
+          const int64_t de = gi - j0;
+          if (de >= 0 && de < 32 && i < n_rows) {
+            const int dei = (int)de;
+            float dv = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dv = fmaf(__uint_as_float(raw[e]), (e == dei) ? 1.0f : 0.0f, dv);
+            const float S = s * dv;
+            diag[i] = S;
+            // the diagonal term is softplus(-z), not softplus(z): swap it (same bits were added above)
+            const float zl = fmaf(dv, c1, c0);
+            part += softplus_l2(-zl) - softplus_l2(zl);
+            const float gd = -sigmoid_l2(-zl);
+            sg_gs = fmaf(gd, S, sg_gs);
+            sg_g += gd;
+          }
+        }
+        sg_loss += part;
+        if (threadIdx.x == 64 && t < 16) TR(96 + t);
+        continue;
+      }
       float v[32];
       if (warp_full) {
 #pragma unroll
@@ -344,7 +418,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       if (j < n_cols && v[0] != 0.f) atomicAdd(col_sumexp + j, v[0]);
       if (threadIdx.x == 64 && t < 16) TR(96 + t);
     }
-    if (i < n_rows) atomicAdd(row_sumexp + i, rsum);
+    if (siglip) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sg_loss += __shfl_xor_sync(0xffffffffu, sg_loss, o);
+        sg_gs += __shfl_xor_sync(0xffffffffu, sg_gs, o);
+        sg_g += __shfl_xor_sync(0xffffffffu, sg_g, o);
+      }
+      if (lane == 0) {
+        atomicAdd(sig_sums, (double)sg_loss);
+        if (sg_g != 0.f) {
+          atomicAdd(sig_sums + 1, (double)sg_gs);
+          atomicAdd(sig_sums + 2, (double)sg_g);
+        }
+      }
+    } else if (i < n_rows) {
+      atomicAdd(row_sumexp + i, rsum);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -374,6 +464,7 @@ struct GradDir {
 struct GradArgs {
   GradDir dir[2];
   int ndir;
+  const float* bias;   // non-null: SigLIP weights (rs / cs unused, gs -> float[2] = (sum G*S, sum G))
 };
 template <int KD, int DNC>
 struct GradCfg {
@@ -533,19 +624,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     const int64_t gi = row_offset + i;
     int64_t lo = 0, hi = 0;
     float rrs = 0.f;
+    const bool siglip = ga.bias != nullptr;
     if (i < n_rows) {
       bucket_range(gi, bs, n_cols, lo, hi);
-      rrs = 1.0f / g.rs[i];
+      if (!siglip) rrs = 1.0f / g.rs[i];
     }
     const float s = expf(*ls);
-    const float c1 = s * kLog2e, c0 = -c1;
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : -c1;
     const bool want_gs = (g.gs != nullptr) && (h == 0);
-    float gs_local = 0.f;
+    float gs_local = 0.f, gsum_local = 0.f;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
-      if (cc == 0) rcs_s[buf * 128 + r] = (j0 + r < n_cols) ? 1.0f / g.cs[j0 + r] : 0.f;
+      if (cc == 0 && !siglip) rcs_s[buf * 128 + r] = (j0 + r < n_cols) ? 1.0f / g.cs[j0 + r] : 0.f;
       named_barrier_sync(1, kEpiThreads);
       mbar_wait(bar_sfull + buf, (t >> 1) & 1);
       tc_fence_after();
@@ -558,7 +650,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       mbar_arrive(bar_sempty + buf);
       uint32_t packed[16];
       grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
-                               want_gs, gs_local);
+                               want_gs, gs_local, siglip, gsum_local);
       mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
       // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
       uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
@@ -598,8 +690,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     if (want_gs) {
       gs_local *= s;  // sum G * S with S = s * (u.v)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
-      if (lane == 0) atomicAdd(g.gs, gs_local);
+      for (int o = 16; o > 0; o >>= 1) {
+        gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+        gsum_local += __shfl_xor_sync(0xffffffffu, gsum_local, o);
+      }
+      if (lane == 0) {
+        atomicAdd(g.gs, gs_local);
+        if (siglip) atomicAdd(g.gs + 1, gsum_local);
+      }
     }
   }
   tc_fence_before();
@@ -631,7 +729,7 @@ struct Grad2Cfg {
   static_assert(kSmem <= kMaxSmem, "tile-buffer backward needs d <= 256");
 };
 
-template <int KD, int CS, bool F16>
+template <int KD, int CS, bool F16, bool SIG>
 __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
     int64_t d, int64_t bs, int tiles_per_seg, const float* __restrict__ ls) {
@@ -774,19 +872,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     const int64_t gi = row_offset + i;
     int64_t lo = 0, hi = 0;
     float rrs = 0.f;
+    constexpr bool siglip = SIG;   // compile-time here: the InfoNCE instantiation carries no extra state
     if (i < n_rows) {
       bucket_range(gi, bs, n_cols, lo, hi);
-      rrs = 1.0f / g.rs[i];
+      if (!siglip) rrs = 1.0f / g.rs[i];
     }
     const float s = expf(*ls);
-    const float c1 = s * kLog2e, c0 = -c1;
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : -c1;
     const bool want_gs = g.gs != nullptr;
-    float gs_local = 0.f;
+    float gs_local = 0.f, gsum_local = 0.f;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // 1/cs of the NEXT tile is fetched one tile ahead (its global-load latency hides behind the
     // exp work of the current tile) and parked in the other half of rcs_s
     float rc_next = 0.f;
-    if (cc == 0) {
+    if (cc == 0 && !siglip) {
       const int64_t jc = jlo + (int64_t)t_begin * kTileRows + r;
       rcs_s[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
     }
@@ -794,7 +893,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
       named_barrier_sync(1, kEpiThreads);   // rcs_s[buf] visible; everyone is done with tile t-1
-      if (cc == 0 && t + 1 < T) {
+      if (cc == 0 && t + 1 < T && !siglip) {
         const int64_t jc = j0 + kTileRows + r;
         rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
       }
@@ -809,7 +908,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       tmem_ld_wait();
       uint32_t packed[16];
       grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
-                               want_gs, gs_local);
+                               want_gs, gs_local, siglip, gsum_local);
       // G overwrites the first 16 of this warp's own 32 logits columns (all 32 were read above)
       tmem_st16(col0, packed);
       tmem_st_wait();
@@ -875,8 +974,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     if (want_gs) {
       gs_local *= s;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
-      if (lane == 0) atomicAdd(g.gs, gs_local);   // zeroed by plk_infonce_loss (waited for above)
+      for (int o = 16; o > 0; o >>= 1) {
+        gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+        gsum_local += __shfl_xor_sync(0xffffffffu, gsum_local, o);
+      }
+      if (lane == 0) {
+        atomicAdd(g.gs, gs_local);   // zeroed by the forward's last kernel (waited for above)
+        if (siglip) atomicAdd(g.gs + 1, gsum_local);
+      }
     }
   }
   griddep_wait();   // no thread block outlives the kernel queued before it (see launch_kernel_ex)
@@ -927,7 +1032,8 @@ static int pick_cluster(int64_t row_blocks, int64_t bs, int64_t n_cols) {
 template <int KD, int CS>
 static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbp, dim3 grid,
                       int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t bs, int tps,
-                      const float* ls, float* rsum, float* csum, float* diag, int f16, cudaStream_t st) {
+                      const float* ls, float* rsum, float* csum, float* diag, int f16, cudaStream_t st,
+                      const float* sig_bias, double* sig_sums) {
   auto kern = infonce_fwd_tc<KD, CS>;
   static bool configured = false;
   if (!configured) {
@@ -935,15 +1041,16 @@ static int launch_fwd(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
     configured = true;
   }
   int rc = launch_kernel_ex(kern, grid, dim3(kNumThreads), FwdCfg<KD>::kSmem, st, CS, true, ta, tb, tbp, n_rows,
-                         row_offset, n_cols, bs, tps, ls, rsum, csum, diag, f16);
+                         row_offset, n_cols, bs, tps, ls, rsum, csum, diag, f16, sig_bias, sig_sums);
   if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
 }
 
-int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows,
-                     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
-                     float* row_sumexp, float* col_sumexp, float* diag, int sums_zeroed, cudaStream_t st) {
+static int fwd_tc16_impl(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows,
+                         int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
+                         float* row_sumexp, float* col_sumexp, float* diag, int sums_zeroed, cudaStream_t st,
+                         const float* sig_bias, double* sig_sums) {
   int rc = check_tc_shape(ld, d);
   if (rc) return rc;
   int64_t row_blocks = ceil_div(n_rows, kTileRows);
@@ -955,7 +1062,7 @@ int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t 
   if ((rc = make_tmap_bf16(&tbp, v, n_cols, ld, ld, kTileRows / 2))) return rc;
   // sums are accumulated with atomics -> zero first; diag needs no init (every owned row has its
   // diagonal column inside its bucket, so it is always written)
-  if (!sums_zeroed && (rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
+  if (!sums_zeroed && sig_bias == nullptr && (rc = zero2(row_sumexp, n_rows, col_sumexp, n_cols, st))) return rc;
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
   const int nseg = pick_segments(row_blocks, max_tiles, 1);
   const int tps = (int)ceil_div(max_tiles, nseg);
@@ -964,13 +1071,27 @@ int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t 
   switch (ld / kChunkK) {
 #define PLK_CASE(KD)                                                                                         \
   case KD:                                                                                                   \
-    return cs == 2 ? launch_fwd<KD, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st) \
-                   : launch_fwd<KD, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st);
+    return cs == 2 ? launch_fwd<KD, 2>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st, sig_bias, sig_sums) \
+                   : launch_fwd<KD, 1>(ta, tb, tbp, grid, n_rows, row_offset, n_cols, bs, tps, ls, row_sumexp, col_sumexp, diag, f16, st, sig_bias, sig_sums);
     PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
 #undef PLK_CASE
   }
   set_error("unsupported padded width %lld", (long long)ld);
   return PLK_ERR_UNSUPPORTED;
+}
+
+int infonce_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows,
+                     int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs, const float* ls,
+                     float* row_sumexp, float* col_sumexp, float* diag, int sums_zeroed, cudaStream_t st) {
+  return fwd_tc16_impl(u, v, f16, ld, n_rows, row_offset, n_cols, d, bs, ls, row_sumexp, col_sumexp, diag,
+                       sums_zeroed, st, nullptr, nullptr);
+}
+
+int siglip_fwd_tc16(const void* u, const void* v, int f16, int64_t ld, int64_t n_rows, int64_t row_offset,
+                    int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* bias, float* diag,
+                    double* sums, cudaStream_t st) {
+  return fwd_tc16_impl(u, v, f16, ld, n_rows, row_offset, n_cols, d, bs, ls, nullptr, nullptr, diag, 1, st, bias,
+                       sums);
 }
 
 template <int KD, int DNC, int CS, bool F16>
@@ -989,10 +1110,10 @@ static int launch_grad(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t ro
   return PLK_OK;
 }
 
-template <int KD, int CS, bool F16>
-static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
-                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
-  auto kern = infonce_grad_tc2<KD, CS, F16>;
+template <int KD, int CS, bool F16, bool SIG>
+static int launch_grad2_m(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                          int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  auto kern = infonce_grad_tc2<KD, CS, F16, SIG>;
   static bool configured = false;
   if (!configured) {
     PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad2Cfg<KD>::kSmem));
@@ -1003,6 +1124,13 @@ static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
   if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;
+}
+template <int KD, int CS, bool F16>
+static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  return ga.bias != nullptr
+             ? launch_grad2_m<KD, CS, F16, true>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev)
+             : launch_grad2_m<KD, CS, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
 }
 
 // number of partial accumulators per direction for this shape (bf16 path); ndir = 1 or 2 directions per launch
@@ -1076,6 +1204,7 @@ int infonce_grad_tc16(const void* a, const void* b, int f16, int64_t ld, int64_t
   if (rc) return rc;
   GradArgs ga;
   ga.ndir = 1;
+  ga.bias = nullptr;
   if ((rc = fill_dir(ga.dir[0], a, b, ld, n_rows, n_cols, rs, cs, acc, gs))) return rc;
   ga.dir[1] = ga.dir[0];
   return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st)
@@ -1086,11 +1215,12 @@ int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1,
                            const void* b1, int f16, int64_t ld, int64_t n_rows, int64_t row_offset,
                            int64_t n_cols, int64_t d, int64_t bs, const float* ls, const float* rs0,
                            const float* cs0, const float* rs1, const float* cs1, float* acc0, float* acc1,
-                           float* gs, cudaStream_t st, int overlap_prev) {
+                           float* gs, cudaStream_t st, int overlap_prev, const float* bias) {
   int rc = check_tc_shape(ld, d);
   if (rc) return rc;
   GradArgs ga;
   ga.ndir = 2;
+  ga.bias = bias;
   if ((rc = fill_dir(ga.dir[0], a0, b0, ld, n_rows, n_cols, rs0, cs0, acc0, gs))) return rc;
   if ((rc = fill_dir(ga.dir[1], a1, b1, ld, n_rows, n_cols, rs1, cs1, acc1, nullptr))) return rc;
   return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st, overlap_prev != 0)

@@ -319,6 +319,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Logistic pieces for the SigLIP epilogues; zl = z * log2(e).
+//   sigmoid(z)  = 1 / (1 + e^-z)                 (2 MUFU; relative accuracy also for z << 0)
+//   softplus(z) = max(z, 0) + log1p(e^-|z|)      (2 MUFU; series below t = 0.01 where 1 + t loses t)
+__device__ __forceinline__ float sigmoid_l2(float zl) {
+  const float e = ex2_approx(-fabsf(zl));
+  const float r = rcp_approx(1.0f + e);
+  return zl >= 0.f ? r : e * r;
+}
+__device__ __forceinline__ float softplus_l2(float zl) {
+  const float t = ex2_approx(-fabsf(zl));
+  const float series = t * fmaf(t, fmaf(t, 0.33333334f, -0.5f), 1.0f);
+  const float l1p = t < 0.01f ? series : lg2_approx(1.0f + t) * 0.6931471805599453f;
+  return fmaf(fmaxf(zl, 0.f), 0.6931471805599453f, l1p);
+}
+
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -377,6 +377,77 @@ class _ClipLossFn(torch.autograd.Function):
         return dx, dy, dls, None, None
 
 
+# ---------------------------------------------------------------------------------------------
+# SigLIP: same state layout, composite calls plk_siglip_loss_forward/backward
+# ---------------------------------------------------------------------------------------------
+def siglip_loss_forward_state(x: torch.Tensor, y: torch.Tensor, ls: torch.Tensor, bias: torch.Tensor, bs: int,
+                              mode: int):
+    """x, y: fp32 [B, d] rows; ls, bias: fp32 scalars on the device.  -> (loss [], state)"""
+    lib = _lib.load()
+    B, d = x.shape
+    dev = x.device
+    state_bytes, _ = _clip_sizes(lib, mode, B, d, bs)
+    state = torch.empty(state_bytes, device=dev, dtype=torch.uint8)
+    loss = torch.empty((), device=dev, dtype=torch.float32)
+    if y.stride(0) != x.stride(0):
+        x, y = x.contiguous(), y.contiguous()
+    with torch.cuda.device(dev):
+        lib.check(lib.plk_siglip_loss_forward(x.data_ptr(), y.data_ptr(), B, d, x.stride(0), mode, bs, ls.data_ptr(),
+                                              bias.data_ptr(), state.data_ptr(), loss.data_ptr(), _stream(x)),
+                  "plk_siglip_loss_forward")
+    return loss, state
+
+
+def siglip_loss_backward_state(go: torch.Tensor, x: torch.Tensor, y: torch.Tensor, ls: torch.Tensor,
+                               bias: torch.Tensor, state, bs: int, mode: int):
+    """-> (dx, dy, dls, dbias) fp32, scaled by the scalar `go` (fp32, on the device)."""
+    lib = _lib.load()
+    B, d = x.shape
+    dev = x.device
+    if y.stride(0) != x.stride(0):
+        x, y = x.contiguous(), y.contiguous()
+    _, ws_bytes = _clip_sizes(lib, mode, B, d, bs)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    dx = torch.empty((B, d), device=dev, dtype=torch.float32)
+    dy = torch.empty((B, d), device=dev, dtype=torch.float32)
+    dls = torch.empty((), device=dev, dtype=torch.float32)
+    dbias = torch.empty((), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        lib.check(lib.plk_siglip_loss_backward(go.data_ptr(), x.data_ptr(), y.data_ptr(), B, d, x.stride(0), mode, bs,
+                                               ls.data_ptr(), bias.data_ptr(), state.data_ptr(), ws.data_ptr(),
+                                               dx.data_ptr(), dy.data_ptr(), dls.data_ptr(), dbias.data_ptr(),
+                                               _stream(x)), "plk_siglip_loss_backward")
+    return dx, dy, dls, dbias
+
+
+class _SigLipLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_emb, profile_emb, logit_scale, bias, buckets, mode):
+        _require_cuda(image_emb, profile_emb, logit_scale, bias)
+        bs = image_emb.shape[0] // buckets
+        x, y = _f32_rows(image_emb), _f32_rows(profile_emb)
+        ls = logit_scale if logit_scale.dtype is torch.float32 else logit_scale.float()
+        b = bias if bias.dtype is torch.float32 else bias.float()
+        loss, state = siglip_loss_forward_state(x, y, ls, b, bs, mode)
+        ctx.save_for_backward(x, y, ls, b, state)
+        ctx.meta = (bs, mode, image_emb.dtype, profile_emb.dtype, logit_scale.dtype, bias.dtype)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_loss):
+        x, y, ls, b, state = ctx.saved_tensors
+        bs, mode, dtx, dty, dtl, dtb = ctx.meta
+        go = g_loss if g_loss.dtype is torch.float32 else g_loss.float()
+        dx, dy, dls, dbias = siglip_loss_backward_state(go, x, y, ls, b, state, bs, mode)
+        return dx.to(dtx), dy.to(dty), dls.to(dtl), dbias.to(dtb), None, None
+
+
+def siglip_loss(image_emb, profile_emb, logit_scale, bias, buckets: int = 1, mode: int = PLK_BF16) -> torch.Tensor:
+    """Pairwise-sigmoid loss of reference src/coordination.py:67-95 on the fused CUDA path."""
+    return _SigLipLossFn.apply(image_emb, profile_emb, logit_scale, bias, int(buckets), int(mode))
+
+
 def clip_loss(image_emb, profile_emb, logit_scale, buckets: int = 1, mode: int = PLK_BF16) -> torch.Tensor:
     """Symmetric InfoNCE of reference src/coordination.py:26-47 on the fused CUDA path.  Under
     torch.compile the registered custom ops are used (traceable); in eager mode the lean path."""

@@ -1,0 +1,107 @@
+"""GPU parity of the SigLIP path through the C ABI (`SigLIPLoss` ->
+plk_siglip_loss_forward / plk_siglip_loss_backward) against the golden vectors produced by running the
+reference's own SigLIPLoss (tests/golden/siglip_*.npz) and against the fp64 oracle on seeded inputs.
+Tolerances: fp32 mode <= 1e-5 relative; bf16 / fp16 operand modes <= 2e-3 (bf16 scaled by the
+temperature like the InfoNCE tests: the operand rounding perturbs every logit by ~ s * 1e-3)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files
+from oracle import siglip as osig
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-5, "bf16": 2e-3, "fp16": 2e-3}
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _run(img, pro, ls, bias, buckets, precision, dtype=torch.float32, grad_out=None):
+    from multimodal_plankton_recognition_b200 import SigLIPLoss
+    dev = torch.device("cuda:0")
+    mod = SigLIPLoss(precision=precision).to(dev)
+    with torch.no_grad():
+        mod.logit_scale.fill_(ls)
+        mod.bias.fill_(bias)
+    x = torch.tensor(img, device=dev, dtype=dtype, requires_grad=True)
+    y = torch.tensor(pro, device=dev, dtype=dtype, requires_grad=True)
+    loss = mod(image_emb=x, profile_emb=y, buckets=buckets)
+    (loss if grad_out is None else loss * grad_out).backward()
+    torch.cuda.synchronize()
+    return (float(loss.detach()), x.grad.float().cpu().numpy(), y.grad.float().cpu().numpy(),
+            float(mod.logit_scale.grad), float(mod.bias.grad))
+
+
+def _check(got, ref, precision, ls, clamp_rows=()):
+    tol = TOL[precision]
+    tol_g = tol * max(1.0, math.exp(ls) / math.e) if precision == "bf16" else tol
+    loss, dx, dy, dls, db = got
+    assert abs(loss - ref["loss"]) <= tol_g * abs(ref["loss"]), ("loss", loss, ref["loss"])
+    rx, ry = np.array(ref["d_image"]), np.array(ref["d_profile"])
+    for arr, r in ((dx, rx), (dy, ry)):
+        for i in clamp_rows:   # rows below the eps clamp carry 1/eps-scaled gradients: compare separately
+            if np.abs(r[i]).max() > 0:
+                assert _rel(arr[i], r[i]) < tol_g * 4
+            arr[i] = 0
+            r[i] = 0
+    assert _rel(dx, rx) < tol_g, ("d_image", _rel(dx, rx))
+    assert _rel(dy, ry) < tol_g, ("d_profile", _rel(dy, ry))
+    assert abs(dls - ref["d_logit_scale"]) <= tol_g * max(abs(ref["d_logit_scale"]), 1e-3), \
+        ("d_logit_scale", dls, ref["d_logit_scale"])
+    assert abs(db - ref["d_bias"]) <= tol_g * max(abs(ref["d_bias"]), 1e-3), ("d_bias", db, ref["d_bias"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("path", golden_files("siglip_"), ids=os.path.basename)
+def test_golden_reference_vectors(path, precision):
+    g = np.load(path)
+    ls, bias, bk = float(g["logit_scale"]), float(g["bias"]), int(g["buckets"])
+    got = _run(g["image"], g["profile"], ls, bias, bk, precision)
+    ref = dict(loss=float(g["loss_f64"]), d_image=g["d_image_f64"].copy(), d_profile=g["d_profile_f64"].copy(),
+               d_logit_scale=float(g["d_logit_scale_f64"]), d_bias=float(g["d_bias_f64"]))
+    clamp = (3, 5) if "edge" in path else ()
+    _check(got, ref, precision, ls, clamp)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("B,d,buckets,ls,bias", [
+    (1024, 256, 1, 1.0, -10.0),      # the reference's initial parameters
+    (1000, 200, 5, 2.0, -5.0),       # ragged width, buckets that cut tiles
+    (768, 512, 3, 1.5, -3.0),        # d > 256: streaming backward kernel
+    (256, 64, 1, 0.0, 0.0),          # logits around 0: every term contributes
+    (4096, 256, 1, 2.3, -8.0),       # BASELINE config[1] shape
+])
+def test_against_oracle(B, d, buckets, ls, bias, precision):
+    from multimodal_plankton_recognition_b200 import synth
+    img, pro, _ = synth.pairs(B, d, 4321 + B + d, "cpu")
+    img, pro = img.numpy(), pro.numpy()
+    ref = osig.siglip_loss_closed_form(img, pro, ls, bias, buckets)
+    got = _run(img, pro, ls, bias, buckets, precision)
+    _check(got, ref, precision, ls)
+
+
+def test_upstream_gradient_half_inputs_and_plus():
+    from multimodal_plankton_recognition_b200 import SigLIPPlus, synth
+    img, pro, _ = synth.pairs(512, 128, 7, "cpu")
+    img, pro = img.numpy(), pro.numpy()
+    ref = osig.siglip_loss_closed_form(img.astype(np.float16).astype(np.float64), pro.astype(np.float16).astype(np.float64),
+                                       1.0, -10.0, 2, grad_out=0.37)
+    got = _run(img, pro, 1.0, -10.0, 2, "fp32", dtype=torch.float16, grad_out=0.37)
+    assert abs(got[0] - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    assert _rel(got[1], ref["d_image"]) < 2e-3 and _rel(got[2], ref["d_profile"]) < 2e-3   # fp16 gradient outputs
+    mod = SigLIPPlus(beta=0.25, precision="fp32").cuda()
+    assert sorted(mod.state_dict().keys()) == ["siglip.bias", "siglip.logit_scale"]
+    x = torch.tensor(img, device="cuda", requires_grad=True)
+    y = torch.tensor(pro, device="cuda", requires_grad=True)
+    loss = mod(image_emb=x, profile_emb=y, buckets=2)
+    loss.backward()
+    full = osig.siglip_loss_closed_form(img, pro, 1.0, -10.0, 2)
+    mse = float(((img.astype(np.float64) - pro) ** 2).mean())
+    assert float(loss) == pytest.approx(full["loss"] + 0.25 * mse, rel=1e-5)
+    with pytest.raises(AssertionError, match="divisible"):
+        mod(image_emb=x[:10], profile_emb=y[:10], buckets=3)

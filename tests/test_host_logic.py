@@ -21,6 +21,21 @@ def test_cliploss_surface_matches_reference():
     assert CLIPLoss(precision="fp16").precision == "fp16"
 
 
+def test_sigliploss_surface_matches_reference():
+    from multimodal_plankton_recognition_b200 import SigLIPLoss, SigLIPPlus
+    mod = SigLIPLoss()                    # reference src/coordination.py:70-73
+    assert sorted(mod.state_dict().keys()) == ["bias", "logit_scale"]
+    assert float(mod.logit_scale) == 1.0 and float(mod.bias) == -10.0
+    assert mod.bias.shape == torch.Size([]) and mod.bias.dtype == torch.float32 and mod.bias.requires_grad
+    x = torch.randn(6, 4)
+    with pytest.raises(AssertionError, match="Batch size must be divisible by number of buckets!"):
+        mod(image_emb=x, profile_emb=x, buckets=4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mod(image_emb=x, profile_emb=x, buckets=1)
+    plus = SigLIPPlus(beta=0.5)           # reference src/coordination.py:98-104
+    assert sorted(plus.state_dict().keys()) == ["siglip.bias", "siglip.logit_scale"] and plus.beta == 0.5
+
+
 def test_no_cpu_fallback():
     from multimodal_plankton_recognition_b200 import CLIPLoss
     x = torch.randn(8, 4, requires_grad=True)
