@@ -157,6 +157,28 @@ class ANNClassifier:
         pred = knn_vote_device(idx, dist, self._labels_dev)
         return pred.cpu().numpy().astype(int).ravel()
 
+    def predict_multi_k(self, *X, ks, **query_args):
+        """`predict` for several k in ONE search per modality (the reference's
+        benchmark drivers call `predict` once per k -- scripts/benchmark_cross.py:57-64,:103-108 --
+        i.e. re-search the gallery for every k).  The exact lists are sorted by (distance, index), so
+        the k nearest are the first k of the k_max nearest.  -> {k: int labels [Nq]}"""
+        ks = [int(k) for k in ks]
+        if not ks or min(ks) < 1:
+            raise ValueError("ks must be a non-empty list of positive integers")
+        k_max = min(max(ks), self.index.n)
+        dev = self.index.device
+        lists = []
+        for x in X:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            lists.append(self.index.search_device(torch.from_numpy(x).to(dev), k_max))
+        out = {}
+        for k in ks:
+            kk = min(k, k_max)
+            idx = torch.cat([p[0][:, :kk] for p in lists], dim=1).contiguous()
+            dist = torch.cat([p[1][:, :kk] for p in lists], dim=1).contiguous()
+            out[k] = knn_vote_device(idx, dist, self._labels_dev).cpu().numpy().astype(int).ravel()
+        return out
+
     def _get_weights(self, dist):
         """Host-side statement of the vote weights (reference src/ann.py:28-34); `predict` applies the same
         rule on the device in plk_knn_vote."""

@@ -142,17 +142,8 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate; issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Same with the two shared-memory descriptors given as (low word, shared high word): the issuing
+// D[tmem] (+)= A[smem] . B[smem]^T, 16-bit inputs, fp32 accumulate; issued by ONE thread.
+// The two shared-memory descriptors are given as (low word, shared high word): the issuing
 // thread is a single serial instruction stream, so everything loop-invariant is hoisted and a
 // K-step costs two integer adds (see umma_desc_lo / kUmmaDescHi).
 __device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
@@ -246,16 +237,9 @@ __device__ __forceinline__ void tmem_ld_wait() {
 //   MN-major view : row = K index,   the 64 elements of a row run along M/N.
 // In both views the stride between 8-row groups (SBO) is 1024 bytes.  LBO is the stride between
 // 64-element column blocks in the MN-major view (unused when the operand is one block wide).
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // [0,14)  start address >> 4
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;     // [16,30) leading byte offset >> 4
-  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;          // [32,46) stride byte offset >> 4
-  d |= (uint64_t)1 << 46;                               // [46,48) descriptor version = 1 (sm_100)
-  d |= (uint64_t)2 << 61;                               // [61,64) layout = SWIZZLE_128B
-  return d;
-}
-// The same descriptor split in words: high word = SBO 1024 B (>>4 = 64), version 1 (bit 46 -> 14),
+// 64-bit descriptor: [0,14) start address >> 4, [16,30) LBO >> 4, [32,46) SBO >> 4, [46,48) version = 1
+// (sm_100), [61,64) layout = 2 (SWIZZLE_128B).  Split in words so the loop-invariant half is a constant:
+// high word = SBO 1024 B (>>4 = 64), version 1 (bit 46 -> 14),
 // SWIZZLE_128B (bits 61..63 -> 29..31); low word = start address >> 4 | (LBO >> 4) << 16.
 constexpr uint32_t kUmmaDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 static_assert(kUmmaDescHi == 0x40004040u, "descriptor high word");
@@ -356,10 +340,6 @@ __device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
   }
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
-  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -101,3 +101,28 @@ def test_large_gallery_properties_bf16():
     best = full.topk(k, dim=1, largest=False)
     assert (best.values - dist[sub]).abs().max() < 1e-6
     assert (best.indices.int() == idx[sub]).float().mean() > 0.999
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_predict_multi_k_equals_one_search_per_k(precision):
+    """One search at k_max + prefix votes gives the labels of the reference's per-k
+    loop (scripts/benchmark_cross.py:57-64), for one and two query modalities, incl. k > gallery size."""
+    from multimodal_plankton_recognition_b200 import ANNClassifier
+    img, lab = _clustered(900, 256, 27, 15)
+    pro = (img + 0.05 * np.random.default_rng(16).standard_normal(img.shape)).astype(np.float32)
+    pro /= np.linalg.norm(pro, axis=1, keepdims=True)
+    tr, te = np.arange(0, 300), np.arange(300, 900)
+    ora = oann.OracleANNClassifier(img[tr], lab[tr])
+    clf = ANNClassifier(img[tr], lab[tr], plk_precision=precision, **KW)
+    ks = (1, 3, 5, 7, 9, 10)
+    for X in ((img[te],), (pro[te],), (img[te], pro[te])):
+        got = clf.predict_multi_k(*X, ks=ks, epsilon=.3)
+        assert sorted(got) == sorted(ks)
+        for k in ks:
+            np.testing.assert_array_equal(got[k], clf.predict(*X, k=k, epsilon=.3))
+            np.testing.assert_array_equal(got[k], ora.predict(*X, k=k))
+    small = ANNClassifier(img[:5], lab[:5], plk_precision=precision, **KW)
+    got = small.predict_multi_k(img[te][:17], ks=(3, 9))
+    np.testing.assert_array_equal(got[9], small.predict(img[te][:17], k=9))
+    with pytest.raises(ValueError):
+        clf.predict_multi_k(img[te], ks=())
