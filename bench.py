@@ -316,13 +316,21 @@ def main():
         pf = HostPairPrefetcher(((hx, hy) for _ in range(e2e_steps + e2e_warm)), dev, depth=3)
         feed = iter(pf)
         losses, pending = [], [None]
+        # one GPU: forward and backward of the module replay CUDA graphs (CLIPLoss.graphed =
+        # torch.cuda.make_graphed_callables), which takes the host out of the critical path
+        step_fn_e2e = None
+        if world == 1 and os.environ.get("PLK_BENCH_GRAPHED_E2E", "1") == "1":
+            try:
+                step_fn_e2e = mod.graphed(img, pro)
+            except Exception as e:
+                print(f"bench: CLIPLoss.graphed unavailable ({e!r}); eager e2e", file=sys.stderr)
 
         def streamed_step():
             x, y = next(feed)
             x.requires_grad_()
             y.requires_grad_()
             mod.logit_scale.grad = None
-            loss = mod(image_emb=x, profile_emb=y, buckets=world)
+            loss = step_fn_e2e(x, y) if step_fn_e2e is not None else mod(image_emb=x, profile_emb=y, buckets=world)
             loss.backward()
             read = pf.read_async(loss)
             if pending[0] is not None:
@@ -358,7 +366,9 @@ def main():
             "parallelism": f"dp{world}"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 2 * n * d * 4, "d2h_bytes_per_step": 4,
-                "path": "CLIPLoss.forward + backward on batches staged by prefetch.HostPairPrefetcher "
+                "path": ("CLIPLoss.graphed (forward + backward as CUDA graphs) " if step_fn_e2e is not None else
+                         "CLIPLoss.forward + backward ") +
+                        "on batches staged by prefetch.HostPairPrefetcher "
                         "(pinned host -> HBM on a copy stream, 2 batches ahead; each loss read back one step late)",
                 "serial_ms_per_step": serial_ms, "serial_value": Bg / (serial_ms * 1e-3)},
         "gpu_launches": int(launches_per_step * args.steps),

@@ -54,8 +54,28 @@ class CLIPLoss(Module):
                                           self.process_group)
         return ops.clip_loss(image_emb, profile_emb, self.logit_scale, int(buckets), mode)
 
+    def graphed(self, image_emb: Tensor, profile_emb: Tensor):
+        """-> callable ``f(image_emb, profile_emb) -> loss`` whose forward AND backward replay CUDA graphs
+        (`torch.cuda.make_graphed_callables`): ~40 us of host time per step instead of ~150.  The sample
+        tensors fix shape and dtype (buckets = 1; single GPU -- collectives are kept out of captures)."""
+        if self.sharded:
+            raise RuntimeError("graphed() is for the single-GPU loss; the sharded path issues collectives")
+        # a positional wrapper is graphed (make_graphed_callables rebinds the forward of the module it is
+        # given and passes tensors positionally); `self` stays usable in eager mode and shares logit_scale
+        return torch.cuda.make_graphed_callables(_Positional(self), (image_emb.detach().clone().requires_grad_(),
+                                                                     profile_emb.detach().clone().requires_grad_()))
+
     def extra_repr(self) -> str:
         return f"precision={self.precision}, sharded={self.sharded}"
+
+
+class _Positional(Module):
+    def __init__(self, inner: Module) -> None:
+        super().__init__()
+        self.inner = inner
+
+    def forward(self, image_emb: Tensor, profile_emb: Tensor) -> Tensor:
+        return self.inner(image_emb=image_emb, profile_emb=profile_emb, buckets=1)
 
 
 class SigLIPLoss(Module):

@@ -237,3 +237,26 @@ def test_prefetcher_streams_batches_in_order():
         assert reads[-1]() == pytest.approx(want[-1], rel=1e-6)
     with pytest.raises(ValueError):
         HostPairPrefetcher(iter(host), dev, depth=1)
+
+
+def test_graphed_module_matches_eager():
+    """CLIPLoss.graphed: forward and backward replayed as CUDA graphs give the eager results."""
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    dev = torch.device("cuda:0")
+    mod = CLIPLoss(precision="bf16").to(dev)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    f = mod.graphed(torch.randn(512, 128, generator=g).to(dev), torch.randn(512, 128, generator=g).to(dev))
+    for _ in range(3):
+        x = torch.randn(512, 128, generator=g).to(dev).requires_grad_()
+        y = torch.randn(512, 128, generator=g).to(dev).requires_grad_()
+        mod.logit_scale.grad = None
+        loss = f(x, y)
+        loss.backward()
+        got = (float(loss.detach()), x.grad.clone(), y.grad.clone(), float(mod.logit_scale.grad))
+        x2, y2 = x.detach().clone().requires_grad_(), y.detach().clone().requires_grad_()
+        mod.logit_scale.grad = None
+        loss2 = mod(image_emb=x2, profile_emb=y2)
+        loss2.backward()
+        assert got[0] == pytest.approx(float(loss2.detach()), rel=1e-6)
+        assert torch.allclose(got[1], x2.grad, rtol=1e-4, atol=1e-9) and torch.allclose(got[2], y2.grad, rtol=1e-4, atol=1e-9)
+        assert got[3] == pytest.approx(float(mod.logit_scale.grad), rel=1e-4, abs=1e-7)
