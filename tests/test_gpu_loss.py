@@ -258,5 +258,8 @@ def test_graphed_module_matches_eager():
         loss2 = mod(image_emb=x2, profile_emb=y2)
         loss2.backward()
         assert got[0] == pytest.approx(float(loss2.detach()), rel=1e-6)
-        assert torch.allclose(got[1], x2.grad, rtol=1e-4, atol=1e-9) and torch.allclose(got[2], y2.grad, rtol=1e-4, atol=1e-9)
+        # same kernels; the sum-exp atomics land in another order, which flips a few bf16 roundings of G
+        # (two eager runs differ by the same ~1e-5)
+        for a, b in ((got[1], x2.grad), (got[2], y2.grad)):
+            assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max())
         assert got[3] == pytest.approx(float(mod.logit_scale.grad), rel=1e-4, abs=1e-7)
