@@ -152,52 +152,65 @@ struct NormPairArgs {
   float* zero[2];
   int64_t nzero[2];
 };
+// Two rows per warp: all four 16-byte loads of a lane are issued before the first use, which doubles the
+// bytes in flight per SM -- this is the first kernel of a step, its inputs come from HBM.
 template <int NV, typename TO>
 __global__ void __launch_bounds__(256) l2norm_pair_vec_kernel(NormPairArgs a, int64_t n, int64_t ldx, int64_t ldu) {
+  constexpr int RPW = 2;
   const int m = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   pdl_trigger();   // the forward kernel may set itself up; it waits for this grid before reading
   {  // zero fill: thread-linear over this modality's accumulator
     const int64_t z = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (a.zero[m] != nullptr && z < a.nzero[m]) a.zero[m][z] = 0.f;
   }
-  if (row >= n) return;
-  const float4* xr = reinterpret_cast<const float4*>(a.x[m] + row * ldx);
+  if (row0 >= n) return;
   TO* u = reinterpret_cast<TO*>(a.u[m]);
-  float4 v[NV];
+  float4 v[RPW][NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
-  float ss = 0.f;
+  for (int r = 0; r < RPW; ++r) {
+    const int64_t row = row0 + r < n ? row0 + r : row0;   // odd tail: re-read the first row, write nothing
+    const float4* xr = reinterpret_cast<const float4*>(a.x[m] + row * ldx);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) ss = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, ss))));
-  ss = warp_sum(ss);
-  const float nrm = sqrtf(ss);
-  const float den = fmaxf(nrm, kNormEps);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    float4 w = v[i];
-    w.x /= den; w.y /= den; w.z /= den; w.w /= den;
-    if constexpr (sizeof(TO) == 4) {
-      reinterpret_cast<float4*>(u + row * ldu)[lane + 32 * i] = w;
-    } else if constexpr (!kIsHalf<TO>) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
-      reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-    } else {
-      __half2 lo = __floats2half2_rn(w.x, w.y), hi = __floats2half2_rn(w.z, w.w);
-      reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-    }
+    for (int i = 0; i < NV; ++i) v[r][i] = xr[lane + 32 * i];
   }
-  if (lane == 0) {
-    a.inv_den[m][row] = 1.0f / den;
-    a.nrm[m][row] = nrm;
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int64_t row = row0 + r;
+    if (row >= n) continue;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      ss = fmaf(v[r][i].x, v[r][i].x, fmaf(v[r][i].y, v[r][i].y, fmaf(v[r][i].z, v[r][i].z, fmaf(v[r][i].w, v[r][i].w, ss))));
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    const float den = fmaxf(nrm, kNormEps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 w = v[r][i];
+      w.x /= den; w.y /= den; w.z /= den; w.w /= den;
+      if constexpr (sizeof(TO) == 4) {
+        reinterpret_cast<float4*>(u + row * ldu)[lane + 32 * i] = w;
+      } else if constexpr (!kIsHalf<TO>) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(w.x, w.y), hi = __floats2bfloat162_rn(w.z, w.w);
+        reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      } else {
+        __half2 lo = __floats2half2_rn(w.x, w.y), hi = __floats2half2_rn(w.z, w.w);
+        reinterpret_cast<uint2*>(u + row * ldu)[lane + 32 * i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+      }
+    }
+    if (lane == 0) {
+      a.inv_den[m][row] = 1.0f / den;
+      a.nrm[m][row] = nrm;
+    }
   }
 }
 
 template <typename TO>
 static bool l2norm_pair_try(const NormPairArgs& a, int64_t n, int64_t d, int64_t ldx, int64_t ldu, cudaStream_t st) {
   int64_t nz = a.nzero[0] > a.nzero[1] ? a.nzero[0] : a.nzero[1];
-  int64_t blocks = ceil_div(n, 8);
+  int64_t blocks = ceil_div(n, 16);   // 8 warps x 2 rows
   if (ceil_div(nz, 256) > blocks) blocks = ceil_div(nz, 256);
   dim3 block(256), grid((unsigned)blocks, 2);
   switch (d / 128) {
@@ -509,14 +522,21 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
   const float4* xr = reinterpret_cast<const float4*>(a.x[m] + row * ldx);
   const float4* pr = reinterpret_cast<const float4*>(a.x[1 - m] + row * ldx);
   const int64_t slab4 = n * d / 4;
-  float4 acc[NV], xv[NV], pv[NV];
+  // every load of the row (first two partial slabs, own row, partner row) is issued before the first use
+  float4 acc[NV], acc1[NV], xv[NV], pv[NV];
+  const bool two = parts > 1;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     acc[i] = ar[lane + 32 * i];
+    acc1[i] = two ? ar[lane + 32 * i + slab4] : make_float4(0.f, 0.f, 0.f, 0.f);
     xv[i] = xr[lane + 32 * i];
     pv[i] = pr[lane + 32 * i];
   }
-  for (int p = 1; p < parts; ++p) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i].x += acc1[i].x; acc[i].y += acc1[i].y; acc[i].z += acc1[i].z; acc[i].w += acc1[i].w;
+  }
+  for (int p = 2; p < parts; ++p) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const float4 t = ar[lane + 32 * i + p * slab4];
