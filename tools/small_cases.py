@@ -1,4 +1,5 @@
-"""Small fwd+bwd / retrieval cases for `compute-sanitizer --tool memcheck` (a few launches of every kernel)."""
+"""Small fwd+bwd / retrieval cases touching every kernel once (CLIP + SigLIP, bf16 + fp32, ragged shapes):
+a quick end-to-end sanity run, e.g. after changing a launch configuration."""
 import os
 import sys
 
