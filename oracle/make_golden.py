@@ -10,6 +10,9 @@ exist on the GPU box):
                   gradients w.r.t. both embeddings and ``logit_scale``.
 * siglip_*.npz    the same for the reference's ``SigLIPLoss`` (reference src/coordination.py:67-95),
                   incl. the gradient w.r.t. ``bias``.
+* bench_*.npz     inputs + every predicted label array of the reference's own benchmark drivers
+                  (reference scripts/benchmark_cross.py:24-87, scripts/benchmark_cross_folds.py:24-85),
+                  same index injection as ann_*.
 * ann_*.npz       inputs + outputs of the reference's own ``ANNClassifier``
                   (reference src/ann.py:6-34) executed with ``oracle.ann.ExactIndex``
                   injected as the module ``pynndescent`` (the real package is not
@@ -123,6 +126,54 @@ def ann_case(name, ng, nq, d, k, seed, n_classes=9, dup=False, two_mod=False):
     print("wrote ann", name, pred[:8])
 
 
+def bench_case(name, n_classes, per_class, d, n, repeats, K, seed):
+    """Run the reference's own drivers -- `benchmark()` of scripts/benchmark_cross.py:24-87 and of
+    scripts/benchmark_cross_folds.py:24-85 -- unmodified, with oracle.ann.ExactIndex standing in for
+    pynndescent, on a synthetic embedding set; store the inputs, the `random` seed and every predicted
+    label array (as class ids, key order = run, k, set-up)."""
+    import importlib.util
+    import random
+    from sklearn.preprocessing import LabelEncoder
+
+    def load(path, modname):
+        spec = importlib.util.spec_from_file_location(modname, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    cross = load("/root/reference/scripts/benchmark_cross.py", "ref_benchmark_cross")
+    folds = load("/root/reference/scripts/benchmark_cross_folds.py", "ref_benchmark_cross_folds")
+    g = np.random.default_rng(seed)
+    cent = g.standard_normal((n_classes, d))
+    lab = np.repeat(np.arange(n_classes), per_class)
+    g.shuffle(lab)
+
+    def emb(noise):
+        e = cent[lab] + noise * g.standard_normal((len(lab), d))
+        return (e / np.linalg.norm(e, axis=1, keepdims=True)).astype(np.float32)
+
+    img, pro = emb(0.45 * np.sqrt(d)), emb(0.55 * np.sqrt(d))   # hard enough that the votes matter (acc ~ 0.5-0.8)
+    names = np.array([f"class_{c:02d}" for c in lab])
+    coder = LabelEncoder().fit(names)
+    out = {"image": img, "profile": pro, "names": names, "n": n, "repeats": repeats, "K": np.array(K), "seed": seed}
+
+    def flatten(res, tag):
+        for run in sorted(res):
+            out[f"{tag}/true/{run}"] = coder.transform(res[run]["true"])
+            for k in K:
+                for setup, pred in res[run]["pred"][k].items():
+                    out[f"{tag}/pred/{run}/{k}/{setup}"] = coder.transform(pred)
+
+    random.seed(seed)
+    flatten(cross.benchmark((img, pro, names), coder, n, repeats, K), "cross")
+    half = len(lab) // 2
+    random.seed(seed)
+    flatten(folds.benchmark((img[:half], pro[:half], names[:half]), (img[half:], pro[half:], names[half:]),
+                            coder, n, repeats, K), "folds")
+    np.savez_compressed(os.path.join(OUT, f"bench_{name}.npz"), **out)
+    print("wrote bench", name, len(out), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     loss_case("b64_d128_k1", 64, 128, 1, 1.0, 1)
@@ -143,6 +194,8 @@ def main():
     siglip_case("b192_d256_k3_ls2.3_b-4", 192, 256, 3, 2.3, -4.0, 23)  # a trained-looking temperature / bias
     siglip_case("b100_d72_k1_ls0_b0", 100, 72, 1, 0.0, 0.0, 24)      # ragged B and d, logits around 0
     siglip_case("b64_d64_edge", 64, 64, 2, 1.0, -10.0, 25, tweak=tiny)
+
+    bench_case("c9_p40_d64_n4", 9, 40, 64, 4, 2, (1, 3, 5), 31)
 
     ann_case("g432_q300_d512_k9", 432, 300, 512, 9, 11, n_classes=27)
     ann_case("g96_q64_d64_k5_dup", 96, 64, 64, 5, 12, dup=True)

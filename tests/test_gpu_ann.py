@@ -126,3 +126,42 @@ def test_predict_multi_k_equals_one_search_per_k(precision):
     np.testing.assert_array_equal(got[9], small.predict(img[te][:17], k=9))
     with pytest.raises(ValueError):
         clf.predict_multi_k(img[te], ks=())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("path", golden_files("bench_"), ids=os.path.basename)
+def test_benchmark_harness_matches_reference_drivers(path, precision):
+    """harness.cross_benchmark / cross_benchmark_folds against the label arrays the reference's own
+    drivers produced (scripts/benchmark_cross.py, scripts/benchmark_cross_folds.py run by
+    oracle/make_golden.py): same `random` stream -> same galleries -> identical predictions for every
+    run, k and set-up."""
+    import random
+    from sklearn.preprocessing import LabelEncoder
+    from multimodal_plankton_recognition_b200 import harness
+    g = np.load(path)
+    img, pro, names = g["image"], g["profile"], g["names"]
+    n, repeats, K, seed = int(g["n"]), int(g["repeats"]), tuple(int(k) for k in g["K"]), int(g["seed"])
+    coder = LabelEncoder().fit(names)
+
+    def check(res, tag):
+        assert sorted(res) == list(range(repeats))
+        n_checked = 0
+        for run in res:
+            np.testing.assert_array_equal(coder.transform(res[run]["true"]), g[f"{tag}/true/{run}"])
+            assert sorted(res[run]["pred"]) == sorted(K)
+            for k in K:
+                assert len(res[run]["pred"][k]) == 8
+                for setup, pred in res[run]["pred"][k].items():
+                    np.testing.assert_array_equal(coder.transform(pred), g[f"{tag}/pred/{run}/{k}/{setup}"],
+                                                  err_msg=f"{tag} run {run} k {k} {setup}")
+                    n_checked += 1
+        assert n_checked == repeats * len(K) * 8
+
+    random.seed(seed)
+    check(harness.cross_benchmark((img, pro, names), coder, n, repeats, K, plk_precision=precision), "cross")
+    half = len(names) // 2
+    random.seed(seed)
+    check(harness.cross_benchmark_folds((img[:half], pro[:half], names[:half]), (img[half:], pro[half:], names[half:]),
+                                        coder, n, repeats, K, plk_precision=precision), "folds")
+    kept = harness.keep_frequent((img, pro, names), coder, 40)      # every class has 40 samples: all kept, grouped by class
+    assert len(kept[2]) == len(names) and (np.diff(coder.transform(kept[2])) >= 0).all()
