@@ -7,7 +7,10 @@ the reference's `main()` gets the same galleries), same nested result
 the gallery index is `ANNClassifier` of this package (exact search on the tensor cores), and every
 (gallery, query) set-up is searched ONCE at max(K) and voted for each k from the prefixes
 (`predict_multi_k`) instead of once per k.  `cross_benchmark_folds` does the same for the
-train-fold / test-fold variant (reference scripts/benchmark_cross_folds.py:24-85).
+train-fold / test-fold variant (reference scripts/benchmark_cross_folds.py:24-85); `joint_benchmark`
+/ `joint_benchmark_folds` are the single set-up "I+P gallery, (I, P) query" of
+reference scripts/benchmark_raw.py:24-50 and scripts/benchmark_folds.py:24-51
+(result ``{run: {"pred": {k: class names}, "true": class names}}``).
 """
 from __future__ import annotations
 
@@ -97,4 +100,40 @@ def cross_benchmark_folds(train, test, coder, n, repeats, K, **ann_overrides):
         pred = _run_setups({"I": image_train[tr], "P": profile_train[tr]}, label_train[tr],
                            {"I": image_test, "P": profile_test}, coder, K, kw)
         results[run] = {"pred": pred, "true": coder.inverse_transform(label_test)}
+    return results
+
+
+def _joint(gallery_i, gallery_p, gallery_labels, query_i, query_p, coder, K, ann_kwargs):
+    clf = ANNClassifier(np.concatenate((gallery_i, gallery_p)), np.tile(gallery_labels, (2,)), **ann_kwargs)
+    by_k = clf.predict_multi_k(query_i, query_p, ks=K, epsilon=.3)
+    return {k: coder.inverse_transform(by_k[k]) for k in K}
+
+
+def joint_benchmark(data, coder, n, repeats, K, **ann_overrides):
+    """Both modalities in the gallery and in the query; n per class drawn from `data`, the rest queried."""
+    images, profiles, names = data
+    labels = coder.transform(names)
+    everything = set(range(len(labels)))
+    kw = {**ANN_KWARGS, **ann_overrides}
+    results = {}
+    for run in range(repeats):
+        tr = draw_gallery(labels, n)
+        te = list(everything - set(tr))
+        results[run] = {"pred": _joint(images[tr], profiles[tr], labels[tr], images[te], profiles[te], coder, K, kw),
+                        "true": coder.inverse_transform(labels[te])}
+    return results
+
+
+def joint_benchmark_folds(train, test, coder, n, repeats, K, **ann_overrides):
+    """Both modalities in the gallery (n per class of the train fold) and in the query (the test fold)."""
+    image_train, profile_train, name_train = train
+    image_test, profile_test, name_test = test
+    label_train, label_test = coder.transform(name_train), coder.transform(name_test)
+    kw = {**ANN_KWARGS, **ann_overrides}
+    results = {}
+    for run in range(repeats):
+        tr = draw_gallery(label_train, n)
+        results[run] = {"pred": _joint(image_train[tr], profile_train[tr], label_train[tr], image_test, profile_test,
+                                       coder, K, kw),
+                        "true": coder.inverse_transform(label_test)}
     return results

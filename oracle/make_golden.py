@@ -11,7 +11,8 @@ exist on the GPU box):
 * siglip_*.npz    the same for the reference's ``SigLIPLoss`` (reference src/coordination.py:67-95),
                   incl. the gradient w.r.t. ``bias``.
 * bench_*.npz     inputs + every predicted label array of the reference's own benchmark drivers
-                  (reference scripts/benchmark_cross.py:24-87, scripts/benchmark_cross_folds.py:24-85),
+                  (reference scripts/benchmark_cross.py:24-87, scripts/benchmark_cross_folds.py:24-85,
+                  scripts/benchmark_raw.py:24-50, scripts/benchmark_folds.py:24-51),
                   same index injection as ann_*.
 * ann_*.npz       inputs + outputs of the reference's own ``ANNClassifier``
                   (reference src/ann.py:6-34) executed with ``oracle.ann.ExactIndex``
@@ -170,6 +171,21 @@ def bench_case(name, n_classes, per_class, d, n, repeats, K, seed):
     random.seed(seed)
     flatten(folds.benchmark((img[:half], pro[:half], names[:half]), (img[half:], pro[half:], names[half:]),
                             coder, n, repeats, K), "folds")
+    # the single set-up drivers: I+P gallery, (I, P) query
+    raw = load("/root/reference/scripts/benchmark_raw.py", "ref_benchmark_raw")
+    jfolds = load("/root/reference/scripts/benchmark_folds.py", "ref_benchmark_folds")
+
+    def flatten_joint(res, tag):
+        for run in sorted(res):
+            out[f"{tag}/true/{run}"] = coder.transform(res[run]["true"])
+            for k in K:
+                out[f"{tag}/pred/{run}/{k}"] = coder.transform(res[run]["pred"][k])
+
+    random.seed(seed)
+    flatten_joint(raw.benchmark((img, pro, names), coder, n, repeats, K), "joint")
+    random.seed(seed)
+    flatten_joint(jfolds.benchmark((img[:half], pro[:half], names[:half]), (img[half:], pro[half:], names[half:]),
+                                   coder, n, repeats, K), "jointfolds")
     np.savez_compressed(os.path.join(OUT, f"bench_{name}.npz"), **out)
     print("wrote bench", name, len(out), "arrays")
 

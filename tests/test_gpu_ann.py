@@ -163,5 +163,19 @@ def test_benchmark_harness_matches_reference_drivers(path, precision):
     random.seed(seed)
     check(harness.cross_benchmark_folds((img[:half], pro[:half], names[:half]), (img[half:], pro[half:], names[half:]),
                                         coder, n, repeats, K, plk_precision=precision), "folds")
+
+    def check_joint(res, tag):
+        for run in range(repeats):
+            np.testing.assert_array_equal(coder.transform(res[run]["true"]), g[f"{tag}/true/{run}"])
+            for k in K:
+                np.testing.assert_array_equal(coder.transform(res[run]["pred"][k]), g[f"{tag}/pred/{run}/{k}"],
+                                              err_msg=f"{tag} run {run} k {k}")
+
+    random.seed(seed)
+    check_joint(harness.joint_benchmark((img, pro, names), coder, n, repeats, K, plk_precision=precision), "joint")
+    random.seed(seed)
+    check_joint(harness.joint_benchmark_folds((img[:half], pro[:half], names[:half]),
+                                              (img[half:], pro[half:], names[half:]), coder, n, repeats, K,
+                                              plk_precision=precision), "jointfolds")
     kept = harness.keep_frequent((img, pro, names), coder, 40)      # every class has 40 samples: all kept, grouped by class
     assert len(kept[2]) == len(names) and (np.diff(coder.transform(kept[2])) >= 0).all()
