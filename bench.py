@@ -6,12 +6,16 @@
 
 Primary line (BASELINE.json config[1]): symmetric InfoNCE forward+backward, batch 4096 x d=256,
 bf16 tensor-core path, `value` = pairs/s with inputs resident in HBM (CUDA-graph replay of the
-whole step, L2 flushed between steps), `e2e` = the same through `CLIPLoss.forward/backward` with
-pinned HOST inputs (H2D of both embedding matrices + D2H of the loss inside the timed region).
+whole step, L2 flushed between steps), `e2e` = the same through `CLIPLoss` forward + backward on
+pinned HOST batches (every step: H2D of both embedding matrices through prefetch.HostPairPrefetcher,
+D2H of the loss, all inside the timed region; on one GPU the module replays CUDA graphs --
+`CLIPLoss.graphed`); `e2e.serial_*` = eager, nothing overlapped.
 N>1: weak scaling -- every rank owns one bucket of 4096 pairs of a global batch 4096*N
-(reference `buckets` semantics, sharded on bucket boundaries, scalar all-reduces only).
+(reference `buckets` semantics, sharded on bucket boundaries; the two per-rank scalars are summed
+inside the gradient-tail kernel over NVLink peer memory).
 Extra objects on the same line: `c3` (global batch 32768, d=512, row-block sharded with
-all-gather / all-reduce: the north-star multi-GPU loss) and `retrieval` (top-10, gallery sharded).
+all-gather / all-reduce: the north-star multi-GPU loss), `retrieval` (top-10, gallery sharded) and,
+on one GPU, `siglip` (SigLIP fwd+bwd at the primary shape, with its own CPU port beside it).
 """
 from __future__ import annotations
 
@@ -166,7 +170,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the c3 / retrieval extra objects")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
