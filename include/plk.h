@@ -106,6 +106,16 @@ int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const
                      const float* logit_scale, int64_t n_rows, int64_t batch_global,
                      float* loss_out, float* diag_sum_out, float* gs_zero, void* stream);
 
+/* Same for a rank of a bucket-aligned sharded step, with the sum over the ranks fused into the kernel
+ * (peer-mapped symmetric memory, arguments as plk_infonce_grad_finish_pair_xgpu):
+ *   *loss_out = GLOBAL loss (identical bits on every rank), *partial_out = this rank's partial.
+ * All ranks must call it the same number of times, interleaved identically with the other _xgpu calls. */
+int plk_infonce_loss_xgpu(const float* row_sumexp, const float* col_sumexp_own, const float* diag,
+                          const float* logit_scale, int64_t n_rows, int64_t batch_global,
+                          float* loss_out, float* diag_sum_out, float* gs_zero, float* partial_out,
+                          void* const* peer_bufs, int rank, int world, unsigned* epoch, float* out2,
+                          void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * a9. Recompute backward, one direction (flash-style: logits are never materialised).
  *   acc_i = sum_{j != i}  E_ij (1/rs_i + 1/cs_j) * b_j     for the owned rows i (global j != i)
@@ -211,14 +221,21 @@ int plk_infonce_dls(const float* gs, const float* diag_sum, const float* grad_ou
  *   complete) passes the global batch: loss / dls are then this rank's PARTIAL sums.  The embedding
  *   gradients are scaled by (*grad_out_emb) * emb_scale; under DDP gradient averaging pass
  *   grad_out_emb = grad_out and emb_scale = world (emb_scale != 1 needs d % 128 == 0, d <= 1024).
- *   plk_clip_loss_backward_xgpu additionally sums (loss partial, dls partial) over the ranks inside
- *   the gradient-tail kernel (arguments as plk_infonce_grad_finish_pair_xgpu).
+ *   plk_clip_loss_forward_xgpu returns the GLOBAL loss (the ranks' partials are exchanged inside the
+ *   loss kernel, plk_infonce_loss_xgpu); plk_clip_loss_backward_xgpu additionally sums (loss partial,
+ *   dls partial) over the ranks inside the gradient-tail kernel (plk_infonce_grad_finish_pair_xgpu):
+ *   a sharded step without a single collective launch.
  * ------------------------------------------------------------------------------------------ */
 size_t plk_clip_loss_state_bytes(int op_dtype, int64_t batch, int64_t d);
 size_t plk_clip_loss_workspace_bytes(int op_dtype, int64_t batch, int64_t d, int64_t bucket_size);
 int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
                           int op_dtype, int64_t bucket_size, int64_t batch_global,
                           const float* logit_scale, void* state, float* loss_out, void* stream);
+int plk_clip_loss_forward_xgpu(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
+                               int op_dtype, int64_t bucket_size, int64_t batch_global,
+                               const float* logit_scale, void* state, float* loss_out,
+                               float* partial_out, void* const* peer_bufs, int rank, int world,
+                               unsigned* epoch, float* out2, void* stream);
 int plk_clip_loss_backward(const float* grad_out, const float* grad_out_emb, float emb_scale,
                            const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx, int op_dtype,
                            int64_t bucket_size, int64_t batch_global, const float* logit_scale,

@@ -85,6 +85,8 @@ SIGNATURES = {
     "plk_infonce_fwd": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _vp]),
     "plk_infonce_grad_finish_pair": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plk_infonce_loss_xgpu": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp,
+                                     _vp]),
     "plk_infonce_loss": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "plk_infonce_grad_parts": (_int, [_int, _i64, _i64, _i64, _i64]),
     "plk_infonce_grad_pair_parts": (_int, [_int, _i64, _i64, _i64, _i64]),
@@ -100,6 +102,8 @@ SIGNATURES = {
     "plk_clip_loss_state_bytes": (_sz, [_int, _i64, _i64]),
     "plk_clip_loss_workspace_bytes": (_sz, [_int, _i64, _i64, _i64]),
     "plk_clip_loss_forward": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "plk_clip_loss_forward_xgpu": (_int, [_vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int,
+                                          _int, _vp, _vp, _vp]),
     "plk_clip_loss_backward": (_int, [_vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _vp]),
     "plk_clip_loss_backward_xgpu": (_int, [_vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i64, _int, _i64, _i64, _vp,

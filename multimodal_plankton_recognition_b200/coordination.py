@@ -40,6 +40,8 @@ class CLIPLoss(Module):
         self.precision = precision
         self.sharded = sharded or process_group is not None
         self.process_group = process_group
+        self._xgpu = None            # dist.XGpuScalars, created at the first bucket-aligned sharded forward
+        self._xgpu_tried = False
 
     def forward(self, image_emb: Tensor, profile_emb: Tensor, buckets: int = 1) -> Tensor:
         assert image_emb.size(0) % buckets == 0, \
@@ -51,8 +53,29 @@ class CLIPLoss(Module):
         if self.sharded:
             from . import dist
             return dist.sharded_clip_loss(image_emb, profile_emb, self.logit_scale, int(buckets), mode,
-                                          self.process_group)
+                                          self.process_group, xgpu=self._peer_scalars(image_emb, int(buckets)))
         return ops.clip_loss(image_emb, profile_emb, self.logit_scale, int(buckets), mode)
+
+    def _peer_scalars(self, image_emb: Tensor, buckets: int):
+        """The peer-memory scalar exchange for the bucket-aligned sharded case (every rank takes the same
+        decision from the same shapes; creating it is a collective).  None -> NCCL all-reduces."""
+        import torch.distributed as tdist
+        if not image_emb.is_cuda or os.environ.get("PLK_XGPU", "1") == "0":
+            return None
+        world = tdist.get_world_size(self.process_group)
+        n = image_emb.size(0)
+        if world < 2 or world > 8 or (n * world) % buckets or n % ((n * world) // buckets):
+            return None
+        if not self._xgpu_tried:
+            self._xgpu_tried = True
+            try:
+                from .dist import XGpuScalars
+                self._xgpu = XGpuScalars(image_emb.device, self.process_group)
+            except Exception as e:      # no symmetric memory on this system
+                import warnings
+                warnings.warn(f"peer-memory scalar exchange unavailable ({e!r}); using NCCL all-reduces")
+                self._xgpu = None
+        return self._xgpu
 
     def graphed(self, image_emb: Tensor, profile_emb: Tensor):
         """-> callable ``f(image_emb, profile_emb) -> loss`` whose forward AND backward replay CUDA graphs

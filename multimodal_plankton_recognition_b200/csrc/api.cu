@@ -145,9 +145,10 @@ size_t plk_clip_loss_workspace_bytes(int op_dtype, int64_t batch, int64_t d, int
   return (size_t)2 * clip_parts(op_dtype, batch, d, bucket_size) * batch * d * sizeof(float);
 }
 
-int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
-                          int op_dtype, int64_t bucket_size, int64_t batch_global,
-                          const float* logit_scale, void* state, float* loss_out, void* stream) {
+static int clip_forward_impl(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx, int op_dtype,
+                             int64_t bucket_size, int64_t batch_global, const float* logit_scale, void* state,
+                             float* loss_out, float* partial_out, void* const* peer_bufs, int rank, int world,
+                             unsigned* epoch, float* out2, void* stream) {
   PLK_REQUIRE(x && y && logit_scale && state && loss_out, PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(op_dtype >= PLK_F32 && op_dtype <= PLK_F16, PLK_ERR_INVALID, "bad op_dtype %d", op_dtype);
   PLK_REQUIRE(batch > 0 && d > 0 && ldx >= d && bucket_size > 0 && batch % bucket_size == 0 && batch_global >= batch,
@@ -165,8 +166,28 @@ int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t
   rc = plk_infonce_fwd(base + L.u, base + L.v, op_dtype, L.ld, B, 0, B, d, bucket_size, logit_scale, st + 4 * B,
                        st + 5 * B, st + 6 * B, 1, stream);
   if (rc) return rc;
+  if (peer_bufs != nullptr)
+    return plk_infonce_loss_xgpu(st + 4 * B, st + 5 * B, st + 6 * B, logit_scale, B, batch_global, loss_out, aux,
+                                 aux + 1, partial_out, peer_bufs, rank, world, epoch, out2, stream);
   return plk_infonce_loss(st + 4 * B, st + 5 * B, st + 6 * B, logit_scale, B, batch_global, loss_out, aux, aux + 1,
                           stream);
+}
+
+int plk_clip_loss_forward(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
+                          int op_dtype, int64_t bucket_size, int64_t batch_global,
+                          const float* logit_scale, void* state, float* loss_out, void* stream) {
+  return clip_forward_impl(x, y, batch, d, ldx, op_dtype, bucket_size, batch_global, logit_scale, state, loss_out,
+                           nullptr, nullptr, 0, 1, nullptr, nullptr, stream);
+}
+
+int plk_clip_loss_forward_xgpu(const float* x, const float* y, int64_t batch, int64_t d, int64_t ldx,
+                               int op_dtype, int64_t bucket_size, int64_t batch_global,
+                               const float* logit_scale, void* state, float* loss_out, float* partial_out,
+                               void* const* peer_bufs, int rank, int world, unsigned* epoch, float* out2,
+                               void* stream) {
+  PLK_REQUIRE(partial_out && peer_bufs && epoch && out2, PLK_ERR_INVALID, "null pointer");
+  return clip_forward_impl(x, y, batch, d, ldx, op_dtype, bucket_size, batch_global, logit_scale, state, loss_out,
+                           partial_out, peer_bufs, rank, world, epoch, out2, stream);
 }
 
 static int clip_backward_impl(const float* grad_out, const float* grad_out_emb, float emb_scale, const float* x, const float* y,

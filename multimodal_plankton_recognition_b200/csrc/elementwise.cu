@@ -247,6 +247,76 @@ static int l2norm_dispatch_out(const TI* x, int64_t n, int64_t d, int64_t ldx, v
   return PLK_OK;
 }
 
+// Cross-GPU sum of the two per-rank scalars of a sharded step (loss partial, d logit_scale
+// partial), fused into the gradient tail: the ranks exchange them through peer-mapped symmetric
+// memory over NVLink -- a release/acquire flag per (parity, rank) and one 8-byte slot per parity --
+// instead of a separate NCCL all-reduce launch (which costs ~25 us of a ~90 us step).
+//   peer[r] -> rank r's buffer: float data[2 parities][2], then at +64 bytes uint32 flags[2][8].
+// Every rank sums the slots in rank order, so the result is bitwise identical everywhere.
+struct XGpuArgs {
+  void* const* peer;          // device array [world] of peer-mapped base pointers (nullptr: single GPU)
+  int rank, world;
+  unsigned* epoch;            // two local device counters, incremented once per launch (CUDA-graph safe)
+  const float* loss_partial;  // this rank's loss partial
+  float* out2;                // OUT: (global loss, global d logit_scale)
+};
+
+// Publish (first thread block of the kernel) and collect (LAST thread block, which is scheduled near the
+// end of the kernel) are separate, so the time the ranks are out of step with each other is
+// absorbed by the kernel's own row work instead of stalling it.  epoch[0] / epoch[1] count the
+// launches seen by the publisher / the collector.
+__device__ __forceinline__ void xgpu_publish(const XGpuArgs& xg, float loss_part, float dls_part) {
+  // executed by warp 0 of block (0,0); lane r signals rank r
+  const int lane = threadIdx.x;
+  unsigned e = 0;
+  if (lane == 0) { e = xg.epoch[0] + 1; xg.epoch[0] = e; }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  const int p = e & 1;
+  if (lane == 0) {
+    volatile float* mine = reinterpret_cast<volatile float*>(xg.peer[xg.rank]) + 2 * p;
+    mine[0] = loss_part;
+    mine[1] = dls_part;
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (lane < xg.world) {
+    unsigned* their_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(xg.peer[lane]) + 64) + p * 8;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(their_flags + xg.rank), "r"(e) : "memory");
+  }
+}
+__device__ __forceinline__ void xgpu_collect(const XGpuArgs& xg) {
+  // executed by warp 0 of the last block; lane r waits for rank r (its own rank included)
+  const int lane = threadIdx.x;
+  unsigned e = 0;
+  if (lane == 0) { e = xg.epoch[1] + 1; xg.epoch[1] = e; }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  const int p = e & 1;
+  float sl = 0.f, sd = 0.f;
+  if (lane < xg.world) {
+    const unsigned* my_flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(xg.peer[xg.rank]) + 64) + p * 8;
+    unsigned seen = 0;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flags + lane) : "memory");
+      if (seen != e && clock64() - t0 > 4000000000LL) {
+        printf("plk: cross-GPU scalar exchange timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n",
+               xg.rank, lane, e, seen);
+        __trap();
+      }
+    } while (seen != e);
+    const volatile float* theirs = reinterpret_cast<const volatile float*>(xg.peer[lane]) + 2 * p;
+    sl = theirs[0];
+    sd = theirs[1];
+  }
+  // fixed-order sum (lane 0 adds ranks 0..world-1 in order): identical bits on every rank
+  float tl = 0.f, td = 0.f;
+  for (int r = 0; r < xg.world; ++r) {
+    tl += __shfl_sync(0xffffffffu, sl, r);
+    td += __shfl_sync(0xffffffffu, sd, r);
+  }
+  if (lane == 0) { xg.out2[0] = tl; xg.out2[1] = td; }
+}
+
 // ---------------------------------------------------------------------------------------------
 // a8: loss partial over the owned rows                              reference src/coordination.py:45
 // ---------------------------------------------------------------------------------------------
@@ -256,7 +326,10 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ rs
                                                     const float* __restrict__ ls, int64_t n,
                                                     int64_t batch, float* __restrict__ loss_out,
                                                     float* __restrict__ diag_sum_out,
-                                                    float* __restrict__ gs_zero) {
+                                                    float* __restrict__ gs_zero, XGpuArgs xg,
+                                                    float* __restrict__ partial_out) {
+  // xg.peer != nullptr: *loss_out is the sum of the partials of all ranks (exchanged through peer
+  // memory by warp 0, see xgpu_publish / xgpu_collect); this rank's partial goes to *partial_out.
   __shared__ double sh[2][32];
   pdl_wait();      // the forward kernel is complete
   // A kernel queued behind this one with programmatic serialization (the recompute backward) may
@@ -279,9 +352,17 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ rs
     dsum = threadIdx.x < (blockDim.x >> 5) ? sh[1][threadIdx.x] : 0.0;
     a = warp_sum(a);
     dsum = warp_sum(dsum);
+    const float part = (float)(a / (2.0 * (double)batch));
     if (threadIdx.x == 0) {
-      *loss_out = (float)(a / (2.0 * (double)batch));
       if (diag_sum_out) *diag_sum_out = (float)dsum;
+      if (xg.peer == nullptr) *loss_out = part;
+      else *partial_out = part;
+    }
+    if (xg.peer != nullptr) {
+      xgpu_publish(xg, threadIdx.x == 0 ? part : 0.f, 0.f);
+      xgpu_collect(xg);
+      __syncwarp();
+      if (threadIdx.x == 0) *loss_out = xg.out2[0];
     }
   }
 }
@@ -417,76 +498,6 @@ struct FinishPairArgs {
   const double* sig_sums;
   float* dbias_out;
 };
-// Cross-GPU sum of the two per-rank scalars of a sharded step (loss partial, d logit_scale
-// partial), fused into the gradient tail: the ranks exchange them through peer-mapped symmetric
-// memory over NVLink -- a release/acquire flag per (parity, rank) and one 8-byte slot per parity --
-// instead of a separate NCCL all-reduce launch (which costs ~25 us of a ~90 us step).
-//   peer[r] -> rank r's buffer: float data[2 parities][2], then at +64 bytes uint32 flags[2][8].
-// Every rank sums the slots in rank order, so the result is bitwise identical everywhere.
-struct XGpuArgs {
-  void* const* peer;          // device array [world] of peer-mapped base pointers (nullptr: single GPU)
-  int rank, world;
-  unsigned* epoch;            // two local device counters, incremented once per launch (CUDA-graph safe)
-  const float* loss_partial;  // this rank's loss partial
-  float* out2;                // OUT: (global loss, global d logit_scale)
-};
-
-// Publish (first thread block of the kernel) and collect (LAST thread block, which is scheduled near the
-// end of the kernel) are separate, so the time the ranks are out of step with each other is
-// absorbed by the kernel's own row work instead of stalling it.  epoch[0] / epoch[1] count the
-// launches seen by the publisher / the collector.
-__device__ __forceinline__ void xgpu_publish(const XGpuArgs& xg, float loss_part, float dls_part) {
-  // executed by warp 0 of block (0,0); lane r signals rank r
-  const int lane = threadIdx.x;
-  unsigned e = 0;
-  if (lane == 0) { e = xg.epoch[0] + 1; xg.epoch[0] = e; }
-  e = __shfl_sync(0xffffffffu, e, 0);
-  const int p = e & 1;
-  if (lane == 0) {
-    volatile float* mine = reinterpret_cast<volatile float*>(xg.peer[xg.rank]) + 2 * p;
-    mine[0] = loss_part;
-    mine[1] = dls_part;
-    __threadfence_system();
-  }
-  __syncwarp();
-  if (lane < xg.world) {
-    unsigned* their_flags = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(xg.peer[lane]) + 64) + p * 8;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(their_flags + xg.rank), "r"(e) : "memory");
-  }
-}
-__device__ __forceinline__ void xgpu_collect(const XGpuArgs& xg) {
-  // executed by warp 0 of the last block; lane r waits for rank r (its own rank included)
-  const int lane = threadIdx.x;
-  unsigned e = 0;
-  if (lane == 0) { e = xg.epoch[1] + 1; xg.epoch[1] = e; }
-  e = __shfl_sync(0xffffffffu, e, 0);
-  const int p = e & 1;
-  float sl = 0.f, sd = 0.f;
-  if (lane < xg.world) {
-    const unsigned* my_flags = reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(xg.peer[xg.rank]) + 64) + p * 8;
-    unsigned seen = 0;
-    const long long t0 = clock64();
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flags + lane) : "memory");
-      if (seen != e && clock64() - t0 > 4000000000LL) {
-        printf("plk: cross-GPU scalar exchange timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n",
-               xg.rank, lane, e, seen);
-        __trap();
-      }
-    } while (seen != e);
-    const volatile float* theirs = reinterpret_cast<const volatile float*>(xg.peer[lane]) + 2 * p;
-    sl = theirs[0];
-    sd = theirs[1];
-  }
-  // fixed-order sum (lane 0 adds ranks 0..world-1 in order): identical bits on every rank
-  float tl = 0.f, td = 0.f;
-  for (int r = 0; r < xg.world; ++r) {
-    tl += __shfl_sync(0xffffffffu, sl, r);
-    td += __shfl_sync(0xffffffffu, sd, r);
-  }
-  if (lane == 0) { xg.out2[0] = tl; xg.out2[1] = td; }
-}
-
 template <int NV>
 __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     FinishPairArgs a, int parts, int64_t n, int64_t ldx, const float* __restrict__ diag,
@@ -787,8 +798,26 @@ int plk_infonce_loss(const float* row_sumexp, const float* col_sumexp_own, const
                      float* diag_sum_out, float* gs_zero, void* stream) {
   PLK_REQUIRE(row_sumexp && col_sumexp_own && diag && logit_scale && loss_out, PLK_ERR_INVALID, "null pointer");
   PLK_REQUIRE(n_rows > 0 && batch_global >= n_rows, PLK_ERR_INVALID, "bad sizes");
+  XGpuArgs xg = {};
   PLK_CUDA(launch_overlapped(loss_kernel, dim3(1), dim3(1024), (cudaStream_t)stream, row_sumexp, col_sumexp_own, diag,
-                             logit_scale, n_rows, batch_global, loss_out, diag_sum_out, gs_zero));
+                             logit_scale, n_rows, batch_global, loss_out, diag_sum_out, gs_zero, xg, (float*)nullptr));
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+
+int plk_infonce_loss_xgpu(const float* row_sumexp, const float* col_sumexp_own, const float* diag,
+                          const float* logit_scale, int64_t n_rows, int64_t batch_global, float* loss_out,
+                          float* diag_sum_out, float* gs_zero, float* partial_out, void* const* peer_bufs,
+                          int rank, int world, unsigned* epoch, float* out2, void* stream) {
+  PLK_REQUIRE(row_sumexp && col_sumexp_own && diag && logit_scale && loss_out && partial_out && peer_bufs && epoch &&
+                  out2, PLK_ERR_INVALID, "null pointer");
+  PLK_REQUIRE(n_rows > 0 && batch_global >= n_rows, PLK_ERR_INVALID, "bad sizes");
+  PLK_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, PLK_ERR_INVALID,
+              "world must be in [2, 8] (got rank %d of %d)", rank, world);
+  XGpuArgs xg;
+  xg.peer = peer_bufs; xg.rank = rank; xg.world = world; xg.epoch = epoch; xg.loss_partial = nullptr; xg.out2 = out2;
+  PLK_CUDA(launch_overlapped(loss_kernel, dim3(1), dim3(1024), (cudaStream_t)stream, row_sumexp, col_sumexp_own, diag,
+                             logit_scale, n_rows, batch_global, loss_out, diag_sum_out, gs_zero, xg, partial_out));
   PLK_LAUNCHED(1);
   return PLK_OK;
 }

@@ -54,10 +54,12 @@ class XGpuScalars:
         dist.barrier(group=group)       # every rank's zero-fill is visible before anyone signals
 
 
-def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduce_scalars=True):
+def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduce_scalars=True, xgpu=None):
     """Forward of the row-block sharded loss without autograd: -> (global loss [], saved state).
     With reduce_scalars=False the returned loss is this rank's partial sum (the caller all-reduces
-    it); in the bucket-aligned case the call then contains no collective at all."""
+    it); in the bucket-aligned case the call then contains no collective at all.  With
+    reduce_scalars=True and `xgpu` (XGpuScalars) the bucket-aligned case has none either: the loss
+    kernel itself sums the partials over the ranks through NVLink peer memory."""
     R, r = _world(group)
     n, d = image_emb.shape
     B = n * R
@@ -71,9 +73,12 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
         # every bucket lives entirely on one rank (block-diagonal logits): no data-path exchange, the
         # local problem is complete -- the single-GPU composite step with the global 1/(2B); only the
         # two scalars are reduced.
-        loss, st = ops.clip_loss_forward_state(x, y, ls, bs, mode, batch_global=B, loss_out=scal[0])
-        if reduce_scalars:
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        if reduce_scalars and xgpu is not None:
+            loss, st = ops.clip_loss_forward_state(x, y, ls, bs, mode, batch_global=B, xgpu=xgpu, partial_out=scal[0:1])
+        else:
+            loss, st = ops.clip_loss_forward_state(x, y, ls, bs, mode, batch_global=B, loss_out=scal[0])
+            if reduce_scalars:
+                dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
         return loss, (x, y, ls, st, scal, (True, n, d, B, bs, off, mode, group))
     st4 = torch.empty((4, n), device=x.device, dtype=torch.float32)
     rs = torch.empty(n, device=x.device, dtype=torch.float32)
@@ -130,36 +135,42 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
                                                    xgpu=xgpu, loss_partial=scal[0:1] if xgpu is not None else None)
     dx, dy = dx.to(out_dtypes[0]), dy.to(out_dtypes[1])
     if reduce_scalars:
-        dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
+        if xgpu is not None and aligned:
+            dls = xgpu.out2[1].clone()      # summed over the ranks inside the gradient-tail kernel
+        else:
+            dist.all_reduce(dls, op=dist.ReduceOp.SUM, group=group)   # identical on every rank afterwards
     return dx, dy, dls
 
 
 class _ShardedClipLoss(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, image_emb, profile_emb, logit_scale, buckets, mode, group, grad_scale):
-        loss, state = sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group)
+    def forward(ctx, image_emb, profile_emb, logit_scale, buckets, mode, group, grad_scale, xgpu):
+        loss, state = sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, xgpu=xgpu)
         ctx.plk_state = state    # intermediates only (detached fp32 rows, opaque buffers): no graph edges
-        ctx.meta = (grad_scale, image_emb.dtype, profile_emb.dtype, logit_scale.dtype)
+        ctx.meta = (grad_scale, image_emb.dtype, profile_emb.dtype, logit_scale.dtype, xgpu)
         return loss
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g):
-        grad_scale, dt_x, dt_y, dt_ls = ctx.meta
-        dx, dy, dls = sharded_bwd(ctx.plk_state, g, grad_scale, (dt_x, dt_y))
-        return dx, dy, dls.to(dt_ls), None, None, None, None
+        grad_scale, dt_x, dt_y, dt_ls, xgpu = ctx.meta
+        dx, dy, dls = sharded_bwd(ctx.plk_state, g, grad_scale, (dt_x, dt_y), xgpu=xgpu)
+        return dx, dy, dls.to(dt_ls), None, None, None, None, None
 
 
 def sharded_clip_loss(image_emb, profile_emb, logit_scale, buckets: int = 1, mode: int = ops.PLK_BF16,
-                      group=None, grad_scale: str = "ddp") -> torch.Tensor:
+                      group=None, grad_scale: str = "ddp", xgpu=None) -> torch.Tensor:
     """Global-batch symmetric InfoNCE from per-rank row blocks (every rank passes n rows; the
-    global batch is the rank-ordered concatenation).  Returns the global loss on every rank."""
+    global batch is the rank-ordered concatenation).  Returns the global loss on every rank.
+    `xgpu` (XGpuScalars of the same group): in the bucket-aligned case the two scalar sums run inside
+    the kernels over NVLink peer memory and the step contains no collective launch."""
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("sharded_clip_loss needs an initialised torch.distributed process group")
     if grad_scale not in ("ddp", "none"):
         raise ValueError("grad_scale must be 'ddp' or 'none'")
-    return _ShardedClipLoss.apply(image_emb, profile_emb, logit_scale, int(buckets), int(mode), group, grad_scale)
+    return _ShardedClipLoss.apply(image_emb, profile_emb, logit_scale, int(buckets), int(mode), group, grad_scale,
+                                  xgpu)
 
 
 def merge_shard_results(idx: torch.Tensor, dst: torch.Tensor, k: int, group=None):

@@ -289,11 +289,14 @@ def _f32_rows(t: torch.Tensor) -> torch.Tensor:
 
 
 def clip_loss_forward_state(x: torch.Tensor, y: torch.Tensor, ls: torch.Tensor, bs: int, mode: int,
-                            batch_global: int | None = None, loss_out: torch.Tensor | None = None):
+                            batch_global: int | None = None, loss_out: torch.Tensor | None = None, xgpu=None,
+                            partial_out: torch.Tensor | None = None):
     """x, y: fp32 [B, d] rows (unit inner stride, equal row stride); ls: fp32 scalar on the device.
     -> (loss [], state) where `state` is the opaque buffer plk_clip_loss_backward consumes.
     `batch_global` > B: the rows are one rank's share of a bucket-aligned global batch and `loss`
-    is that rank's partial sum."""
+    is that rank's partial sum -- unless `xgpu` (dist.XGpuScalars) is given: then the loss kernel sums
+    the partials over the ranks through peer memory, `loss` is the global loss and the partial goes
+    to `partial_out`."""
     lib = _lib.load()
     B, d = x.shape
     dev = x.device
@@ -305,11 +308,16 @@ def clip_loss_forward_state(x: torch.Tensor, y: torch.Tensor, ls: torch.Tensor, 
     idx = dev.index
     if torch.cuda.current_device() != idx:
         with torch.cuda.device(idx):
-            return clip_loss_forward_state(x, y, ls, bs, mode, batch_global, loss)
-    lib.check(lib.plk_clip_loss_forward(x.data_ptr(), y.data_ptr(), B, d, x.stride(0), mode, bs,
-                                        B if batch_global is None else batch_global, ls.data_ptr(),
-                                        state.data_ptr(), loss.data_ptr(),
-                                        torch._C._cuda_getCurrentRawStream(idx)), "plk_clip_loss_forward")
+            return clip_loss_forward_state(x, y, ls, bs, mode, batch_global, loss, xgpu, partial_out)
+    stream = torch._C._cuda_getCurrentRawStream(idx)
+    common = (x.data_ptr(), y.data_ptr(), B, d, x.stride(0), mode, bs, B if batch_global is None else batch_global,
+              ls.data_ptr(), state.data_ptr(), loss.data_ptr())
+    if xgpu is None:
+        lib.check(lib.plk_clip_loss_forward(*common, stream), "plk_clip_loss_forward")
+    else:
+        lib.check(lib.plk_clip_loss_forward_xgpu(*common, partial_out.data_ptr(), xgpu.peer_ptrs_dev, xgpu.rank,
+                                                 xgpu.world, xgpu.epoch.data_ptr(), xgpu.out2.data_ptr(), stream),
+                  "plk_clip_loss_forward_xgpu")
     return loss, state
 
 

@@ -106,8 +106,9 @@ def infonce_dls(gs, diag_sum, go, batch_global, out=None):
     return val
 
 
-def clip_loss_forward_state(x, y, ls, bs, mode, batch_global=None, loss_out=None):
+def clip_loss_forward_state(x, y, ls, bs, mode, batch_global=None, loss_out=None, xgpu=None, partial_out=None):
     """plk_clip_loss_forward: the complete local problem with the global 1/(2B)."""
+    assert xgpu is None, "the fused cross-GPU exchange is CUDA-only"
     n, d = x.shape
     stats = torch.empty((4, n))
     u, v = l2norm_pair(x, y, mode, stats)

@@ -62,6 +62,34 @@ except Exception as e:
     ok = False
     print(f"rank {rank}: fused xgpu exchange failed: {e!r}", flush=True)
 
+# the module path: CLIPLoss(sharded=True) -- bucket-aligned steps run without a collective launch (the loss
+# kernel and the gradient-tail kernel exchange the scalars over peer memory); three steps on one module
+for prec, tol in (("fp32", 2e-5), ("bf16", 2e-3)):
+    mod = CLIPLoss(precision=prec, sharded=True).to(dev)
+    ref = CLIPLoss(precision="fp32").to(dev)
+    for step, (B, d, buckets) in enumerate(((1024, 256, world), (2048, 128, 2 * world), (1024, 256, 1))):
+        img, pro, _ = synth.pairs(B, d, 90 + step, "cpu")
+        n = B // world
+        x = img[rank * n:(rank + 1) * n].to(dev).requires_grad_()
+        y = pro[rank * n:(rank + 1) * n].to(dev).requires_grad_()
+        mod.logit_scale.grad = None
+        ref.logit_scale.grad = None
+        loss = mod(image_emb=x, profile_emb=y, buckets=buckets)
+        loss.backward()
+        xf, yf = img.to(dev).requires_grad_(), pro.to(dev).requires_grad_()
+        lref = ref(image_emb=xf, profile_emb=yf, buckets=buckets)
+        lref.backward()
+        gx = xf.grad[rank * n:(rank + 1) * n] * world          # grad_scale="ddp": pre-multiplied by the world size
+        e_loss = abs(float(loss.detach()) - float(lref.detach())) / abs(float(lref.detach()))
+        e_gx = float((x.grad - gx).abs().max() / gx.abs().max())
+        e_ls = abs(float(mod.logit_scale.grad) - float(ref.logit_scale.grad)) / max(abs(float(ref.logit_scale.grad)), 1e-6)
+        good = max(e_loss, e_gx, e_ls) < tol
+        ok &= good
+        if rank == 0:
+            how = "peer memory" if (mod._xgpu is not None and buckets % world == 0) else "NCCL"
+            print(f"module[{prec}] B={B} d={d} bk={buckets} ({how}): loss {e_loss:.1e} dI {e_gx:.1e} dls {e_ls:.1e} "
+                  f"{'OK' if good else 'FAIL'}", flush=True)
+
 gal, lab = synth.unit_embeddings(40000, 256, 3, "cpu", 1)
 q, _ = synth.unit_embeddings(2000, 256, 4, "cpu", 0)
 shard = 40000 // world
