@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from ._lib import PLK_BF16, PLK_F32
+from ._lib import PLK_F32
 
 
 class GpuExactIndex:
