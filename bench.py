@@ -131,9 +131,12 @@ def run_reference(args, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"InfoNCE fwd+bwd B={B_C2} d={D_C2} buckets=1 (BASELINE config[1])",
-                   "note": "oracle port of reference CLIPLoss on host cores; /root/reference (Python) "
-                           "does not travel to the GPU box"},
+        "config": {"workload": f"symmetric InfoNCE fwd+bwd, batch {B_C2} per GPU x d={D_C2}, f32 "
+                               f"(BASELINE config[1]); N>1: global batch {B_C2 * args.gpus}, buckets={args.gpus}",
+                   "global_batch": B_C2 * args.gpus, "d": D_C2, "buckets": args.gpus, "logit_scale": 1.0,
+                   "note": "oracle port of reference CLIPLoss on host cores (/root/reference is Python and does "
+                           "not travel to the GPU box); each step is one bucket of 4096 pairs -- the buckets "
+                           "of the block-diagonal problem are independent, so pairs/s does not depend on N"},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{len(times)} full fwd+bwd steps at B={B_C2}, d={D_C2}, fp32, "
                                    f"best {1e3 * min(times):.1f} ms"},

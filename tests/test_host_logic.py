@@ -65,3 +65,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_prefetcher_argument_validation():
+    """prefetch.HostPairPrefetcher rejects an unusable configuration before touching CUDA."""
+    from multimodal_plankton_recognition_b200.prefetch import HostPairPrefetcher
+    with pytest.raises(ValueError, match="depth"):
+        HostPairPrefetcher(iter(()), "cuda:0", depth=1)
+    with pytest.raises(ValueError, match="CUDA"):
+        HostPairPrefetcher(iter(()), "cpu", depth=2)
+
+
+def test_sharded_module_keeps_nccl_path_without_cuda():
+    """CLIPLoss._peer_scalars only turns the peer-memory exchange on for CUDA tensors in a bucket-aligned
+    layout; anything else keeps the all-reduce path (and creates nothing)."""
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    mod = CLIPLoss(sharded=True)
+    assert mod._peer_scalars(torch.randn(8, 4), 2) is None and mod._xgpu is None and not mod._xgpu_tried
