@@ -109,6 +109,36 @@ def test_ddp_gradient_scaling():
     assert out[0][3] == pytest.approx(ref["d_logit_scale"], rel=1e-5)
 
 
+def _module_worker(d, buckets, rank):
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    img, pro = _data(96, d, seed=3)
+    n = img.shape[0] // WORLD
+    x = torch.tensor(img[rank * n:(rank + 1) * n], requires_grad=True)
+    y = torch.tensor(pro[rank * n:(rank + 1) * n], requires_grad=True)
+    mod = CLIPLoss(precision="fp32", sharded=True)
+    loss = mod(image_emb=x, profile_emb=y, buckets=buckets)
+    loss.backward()
+    return float(loss.detach()), x.grad.numpy(), y.grad.numpy(), float(mod.logit_scale.grad)
+
+
+@pytest.mark.parametrize("d,buckets", [(128, 2), (24, 2), (128, 3)])   # in-kernel DDP factor / host factor / not aligned
+def test_sharded_module_path_with_ddp_scaling(d, buckets):
+    """`CLIPLoss(sharded=True)` end to end (module -> dist -> composite calls): global loss on every rank,
+    embedding gradients pre-multiplied by the world size (DDP averages them back), `d logit_scale` global."""
+    import functools
+    from oracle import infonce as oinf
+    img, pro = _data(96, d, seed=3)
+    ref = oinf.clip_loss_closed_form(img, pro, 1.0, buckets)
+    out = _run(functools.partial(_module_worker, d, buckets))
+    n = img.shape[0] // WORLD
+    for r in range(WORLD):
+        loss, dx, dy, dls = out[r]
+        assert loss == pytest.approx(ref["loss"], rel=1e-6)
+        np.testing.assert_allclose(dx, WORLD * ref["d_image"][r * n:(r + 1) * n], rtol=2e-4, atol=1e-8)
+        np.testing.assert_allclose(dy, WORLD * ref["d_profile"][r * n:(r + 1) * n], rtol=2e-4, atol=1e-8)
+        assert dls == pytest.approx(ref["d_logit_scale"], rel=1e-5)
+
+
 def _ann_case(rank):
     from multimodal_plankton_recognition_b200.dist import ShardedANNClassifier
     r = np.random.default_rng(5)
