@@ -104,3 +104,27 @@ def test_zero_distance_weights():
 def test_bucket_divisibility_assert():
     with pytest.raises(AssertionError, match="divisible"):
         oinf.clip_loss_closed_form(np.ones((6, 4)), np.ones((6, 4)), buckets=4)
+
+
+def test_siglip_oracle_properties():
+    """Size-independent properties of the SigLIP restatement: gradients scale linearly with the upstream
+    gradient, buckets decouple (block-diagonal), and `d bias` is the sum of the logit gradients."""
+    r = np.random.default_rng(7)
+    img = r.standard_normal((48, 20))
+    pro = img + 0.6 * r.standard_normal((48, 20))
+    a = osig.siglip_loss_closed_form(img, pro, 1.2, -3.0, 3)
+    b = osig.siglip_loss_closed_form(img, pro, 1.2, -3.0, 3, grad_out=2.5)
+    np.testing.assert_allclose(b["d_image"], 2.5 * a["d_image"], rtol=1e-12)
+    assert b["d_bias"] == pytest.approx(2.5 * a["d_bias"], rel=1e-12)
+    # three buckets of 16 == three independent problems of batch 16, averaged
+    parts = [osig.siglip_loss_closed_form(img[i:i + 16], pro[i:i + 16], 1.2, -3.0, 1) for i in (0, 16, 32)]
+    assert a["loss"] == pytest.approx(np.mean([p["loss"] for p in parts]), rel=1e-12)
+    np.testing.assert_allclose(a["d_image"][16:32], parts[1]["d_image"] / 3, rtol=1e-10)
+    # finite-difference check of d bias and d logit_scale
+    eps = 1e-6
+    up = osig.siglip_loss_closed_form(img, pro, 1.2, -3.0 + eps, 3)["loss"]
+    dn = osig.siglip_loss_closed_form(img, pro, 1.2, -3.0 - eps, 3)["loss"]
+    assert (up - dn) / (2 * eps) == pytest.approx(a["d_bias"], rel=1e-6)
+    up = osig.siglip_loss_closed_form(img, pro, 1.2 + eps, -3.0, 3)["loss"]
+    dn = osig.siglip_loss_closed_form(img, pro, 1.2 - eps, -3.0, 3)["loss"]
+    assert (up - dn) / (2 * eps) == pytest.approx(a["d_logit_scale"], rel=1e-6)
