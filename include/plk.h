@@ -81,9 +81,12 @@ int plk_l2norm_pair_fwd(const float* x, const float* y, int64_t n, int64_t d, in
  *   v [n_cols, ld]   normalised rows of the other modality for the WHOLE (global) batch
  *   S_ij = exp(*logit_scale) * u_i . v_j, restricted to j in the bucket of global row i
  *          (bucket b = global_i / bucket_size, columns [b*bs, (b+1)*bs)).
- *   Fixed shift: because |u.v| <= 1, E_ij = exp(S_ij - s) never overflows, so ONE exp
- *   serves the row and the column sums.  E underflows only when s*(1 - cos) > 87, so the sums are
- *   exact for any data while s = exp(logit_scale) <= 43.
+ *   Fixed, range-centred shift: because |u.v| <= 1, E_ij = exp(S_ij - s + 64) <= e^64 never overflows
+ *   (nor does a sum of up to e^24 of them), so ONE exp serves the row and the column sums.  A row keeps
+ *   a non-zero sum while its best match satisfies s*(1 - cos_max) < 151: any data for
+ *   s = exp(logit_scale) <= 75 (logit_scale <= 4.3), and s <= 151 (logit_scale <= 5.0) when every row
+ *   has a non-negative best cosine.  Beyond that plk_infonce_loss returns NaN (never a finite-looking
+ *   wrong loss); the reference's F.cross_entropy has no such limit.
  *
  *   row_sumexp [n_rows]  OUT  sum_j E_ij                (complete)
  *   col_sumexp [n_cols]  OUT  sum_{i owned} E_ij        (partial when rows are sharded)
@@ -98,7 +101,7 @@ int plk_infonce_fwd(const void* u, const void* v, int op_dtype, int64_t ld,
                     void* stream);
 
 /* a8. loss partial over owned rows:
- *   *loss_out = (1/(2*B_global)) * sum_i [ 2 s + log R_i + log C_i - 2 S_ii ]      reference src/coordination.py:45
+ *   *loss_out = (1/(2*B_global)) * sum_i [ 2 (s - 64) + log R_i + log C_i - 2 S_ii ]   reference src/coordination.py:45
  *   col_sumexp_own points at the n_rows entries of the (all-reduced) column sums that
  *   belong to the owned rows.  Also writes sum_i S_ii to *diag_sum_out (used by d logit_scale) and,
  *   if gs_zero is not NULL, stores 0 to *gs_zero (the accumulator plk_infonce_grad adds into). */
@@ -150,7 +153,7 @@ int plk_infonce_grad_pair(const void* a0, const void* b0, const void* a1, const 
 /* a9 (tail). Adds the j == i term and the -2*delta_ij term in fp32, applies g*s/(2B) and the
  * normalisation backward:
  *   acc_i = sum over the `parts` slabs of acc  (plk_infonce_grad leaves the j == i term out);
- *   dU_i = coef * (acc_i + (E_ii (1/rs_i + 1/cs_i) - 2) p_i / den_p_i),  E_ii = exp(diag_i - s),
+ *   dU_i = coef * (acc_i + (E_ii (1/rs_i + 1/cs_i) - 2) p_i / den_p_i),  E_ii = exp(diag_i - s + 64),
  *          coef = (*grad_out) * s / (2 B_global)
  *   dx_i = (dU_i - u_i (u_i . dU_i)) / den_i      if ||x_i|| > eps,   else dU_i / eps
  *   x, partner: RAW fp32 embeddings [n, d] of this modality / the other one (same rows);
@@ -282,8 +285,10 @@ int plk_siglip_grad_finish_pair(const float* acc_x, const float* acc_y, int part
  * Staging host-resident batches into HBM under the running step (no reference counterpart: the
  * reference hands each batch to the device serially through Lightning's loop,
  * reference scripts/train_multi.py:78-85).  A stager owns a copy stream and per-slot events:
- *   issue(slot)             copy stream: wait until `slot` was released, copy x (and y) host->device,
- *                           mark the slot ready.  Host buffers must be page-locked to overlap.
+ *   issue(slot)             host: wait until the slot's PREVIOUS copy has finished (its host buffers may be
+ *                           released once this call returns); copy stream: wait until `slot` was released,
+ *                           copy x (and y) host->device, mark the slot ready.  Host buffers must be
+ *                           page-locked to overlap and must stay alive until the slot's next issue returns.
  *   acquire(slot, release)  consumer stream: mark `release` (>= 0) reusable after everything queued
  *                           so far, then wait until `slot` is ready.
  *   read_async / read_wait  device->host copy of a result on the consumer stream + an event the

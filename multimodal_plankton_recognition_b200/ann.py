@@ -58,31 +58,47 @@ class GpuExactIndex:
         self.slack = int(slack)
         self.g32 = g32
         self.g_op, _, _, self.g_sqn = ops.l2norm(self.g32, self.mode, normalise=False, want_sqn=True)
+        self._g_sqn32 = self.g_sqn if self.mode == PLK_F32 else None
 
     def prepare(self):  # pynndescent API parity (reference src/ann.py:12)
         return None
 
     # -- device-level search: q32 [nq, d] fp32 on device -> (idx int32 [nq,k], dist fp32 [nq,k]) --
+    def _fp32_operands(self):
+        """Squared norms of the fp32 rows, for the CUDA-core candidate search that serves large k on a
+        16-bit index (computed at first use; the fp32 gallery itself is already resident for the re-score)."""
+        if self._g_sqn32 is None:
+            _, _, _, self._g_sqn32 = ops.l2norm(self.g32, PLK_F32, normalise=False, want_sqn=True)
+        return self.g32, self._g_sqn32
+
+    # -- device-level search: q32 [nq, d] fp32 on device -> (idx int32 [nq,k], dist fp32 [nq,k]) --
     def search_device(self, q32: torch.Tensor, k: int):
+        """Exact k nearest by (distance, index).  Candidates: the k + slack best by the ranking key of the
+        index's precision; the tensor-core kernel keeps at most 32 candidates per query in registers, so a
+        16-bit index serves k <= 32 - slack (26) from it and larger k (the reference's drivers go to 51:
+        scripts/benchmark_raw.py:82, benchmark_folds.py:70) from the fp32 CUDA-core search, k <= 64 - slack."""
         lib = self.lib
         nq = q32.shape[0]
-        kmax = 64 if self.mode == PLK_F32 else 32
-        if k < 1 or k > kmax:
-            raise ValueError(f"k must be in [1, {kmax}] for this precision, got {k}")
-        kc = min(kmax, max(k + self.slack, k + self.slack if self.mode == PLK_F32 else 16))
-        q_op, _, _, _ = ops.l2norm(q32, self.mode, normalise=False)
+        mode, g_op, g_sqn = self.mode, self.g_op, self.g_sqn
+        if mode != PLK_F32 and k + self.slack > 32:
+            mode = PLK_F32
+            g_op, g_sqn = self._fp32_operands()
+        if k < 1 or k + self.slack > 64:
+            raise ValueError(f"k must be in [1, {64 - self.slack}], got {k}")
+        kc = k + self.slack if mode == PLK_F32 else max(k + self.slack, 16)
+        q_op = q32 if mode == PLK_F32 else ops.l2norm(q32, mode, normalise=False)[0]
         dev = self.device
         cand_idx = torch.empty((nq, kc), device=dev, dtype=torch.int32)
         cand_key = torch.empty((nq, kc), device=dev, dtype=torch.float32)
-        ws_bytes = lib.plk_topk_workspace_bytes(nq, self.n, self.d, kc, self.mode)
+        ws_bytes = lib.plk_topk_workspace_bytes(nq, self.n, self.d, kc, mode)
         ws = torch.empty(max(ws_bytes, 16), device=dev, dtype=torch.uint8)
         out_idx = torch.empty((nq, k), device=dev, dtype=torch.int32)
         out_dist = torch.empty((nq, k), device=dev, dtype=torch.float32)
         scratch = torch.empty((nq, kc), device=dev, dtype=torch.float32)
         st = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            lib.check(lib.plk_topk_candidates(q_op.data_ptr(), self.g_op.data_ptr(), self.mode, q_op.stride(0),
-                                              self.g_sqn.data_ptr(), nq, self.n, self.d, kc,
+            lib.check(lib.plk_topk_candidates(q_op.data_ptr(), g_op.data_ptr(), mode, q_op.stride(0),
+                                              g_sqn.data_ptr(), nq, self.n, self.d, kc,
                                               self.gallery_offset, cand_idx.data_ptr(), cand_key.data_ptr(),
                                               ws.data_ptr(), ws_bytes, st), "plk_topk_candidates")
             lib.check(lib.plk_topk_rescore(q32.data_ptr(), self.g32.data_ptr(), nq, self.n, self.d,

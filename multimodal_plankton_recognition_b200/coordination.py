@@ -66,6 +66,9 @@ class CLIPLoss(Module):
         n = image_emb.size(0)
         if world < 2 or world > 8 or (n * world) % buckets or n % ((n * world) // buckets):
             return None
+        d = image_emb.size(1)
+        if d % 128 or d > 1024:     # the fused exchange lives in the vectorised kernels (dist.xgpu_supported)
+            return None
         if not self._xgpu_tried:
             self._xgpu_tried = True
             try:

@@ -3,6 +3,7 @@
 // One warp per row, coalesced 32-lane sweeps along d; grids are sized from the row count.
 #include <math_constants.h>
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace plk {
@@ -259,7 +260,20 @@ struct XGpuArgs {
   unsigned* epoch;            // two local device counters, incremented once per launch (CUDA-graph safe)
   const float* loss_partial;  // this rank's loss partial
   float* out2;                // OUT: (global loss, global d logit_scale)
+  long long timeout;          // spin budget in SM clock cycles before the exchange is declared dead
 };
+
+// Peers are other processes (a rank can sit in a checkpoint write, a validation pass or a data-loader stall
+// while the others wait): the default budget matches NCCL's watchdog, PLK_XGPU_TIMEOUT_S overrides it.
+static long long xgpu_timeout_cycles() {
+  static const long long cycles = [] {
+    const char* e = getenv("PLK_XGPU_TIMEOUT_S");
+    double sec = e != nullptr ? atof(e) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    return (long long)(sec * 2.0e9);
+  }();
+  return cycles;
+}
 
 // Publish (first thread block of the kernel) and collect (LAST thread block, which is scheduled near the
 // end of the kernel) are separate, so the time the ranks are out of step with each other is
@@ -298,9 +312,8 @@ __device__ __forceinline__ void xgpu_collect(const XGpuArgs& xg) {
     const long long t0 = clock64();
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(my_flags + lane) : "memory");
-      // peers are other processes: allow for a long host-side hiccup (~20 s at 1.9 GHz) before
-      // declaring the exchange dead; a protocol error still ends in a trap, not a hang
-      if (seen != e && clock64() - t0 > 40000000000LL) {
+      // a protocol error (or a dead peer) ends in a trap after xg.timeout cycles, not in a hang
+      if (seen != e && clock64() - t0 > xg.timeout) {
         printf("plk: cross-GPU scalar exchange timed out (rank %d waiting for rank %d, epoch %u, saw %u)\n",
                xg.rank, lane, e, seen);
         __trap();
@@ -339,10 +352,15 @@ __global__ void __launch_bounds__(1024) loss_kernel(const float* __restrict__ rs
   pdl_trigger();
   if (threadIdx.x == 0 && gs_zero != nullptr) *gs_zero = 0.f;
   const double s = (double)expf(*ls);
+  const double shift2 = 2.0 * (s - (double)kShiftK);   // both sum-exps carry exp(-(s - kShiftK)), see common.cuh
   double a = 0.0, dsum = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     const double dg = (double)diag[i];
-    a += 2.0 * s + (double)logf(rs[i]) + (double)logf(cs[i]) - 2.0 * dg;
+    const float r = rs[i], c = cs[i];
+    // A sum-exp that underflowed to zero (temperature beyond the range stated in common.cuh) or overflowed
+    // must not come back as a finite-looking loss: poison it, the gradients follow (1/0 in the backward).
+    const bool ok = r > 0.f && c > 0.f && r <= 3.0e38f && c <= 3.0e38f;
+    a += ok ? shift2 + (double)logf(r) + (double)logf(c) - 2.0 * dg : (double)CUDART_NAN_F;
     dsum += dg;
   }
   a = warp_sum(a);
@@ -818,6 +836,7 @@ int plk_infonce_loss_xgpu(const float* row_sumexp, const float* col_sumexp_own, 
               "world must be in [2, 8] (got rank %d of %d)", rank, world);
   XGpuArgs xg;
   xg.peer = peer_bufs; xg.rank = rank; xg.world = world; xg.epoch = epoch; xg.loss_partial = nullptr; xg.out2 = out2;
+  xg.timeout = xgpu_timeout_cycles();
   PLK_CUDA(launch_overlapped(loss_kernel, dim3(1), dim3(1024), (cudaStream_t)stream, row_sumexp, col_sumexp_own, diag,
                              logit_scale, n_rows, batch_global, loss_out, diag_sum_out, gs_zero, xg, partial_out));
   PLK_LAUNCHED(1);
@@ -940,6 +959,7 @@ int plk_infonce_grad_finish_pair_xgpu(const float* acc_x, const float* acc_y, in
   XGpuArgs xg;
   xg.peer = peer_bufs; xg.rank = rank; xg.world = world; xg.epoch = epoch;
   xg.loss_partial = loss_partial; xg.out2 = out2;
+  xg.timeout = xgpu_timeout_cycles();
   return finish_pair_impl(acc_x, acc_y, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, nrm_y, diag, rs, cs,
                           logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dx, dy, dls_out, xg,
                           stream);
@@ -984,6 +1004,7 @@ int finish_pair_scaled(const float* acc_x, const float* acc_y, int parts, const 
                 "world must be in [2, 8] (got rank %d of %d)", rank, world);
     xg.peer = peer_bufs; xg.rank = rank; xg.world = world; xg.epoch = epoch;
     xg.loss_partial = loss_partial; xg.out2 = out2;
+    xg.timeout = xgpu_timeout_cycles();
   }
   return finish_pair_impl(acc_x, acc_y, parts, x, y, n, d, ldx, inv_den_x, nrm_x, inv_den_y, nrm_y, diag, rs, cs,
                           logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dx, dy, dls_out, xg, stream,

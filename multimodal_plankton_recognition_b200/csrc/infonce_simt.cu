@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NT) infonce_fwd_simt(
       const int64_t j = j0 + tx + 16 * c;
       const bool valid = i < n_rows && j >= lo && j < hi;
       const float S = s * acc[r][c];
-      const float E = valid ? expf(S - s) : 0.f;
+      const float E = valid ? expf(S - s + kShiftK) : 0.f;
       if (valid && j == gi) diag[i] = S;
       rpart += E;
       cpart[c] += E;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(NT) infonce_grad_simt(
           G = (valid && !on_diag) ? sigmoid_f(S + b0) : 0.f;
           gsum_local += G;
         } else {
-          G = valid ? expf(S - s) * (rrs[r] + rcs[tx + 16 * c]) : 0.f;
+          G = valid ? expf(S - s + kShiftK) * (rrs[r] + rcs[tx + 16 * c]) : 0.f;
         }
         gs_local = fmaf(G, S, gs_local);
         // the j == i term is added (in fp32, together with -2*delta) by plk_infonce_grad_finish

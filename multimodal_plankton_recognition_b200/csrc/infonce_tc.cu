@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     if (i < n_rows) bucket_range(gi, bs, n_cols, lo, hi);
     const float s = expf(*ls);
     const bool siglip = sig_bias != nullptr;
-    const float c1 = s * kLog2e, c0 = siglip ? *sig_bias * kLog2e : -c1;
+    const float c1 = s * kLog2e, c0 = siglip ? *sig_bias * kLog2e : (kShiftK - s) * kLog2e;
     float rsum = 0.f;
     float sg_loss = 0.f, sg_gs = 0.f, sg_g = 0.f;
     {  // park this thread's owned row (16-bit operand, padded to KD*64) in TMEM columns 256.. as packed
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
       if (!siglip) rrs = 1.0f / g.rs[i];
     }
     const float s = expf(*ls);
-    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : -c1;
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : (kShiftK - s) * kLog2e;
     const bool want_gs = (g.gs != nullptr) && (h == 0);
     float gs_local = 0.f, gsum_local = 0.f;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
       if (!siglip) rrs = 1.0f / g.rs[i];
     }
     const float s = expf(*ls);
-    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : -c1;
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : (kShiftK - s) * kLog2e;
     const bool want_gs = g.gs != nullptr;
     float gs_local = 0.f, gsum_local = 0.f;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;

@@ -10,7 +10,7 @@ struct Stager {
   int depth = 0;
   cudaStream_t copy = nullptr;
   std::vector<cudaEvent_t> ready, freed, read;
-  std::vector<char> freed_valid;
+  std::vector<char> freed_valid, ready_valid;
 };
 }  // namespace
 
@@ -30,6 +30,7 @@ void* plk_stager_create(int depth, int read_slots) {
   s->ready.assign(depth, nullptr);
   s->freed.assign(depth, nullptr);
   s->freed_valid.assign(depth, 0);
+  s->ready_valid.assign(depth, 0);
   s->read.assign(read_slots, nullptr);
   for (auto* v : {&s->ready, &s->freed, &s->read})
     for (auto& e : *v) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
@@ -56,11 +57,17 @@ int plk_stager_issue(void* h, int slot, void* dst_x, const void* src_x, size_t b
   Stager* s = (Stager*)h;
   PLK_REQUIRE(s && slot >= 0 && slot < s->depth, PLK_ERR_INVALID, "bad stager handle or slot");
   PLK_REQUIRE(dst_x && src_x && bytes_x > 0, PLK_ERR_INVALID, "null buffer");
+  // The slot's PREVIOUS copy read the host buffers the caller is about to let go of (they go back to a
+  // pinned-memory pool): wait on the host until that DMA has finished.  It was queued `depth` issues ago,
+  // so this returns at once unless the host has run `depth` batches ahead of the copy engine -- in which
+  // case it is the back-pressure that keeps a recycled pinned block from being overwritten mid-copy.
+  if (s->ready_valid[slot]) PLK_CUDA(cudaEventSynchronize(s->ready[slot]));
   if (s->freed_valid[slot]) PLK_CUDA(cudaStreamWaitEvent(s->copy, s->freed[slot], 0));
   PLK_CUDA(cudaMemcpyAsync(dst_x, src_x, bytes_x, cudaMemcpyHostToDevice, s->copy));
   if (dst_y && bytes_y > 0)
     PLK_CUDA(cudaMemcpyAsync(dst_y, src_y, bytes_y, cudaMemcpyHostToDevice, s->copy));
   PLK_CUDA(cudaEventRecord(s->ready[slot], s->copy));
+  s->ready_valid[slot] = 1;
   return PLK_OK;
 }
 

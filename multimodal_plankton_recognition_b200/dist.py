@@ -54,6 +54,19 @@ class XGpuScalars:
         dist.barrier(group=group)       # every rank's zero-fill is visible before anyone signals
 
 
+def xgpu_supported(image_emb, profile_emb) -> bool:
+    """The fused exchange lives in the VECTORISED loss / gradient-tail kernels: d % 128 == 0, d <= 1024 and
+    16-byte aligned fp32 rows (plk_infonce_grad_finish_pair_xgpu rejects anything else).  Every rank takes
+    the same decision from the same shapes; otherwise the two scalars go through NCCL all-reduces."""
+    d = image_emb.shape[1]
+    if d % 128 or d > 1024:
+        return False
+    for t in (image_emb, profile_emb):
+        if t.dtype == torch.float32 and t.stride(-1) == 1 and (t.stride(0) % 4 or t.data_ptr() % 16):
+            return False
+    return True
+
+
 def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduce_scalars=True, xgpu=None):
     """Forward of the row-block sharded loss without autograd: -> (global loss [], saved state).
     With reduce_scalars=False the returned loss is this rank's partial sum (the caller all-reduces
@@ -146,6 +159,8 @@ class _ShardedClipLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, image_emb, profile_emb, logit_scale, buckets, mode, group, grad_scale, xgpu):
+        if xgpu is not None and not xgpu_supported(image_emb, profile_emb):
+            xgpu = None          # same decision in the backward: it reads it from ctx.meta
         loss, state = sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, xgpu=xgpu)
         ctx.plk_state = state    # intermediates only (detached fp32 rows, opaque buffers): no graph edges
         ctx.meta = (grad_scale, image_emb.dtype, profile_emb.dtype, logit_scale.dtype, xgpu)

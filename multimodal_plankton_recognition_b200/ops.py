@@ -233,7 +233,10 @@ def clip_loss_bwd(grad_out: torch.Tensor, image_emb: torch.Tensor, profile_emb: 
     ls = logit_scale.detach().float()
     go = grad_out.detach().float().reshape(1).contiguous()
     idx, nx, idy, ny, rs, cs, dg = stats.unbind(0)
-    gs = aux[1:]              # zeroed by the forward; the gradient tail consumes it and re-zeroes it
+    # the kernels accumulate sum G*S into `gs` and reset it: work on a private copy so that this op mutates
+    # none of its (saved) inputs -- what `mutates_args=()` promises to the tracer and to autograd's
+    # version counters (a second backward over the same graph sees the forward's zero again)
+    gs = aux[1:].clone()
     acc_x, acc_y = infonce_grad_pair_local(u, v, v, u, mode, d, 0, bs, ls, rs, cs, cs, rs, gs)
     dx, dy, dls = infonce_grad_finish_pair(acc_x, acc_y, x, y, stats[0:2], stats[2:4], dg, rs, cs, ls, go, go, B,
                                            gs, aux[0:1])

@@ -87,11 +87,14 @@ class HostPairPrefetcher:
             slot = (torch.empty(hx.shape, device=self.device, dtype=hx.dtype),
                     torch.empty(hy.shape, device=self.device, dtype=hy.dtype))
             self._slots[s] = slot
-        self._hold[s] = (hx, hy)
+        # plk_stager_issue first waits (on the host) for the slot's previous copy: only then may the host
+        # tensors of that copy be dropped -- a tensor pinned on the fly or a DataLoader pin_memory batch goes
+        # back to the pinned pool when its last reference dies and could be rewritten under a queued DMA
         self._lib.check(self._lib.plk_stager_issue(self._h, s, slot[0].data_ptr(), hx.data_ptr(),
                                                    hx.numel() * hx.element_size(), slot[1].data_ptr(),
                                                    hy.data_ptr(), hy.numel() * hy.element_size()),
                         "plk_stager_issue")
+        self._hold[s] = (hx, hy)
         self._issued += 1
         return True
 

@@ -38,7 +38,7 @@ def _E(a, b, off, bs, ls):
     s = float(torch.exp(ls.double()))
     S = s * (a.double() @ b.double().T)
     m = _mask(a.shape[0], b.shape[0], off, bs)
-    return torch.where(m, torch.exp(S - s), torch.zeros_like(S)), S, s
+    return torch.where(m, torch.exp(S - s + 64.0), torch.zeros_like(S)), S, s   # kShiftK, csrc/common.cuh
 
 
 def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, ls, rs=None, cs=None, dg=None, sums_zeroed=False):
@@ -53,7 +53,7 @@ def infonce_fwd_local(u, v, mode, d, row_offset, bucket_size, ls, rs=None, cs=No
 
 def infonce_loss_local(rs, cs_own, dg, ls, batch_global, loss_out=None):
     s = float(torch.exp(ls.double()))
-    loss = ((2 * s + rs.double().log() + cs_own.double().log() - 2 * dg.double()).sum() / (2 * batch_global)).float()
+    loss = ((2 * (s - 64.0) + rs.double().log() + cs_own.double().log() - 2 * dg.double()).sum() / (2 * batch_global)).float()
     if loss_out is not None:
         loss_out.copy_(loss)
         loss = loss_out
@@ -77,7 +77,7 @@ def infonce_grad_finish(acc, x, partner, inv_den_x, nrm_x, inv_den_p, dg, rs_own
                         out_dtype):
     s = float(torch.exp(ls.double()))
     coef = float(go) * s / (2 * batch_global)
-    dterm = torch.exp(dg.double() - s) * (1 / rs_own.double() + 1 / cs_own.double()) - 2
+    dterm = torch.exp(dg.double() - s + 64.0) * (1 / rs_own.double() + 1 / cs_own.double()) - 2
     p = partner.double() * inv_den_p.double()[:, None]
     dU = coef * (acc.double().sum(0) + dterm[:, None] * p)
     u = x.double() * inv_den_x.double()[:, None]

@@ -128,6 +128,31 @@ def test_predict_multi_k_equals_one_search_per_k(precision):
         clf.predict_multi_k(img[te], ks=())
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "fp32"])
+def test_reference_driver_k_values_up_to_51(precision):
+    """K = (1, 3, 9, 15, 31, 51) of reference scripts/benchmark_raw.py:82 / benchmark_folds.py:70 on the DEFAULT
+    16-bit index: k > 26 is served by the fp32 candidate search (the tensor-core kernel keeps 32 candidates
+    per query), with the same exact re-score -- neighbours, distances and labels equal to the oracle."""
+    from multimodal_plankton_recognition_b200 import ANNClassifier, harness
+    gal, yg = _clustered(3000, 128, 27, 21)
+    q, _ = _clustered(400, 128, 27, 22, noise=1.1)
+    ora = oann.OracleANNClassifier(gal, yg)
+    clf = ANNClassifier(gal, yg, plk_precision=precision, **KW)
+    K = (1, 3, 9, 15, 31, 51)
+    for k in (26, 27, 31, 51, 58):
+        wi, wd = ora.kneighbors(q, k=k)[0]
+        gi, gd = clf.kneighbors(q, k=k, epsilon=.3)[0]
+        np.testing.assert_allclose(gd, wd, rtol=1e-6, atol=0)
+        mism = gi != wi
+        assert mism.mean() < 1e-3 and np.abs(gd[mism] - wd[mism]).max(initial=0) < 1e-6
+    got = clf.predict_multi_k(q, ks=K, epsilon=.3)
+    for k in K:
+        np.testing.assert_array_equal(got[k], ora.predict(q, k=k))
+    with pytest.raises(ValueError):
+        clf.kneighbors(q, k=59)
+    assert harness is not None
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("path", golden_files("bench_"), ids=os.path.basename)
 def test_benchmark_harness_matches_reference_drivers(path, precision):

@@ -2,13 +2,15 @@
 produced by the reference.  Tolerances from BASELINE.json: 1e-5 relative in fp32 mode, 2e-3 in
 bf16 mode.  "Relative" for a gradient tensor:
   fp32 mode: max-abs error / max-abs of the reference gradient  <= 1e-5
-  bf16 mode: max-abs error / max-abs AND ||got - ref||_2 / ||ref||_2, both <= 2e-3 * max(1, s/e).
-             Rounding the unit-norm operands (and the recomputed softmax weights) to bf16 perturbs
-             every logit by ~s * 1e-4, so the gradient error grows linearly with the temperature
-             s = exp(logit_scale); at the reference's initial logit_scale = 1 (s = e) -- the BASELINE
-             configuration -- the plain 2e-3 bound is asserted.  Measured: 3e-4 at s = e, 2.3e-3..3.0e-3
-             at s = 14.3 (logit_scale = 2.659).
-  fp16 mode: the same two metrics <= 2e-3 flat (fp16 has 3 more mantissa bits; measured ~4e-4 at s = 14.3)."""
+  fp16 mode: max-abs error / max-abs AND ||got - ref||_2 / ||ref||_2, both <= 2e-3 at every temperature.
+  bf16 mode: the same two metrics <= 2e-3 at the reference's temperature (logit_scale <= 1, the BASELINE
+             configuration; measured 3e-4) and <= BF16_TRAINED_BOUND = 3.2e-3 at the trained temperature
+             logit_scale = 2.659 (s = 14.3) -- a DECLARED DEVIATION from the flat 2e-3:
+             rounding the unit-norm operands of the similarity GEMM to 8 mantissa bits perturbs every logit
+             by ~s * 1e-4, which alone costs 2.3e-3..2.8e-3 there whatever the format of the recomputed
+             softmax weights (tools/bf16_error_budget.py emulates the path on the CPU: bf16 operands with
+             exact weights 2.8e-3, with fp16 weights 2.9e-3, fp16 operands 3.5e-4).  The bounds are
+             constants: no assertion scales with the temperature."""
 import math
 import os
 
@@ -21,6 +23,11 @@ from oracle import infonce as oinf
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-5, "bf16": 2e-3, "fp16": 2e-3}
+BF16_TRAINED_BOUND = 3.2e-3     # bf16 operands at logit_scale = 2.659: declared deviation, see the module docstring
+
+
+def grad_bound(precision, ls):
+    return BF16_TRAINED_BOUND if (precision == "bf16" and ls > 1.0) else TOL[precision]
 
 
 def _rel(a, b):
@@ -51,7 +58,7 @@ def _rel_l2(a, b):
 
 def _check(got, ref, tol, clamp_rows=None, ls=1.0, precision="bf16"):
     loss, dx, dy, dls = got
-    tol_max = tol * max(1.0, math.exp(ls) / math.e) if precision == "bf16" else tol   # fp16/fp32: flat bound
+    tol_max = grad_bound(precision, ls)
     assert abs(loss - ref["loss"]) / abs(ref["loss"]) < tol, ("loss", loss, ref["loss"])
     rx, ry = np.array(ref["d_image"]), np.array(ref["d_profile"])
     if clamp_rows is not None:  # rows below the eps clamp have 1/eps-scaled gradients: compare separately
@@ -97,6 +104,40 @@ def test_against_oracle(B, d, buckets, ls, precision):
     pro = (cent[lab] + 0.5 * z + 0.3 * r.standard_normal((B, d))).astype(np.float32)
     ref = oinf.clip_loss_closed_form(img, pro, ls, buckets)
     _check(_run(img, pro, ls, buckets, precision), ref, TOL[precision], ls=ls, precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("ls", [3.7, 4.6])
+def test_large_temperature(ls, precision):
+    """The reference never clamps logit_scale (src/coordination.py:23,:38) and F.cross_entropy is stable at any
+    temperature.  On unaligned rows (independent random modalities, d = 512) the best match of a row sits at
+    cos ~ 0.1, so at logit_scale = 4.6 (s = 99.5, CLIP's usual ceiling) s (1 - cos_max) reaches 89.6: a plain
+    shift by s flushes whole row sums to zero there; the range-centred shift (kShiftK, csrc/common.cuh) does
+    not.  fp32 and fp16 modes meet their flat bounds; for bf16 operands the logit perturbation s * 1e-4 is
+    no longer small, so only the loss bound and a coarse gradient bound are asserted (measured 6e-3)."""
+    r = np.random.default_rng(0)
+    B, d = 512, 512
+    img = r.standard_normal((B, d)).astype(np.float32)
+    pro = r.standard_normal((B, d)).astype(np.float32)
+    ref = oinf.clip_loss_closed_form(img, pro, ls, 1)
+    got = _run(img, pro, ls, 1, precision)
+    assert np.isfinite(got[0]) and np.isfinite(got[1]).all() and np.isfinite(got[2]).all()
+    if precision == "bf16":
+        assert abs(got[0] - ref["loss"]) / abs(ref["loss"]) < 2e-3
+        assert _rel(got[1], ref["d_image"]) < 1e-2 and _rel(got[2], ref["d_profile"]) < 1e-2
+    else:
+        _check(got, ref, TOL[precision], ls=ls, precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_out_of_range_temperature_is_loud(precision):
+    """Beyond the range of the fixed shift (s (1 - cos_max) > 151: here s = e^6.5 = 665 on unaligned rows) a
+    sum-exp underflows to zero; the loss must come back as NaN, never as a finite number or a silent inf."""
+    r = np.random.default_rng(1)
+    img = r.standard_normal((256, 128)).astype(np.float32)
+    pro = r.standard_normal((256, 128)).astype(np.float32)
+    got = _run(img, pro, 6.5, 1, precision)
+    assert np.isnan(got[0])
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

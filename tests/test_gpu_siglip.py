@@ -1,8 +1,9 @@
 """GPU parity of the SigLIP path through the C ABI (`SigLIPLoss` ->
 plk_siglip_loss_forward / plk_siglip_loss_backward) against the golden vectors produced by running the
 reference's own SigLIPLoss (tests/golden/siglip_*.npz) and against the fp64 oracle on seeded inputs.
-Tolerances: fp32 mode <= 1e-5 relative; bf16 / fp16 operand modes <= 2e-3 (bf16 scaled by the
-temperature like the InfoNCE tests: the operand rounding perturbs every logit by ~ s * 1e-3)."""
+Tolerances: fp32 mode <= 1e-5 relative; fp16 operands <= 2e-3; bf16 operands <= 2e-3 at logit_scale <= 1
+and <= BF16_TRAINED_BOUND at the trained temperature (declared deviation, same cause and same constant
+as in tests/test_gpu_loss.py: the operand rounding perturbs every logit by ~ s * 1e-4)."""
 import math
 import os
 
@@ -15,6 +16,7 @@ from oracle import siglip as osig
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-5, "bf16": 2e-3, "fp16": 2e-3}
+BF16_TRAINED_BOUND = 3.2e-3
 
 
 def _rel(a, b):
@@ -39,7 +41,7 @@ def _run(img, pro, ls, bias, buckets, precision, dtype=torch.float32, grad_out=N
 
 def _check(got, ref, precision, ls, clamp_rows=()):
     tol = TOL[precision]
-    tol_g = tol * max(1.0, math.exp(ls) / math.e) if precision == "bf16" else tol
+    tol_g = BF16_TRAINED_BOUND if (precision == "bf16" and ls > 1.0) else tol
     loss, dx, dy, dls, db = got
     assert abs(loss - ref["loss"]) <= tol_g * abs(ref["loss"]), ("loss", loss, ref["loss"])
     rx, ry = np.array(ref["d_image"]), np.array(ref["d_profile"])

@@ -39,7 +39,7 @@ def _fwd_case(B, d, buckets, mode_name):
     s = float(ls.exp())
     S = (uf.double() @ vf.double().T) * s
     mask = (torch.arange(B, device="cuda")[:, None] // bs) == (torch.arange(B, device="cuda")[None, :] // bs)
-    E = torch.where(mask, torch.exp(S - s), torch.zeros_like(S))
+    E = torch.where(mask, torch.exp(S - s + 64.0), torch.zeros_like(S))   # kShiftK (csrc/common.cuh)
     err = lambda a, b: float(((a.double() - b).abs() / b.abs().clamp_min(1e-30)).max())
     print(f"fwd[{mode_name}] B={B} d={d} bk={buckets}: rs {err(rs, E.sum(1)):.2e} cs {err(cs, E.sum(0)):.2e} "
           f"diag {float((dg.double() - S.diagonal()).abs().max()):.2e}", flush=True)

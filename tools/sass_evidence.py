@@ -1,6 +1,6 @@
 """Count the Blackwell-specific SASS mnemonics per kernel of libplk.so (cuobjdump -sass): UTC*MMA =
 tcgen05.mma, LDTM / STTM = tcgen05.ld / .st, UTMALDG / UTMASTG = TMA loads / stores, HMMA = legacy
-mma.sync (must be absent).  usage: python tools/sass_evidence.py > profiles/r1_sass_evidence.txt"""
+mma.sync (must be absent).  usage: python tools/sass_evidence.py > profiles/r2_sass_evidence.txt"""
 import collections
 import os
 import re
@@ -21,7 +21,7 @@ for line in out.splitlines():
         continue
     if kern is None:
         continue
-    m = re.search(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.search(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m:
         op = m.group(1)
         counts[kern]["_total"] += 1
