@@ -271,38 +271,40 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
-      mbar_wait(bar_a, 0);     // the epilogue warps have parked the owned rows in TMEM (columns 256..)
+    // All 32 lanes run this loop (warp-uniform control flow, see elect_one); one elected lane issues.
+    const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
+    mbar_wait(bar_a, 0);     // the epilogue warps have parked the owned rows in TMEM (columns 256..)
+    tc_fence_after();
+    if (lane == 0) TR(3);
+    const uint32_t a_tmem0 = tmem_base + 256;
+    const uint32_t b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
+    int st = 0; uint32_t ph = 0;
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
       tc_fence_after();
-      TR(3);
-      const uint32_t a_tmem0 = tmem_base + 256;
-      const uint32_t b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
-      int st = 0; uint32_t ph = 0;
-      for (int t = 0; t < T; ++t) {
-        const int buf = t & 1;
-        mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
+      const uint32_t d_tmem = tmem_base + buf * 128;
+#pragma unroll 1
+      for (int c = 0; c < KD; c += CPS) {
+        mbar_wait(bar_full + st, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 128;
-        for (int c = 0; c < KD; c += CPS) {
-          mbar_wait(bar_full + st, ph);
-          tc_fence_after();
-          const uint32_t b_lo = b_lo0 + st * (Cfg::kStageBytes >> 4);
+        const uint32_t b_lo = b_lo0 + st * (Cfg::kStageBytes >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int cs = 0; cs < CPS; ++cs)
 #pragma unroll
             for (int k = 0; k < kChunkK / kUmmaK; ++k)   // A: 8 packed TMEM columns per K step; B: 32 bytes
               umma_bf16_ts(d_tmem, a_tmem0 + (c + cs) * 32 + k * 8, b_lo + cs * (kChunkBytes >> 4) + 2 * k, idesc,
                            (c | cs | k) != 0);
-          if (t == 0 && c == 0) TR(4);
           ring_release<CS>(bar_empty + st);
-          if (++st == NST) { st = 0; ph ^= 1; }
+          if (c + CPS >= KD) umma_commit(bar_sfull + buf);
         }
-        umma_commit(bar_sfull + buf);
-        if (t < 16) TR(64 + t);
+        __syncwarp();
+        if (lane == 0 && t == 0 && c == 0) TR(4);
+        if (++st == NST) { st = 0; ph ^= 1; }
       }
+      if (lane == 0 && t < 16) TR(64 + t);
     }
-    __syncwarp();
   } else {
     // ---------------- epilogue: 16 warps, thread = one logit row x 32 columns ----------------
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
@@ -564,42 +566,49 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
-      constexpr uint32_t idesc_g = umma_idesc_16(128, 64, 0, 1, F16);  // B = streamed chunk, MN-major
-      mbar_wait(bar_a, 0);
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
-      int st = 0; uint32_t ph = 0;
-      const uint32_t g_lo0 = umma_desc_lo(smem_u32(sm_g), 16);
-      const uint32_t b2_lo0 = umma_desc_lo(smem_u32(sm_ring), kChunkBytes);
-      for (int t = 0; t <= T; ++t) {
-        if (t < T) {
-          const int buf = t & 1;
-          mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
+    // All 32 lanes run this loop (warp-uniform control flow, see elect_one); one elected lane issues.
+    constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
+    constexpr uint32_t idesc_g = umma_idesc_16(128, 64, 0, 1, F16);  // B = streamed chunk, MN-major
+    mbar_wait(bar_a, 0);
+    tc_fence_after();
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
+    int st = 0; uint32_t ph = 0;
+    const uint32_t g_lo0 = umma_desc_lo(smem_u32(sm_g), 16);
+    const uint32_t b2_lo0 = umma_desc_lo(smem_u32(sm_ring), kChunkBytes);
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        const int buf = t & 1;
+        mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * 128;
+#pragma unroll 1
+        for (int c = 0; c < KD; ++c) {
+          mbar_wait(bar_full + st, ph);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * 128;
-          for (int c = 0; c < KD; ++c) {
-            mbar_wait(bar_full + st, ph);
-            tc_fence_after();
-            const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
-            const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
+          const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
+          const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kChunkK / kUmmaK; ++k)
               umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
             ring_release<CS>(bar_empty + st);
-            if (++st == NST) { st = 0; ph ^= 1; }
+            if (c == KD - 1) umma_commit(bar_sfull + buf);
           }
-          umma_commit(bar_sfull + buf);
+          __syncwarp();
+          if (++st == NST) { st = 0; ph ^= 1; }
         }
-        if (t >= 1) {
-          const int u = t - 1;
-          mbar_wait(bar_gfull, u & 1);
+      }
+      if (t >= 1) {
+        const int u = t - 1;
+        mbar_wait(bar_gfull, u & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int dc = 0; dc < DNC; ++dc) {
+          mbar_wait(bar_full + st, ph);
           tc_fence_after();
-          for (int dc = 0; dc < DNC; ++dc) {
-            mbar_wait(bar_full + st, ph);
-            tc_fence_after();
-            const uint32_t b_lo = b2_lo0 + st * (kChunkBytes >> 4);
-            const uint32_t d_tmem = tmem_base + kAccCol + dc * 64;
+          const uint32_t b_lo = b2_lo0 + st * (kChunkBytes >> 4);
+          const uint32_t d_tmem = tmem_base + kAccCol + dc * 64;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kTileRows / kUmmaK; ++k) {
               // A = G[128 x 128] K-major: K 0..63 in sub-tile 0, 64..127 in sub-tile 1
@@ -608,13 +617,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
                            idesc_g, (u | k) != 0);
             }
             ring_release<CS>(bar_empty + st);
-            if (++st == NST) { st = 0; ph ^= 1; }
+            if (dc == DNC - 1) umma_commit(bar_gempty);
           }
-          umma_commit(bar_gempty);
+          __syncwarp();
+          if (++st == NST) { st = 0; ph ^= 1; }
         }
       }
-      umma_commit(bar_accfull);
     }
+    if (elect_one()) umma_commit(bar_accfull);
     __syncwarp();
   } else {
     const int q = warp & 3;
@@ -811,27 +821,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
-      constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A from TMEM (K-major), B MN-major
-      mbar_wait(bar_a, 0);
-      TR(3);
-      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
-      const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);               // K-major view (S)
-      const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), kChunkBytes);     // MN-major view (G.V), LBO = chunk
-      // Issue order: S(0) S(1) | GV(0) GV(1) S(2) S(3) | GV(2) GV(3) S(4) S(5) | ...
-      // Tile buffer t&1 is released when GV(t) retires; issuing the two GVs back to back lets the
-      // TMA refill of buffer 0 (~1000 cycles) overlap GV(2p+1) and the refill of buffer 1 overlap
-      // S(2p+2), instead of stalling the in-order issue stream once per tile.
-      for (int t0 = 0; t0 < T + 2; t0 += 2) {
+    // All 32 lanes run this loop (warp-uniform control flow, see elect_one); one elected lane issues.
+    constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
+    constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A from TMEM (K-major), B MN-major
+    mbar_wait(bar_a, 0);
+    tc_fence_after();
+    if (lane == 0) TR(3);
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16);
+    const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);               // K-major view (S)
+    const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), kChunkBytes);     // MN-major view (G.V), LBO = chunk
+    // Issue order: S(0) S(1) | GV(0) GV(1) S(2) S(3) | GV(2) GV(3) S(4) S(5) | ...
+    // Tile buffer t&1 is released when GV(t) retires; issuing the two GVs back to back lets the
+    // TMA refill of buffer 0 (~1000 cycles) overlap GV(2p+1) and the refill of buffer 1 overlap
+    // S(2p+2), instead of stalling the in-order issue stream once per tile.
+    for (int t0 = 0; t0 < T + 2; t0 += 2) {
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {          // GV of the previous pair
-          const int u = t0 - 2 + h2;
-          if (u < 0 || u >= T) continue;
-          const int b = u & 1;
-          mbar_wait(bar_gfull + b, (u >> 1) & 1);
-          tc_fence_after();
-          const uint32_t b_lo = y2_lo0 + b * KD * (kChunkBytes >> 4);
+      for (int h2 = 0; h2 < 2; ++h2) {          // GV of the previous pair
+        const int u = t0 - 2 + h2;
+        if (u < 0 || u >= T) continue;
+        const int b = u & 1;
+        mbar_wait(bar_gfull + b, (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t b_lo = y2_lo0 + b * KD * (kChunkBytes >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < kTileRows / kUmmaK; ++k) {
             // A: packed G, K elements 32c..32c+31 live in columns 32c .. 32c+15 of logits buffer b
@@ -839,16 +851,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
             umma_bf16_ts(tmem_base + kAccCol, a_tmem, b_lo + k * (2048 >> 4), idesc_g, (u | k) != 0);
           }
           ring_release<CS>(bar_yempty + b);   // tile buffer b (and logits buffer b) free once these retire
-          if (u < 16) TR(112 + u);
         }
+        __syncwarp();
+        if (lane == 0 && u < 16) TR(112 + u);
+      }
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {          // S of this pair
-          const int t = t0 + h2;
-          if (t >= T) continue;
-          const int b = t & 1;
-          mbar_wait(bar_yfull + b, (t >> 1) & 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + b * 128;
+      for (int h2 = 0; h2 < 2; ++h2) {          // S of this pair
+        const int t = t0 + h2;
+        if (t >= T) continue;
+        const int b = t & 1;
+        mbar_wait(bar_yfull + b, (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + b * 128;
+        if (elect_one()) {
 #pragma unroll
           for (int c = 0; c < KD; ++c) {
             const uint32_t a_lo = a_lo0 + c * (kChunkBytes >> 4);
@@ -858,11 +873,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
               umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, (c | k) != 0);
           }
           umma_commit(bar_sfull + b);
-          if (t < 16) TR(64 + t);
         }
+        __syncwarp();
+        if (lane == 0 && t < 16) TR(64 + t);
       }
-      umma_commit(bar_accfull);
     }
+    if (elect_one()) umma_commit(bar_accfull);
     __syncwarp();
   } else {
     const int q = warp & 3;
@@ -989,6 +1005,335 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
   __syncthreads();
   if (threadIdx.x == 0) TR(5);
   if constexpr (CS > 1) cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+  if (threadIdx.x == 0) TR(6);
+}
+
+
+// =============================================================================================
+// backward, d <= 256, BOTH GEMMs with the A operand in tensor memory (TS mode).
+//
+// infonce_grad_tc2 above reads the owned rows from shared memory for S = a . b_t^T: an SS-mode
+// 128x128x16 MMA pulls 8 KiB of operands per 64 cycles -- all of the 128 B/clk a shared memory delivers --
+// and the TMA refill of the tile buffers comes on top, so a 128-column tile took 3100 cycles for 2048 cycles
+// of tensor work.  Here the owned rows are parked in TMEM once (as in the forward) and the logits are
+// produced 64 columns at a time, which is what makes everything fit in the 512 TMEM columns:
+//     [0, 64)     S        fp32 logits of the current 64-column tile            (one buffer)
+//     [64, 128)   G ring   2 x 32 columns: packed 16-bit weights of tiles t, t+1 (A operand of G . b_t)
+//     [128, 256)  A        owned rows, packed 16-bit pairs, KD x 32 columns
+//     [256, 512)  acc      [128 x d] fp32, resident for the whole sweep
+// Shared memory only holds streamed tiles ([64 x d] 16-bit, a ring of six) and is read at 64 B/clk by either
+// MMA (+ 32 B/clk of TMA refill).  Issue order S(0) | S(1) GV(0) | S(2) GV(1) | ... on the in-order tensor
+// pipe: the epilogue of tile t (tcgen05.ld, one exp per logit, tcgen05.st of G) has the whole of GV(t-1) and
+// S(t+1) -- 1024 cycles -- before GV(t) needs its result, and it releases the single S buffer right after its
+// tcgen05.ld, long before S(t+1) is due.  The sixteen epilogue warps form two groups that take alternate tiles
+// (8 warps = 4 lane quadrants x 2 chunks of 32 columns), so a warp has two tile periods for one chunk.
+// G ring slot t&1 is rewritten by the same group two tiles later, after S(t+2) -- issued behind GV(t) -- has
+// completed: no extra barrier.  A tile slot is released by the commit that follows GV(t).  No cluster /
+// multicast here: at 32 B/clk per SM the streamed tiles use half of the L2 bandwidth, and pairing row blocks
+// measured as neutral in infonce_grad_tc2.
+// =============================================================================================
+constexpr int kG3Slots = 6;
+constexpr int kG3Cols = 64;                     // logits columns per tile
+constexpr int kG3ChunkBytes = kChunkBytes / 2;  // [64 x 64] 16-bit = 8 KiB
+template <int KD>
+struct Grad3Cfg {
+  static constexpr int kSlotBytes = KD * kG3ChunkBytes;
+  static constexpr int kRing = kG3Slots * kSlotBytes;
+  static constexpr int kSmem = 1024 + kRing + kAuxBytes;
+  static constexpr int kAStage = (kG3Slots - 2) * kSlotBytes;   // owned rows (KD x 16 KiB) arrive in the last two slots
+  static_assert(kSmem <= kMaxSmem, "ring too large");
+  static_assert(4 * kSlotBytes >= kTileRows * KD * 64 * 4, "accumulator drain is staged in four slots");
+};
+
+template <int KD, bool F16, bool SIG>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc3(
+    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+    int64_t d, int64_t bs, int tiles_per_seg, const float* __restrict__ ls) {
+  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
+  using Cfg = Grad3Cfg<KD>;
+  constexpr int NSL = kG3Slots;
+  constexpr int DN = KD * 64;  // accumulator columns = padded d
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_ring = smem;
+  uint8_t* aux = sm_ring + Cfg::kRing;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);   // [NSL] tile landed
+  uint64_t* bar_empty = bar_full + NSL;                     // [NSL] tile consumed by S and G.V
+  uint64_t* bar_afull = bar_empty + NSL;                    // [1] owned rows landed in their staging slots
+  uint64_t* bar_a = bar_afull + 1;                          // [1] owned rows parked in TMEM
+  // One barrier per epilogue group (= tile parity) for each hand-over: a parity wait only tells "the phase
+  // before the current one is complete", so two groups waiting on ONE barrier for alternate completions
+  // would see each other's phases.
+  uint64_t* bar_sfull = bar_a + 1;                          // [2] logits tile t complete            (index t&1)
+  uint64_t* bar_sempty = bar_sfull + 2;                     // [2] logits tile t read by its group    (index t&1)
+  uint64_t* bar_gfull = bar_sempty + 2;                     // [2] packed weights of tile t in ring slot t&1
+  uint64_t* bar_accfull = bar_gfull + 2;                    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
+  float* rcs_s = reinterpret_cast<float*>(aux + 512);       // [2 groups][2 buffers][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
+  int64_t jlo = 0, jhi = n_cols;
+  row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const int total_tiles = (int)((jhi - jlo + kG3Cols - 1) / kG3Cols);
+  const int t_begin = blockIdx.x * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;
+  float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
+  if (T == 0) {
+    griddep_wait();   // global writes only after the kernel queued before this one is done
+    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DN; e += kNumThreads) {
+      const int64_t rr = i0 + e / DN, col = e % DN;
+      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) TR(0);
+  pdl_trigger();   // the gradient-tail kernel may become resident; it waits for this grid's completion
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.ta);
+    tma_prefetch_desc(&g.tbp);
+    for (int s = 0; s < NSL; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_a, kEpiThreads);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_sfull + b, 1);
+      mbar_init(bar_sempty + b, kEpiThreads / 64);      // one elected arrival per warp of the tile's group
+      mbar_init(bar_gfull + b, kEpiThreads / 64);
+    }
+    mbar_init(bar_accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kSCol = 0, kGCol = 64, kACol = 128, kAccCol = 256;
+  if (threadIdx.x == 0) TR(1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_afull, KD * kChunkBytes);
+      for (int c = 0; c < KD; ++c)
+        tma_load_2d(sm_ring + Cfg::kAStage + c * kChunkBytes, &g.ta, bar_afull, c * kChunkK, (int)i0);
+      bool a_parked = false;
+      int st = 0; uint32_t ph = 0;
+      for (int t = 0; t < T; ++t) {
+        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kG3Cols);
+        if (!a_parked && st >= NSL - 2) {   // first use of a slot that overlaps the staged owned rows
+          mbar_wait(bar_a, 0);
+          a_parked = true;
+        }
+        mbar_wait(bar_empty + st, ph ^ 1);
+        mbar_expect_tx(bar_full + st, Cfg::kSlotBytes);
+        uint8_t* slot = sm_ring + st * Cfg::kSlotBytes;
+#pragma unroll
+        for (int c = 0; c < KD; ++c)   // g.tbp: boxes of 64 rows
+          tma_load_2d(slot + c * kG3ChunkBytes, &g.tbp, bar_full + st, c * kChunkK, j0);
+        if (++st == NSL) { st = 0; ph ^= 1; }
+        if (t < 16) TR(48 + t);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // All 32 lanes run this loop (warp-uniform control flow, see elect_one); one elected lane issues.
+    constexpr uint32_t idesc_s = umma_idesc_16(128, kG3Cols, 0, 0, F16);
+    constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A from TMEM (K-major), B MN-major
+    mbar_wait(bar_a, 0);     // the epilogue warps have parked the owned rows in TMEM
+    tc_fence_after();
+    if (lane == 0) TR(3);
+    const uint32_t s_tmem = tmem_base + kSCol, a_tmem0 = tmem_base + kACol, acc_tmem = tmem_base + kAccCol;
+    const uint32_t k_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);              // K-major view (S)
+    const uint32_t mn_lo0 = umma_desc_lo(smem_u32(sm_ring), kG3ChunkBytes);  // MN-major view (G.V): LBO = chunk
+    int st = 0; uint32_t ph = 0;   // slot of tile t (S side)
+    int st_g = 0;                  // slot of tile t-1 (G.V side)
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        mbar_wait(bar_full + st, ph);
+        if (t >= 1) mbar_wait(bar_sempty + ((t - 1) & 1), ((t - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t b_lo = k_lo0 + st * (Cfg::kSlotBytes >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < KD; ++c)
+#pragma unroll
+            for (int k = 0; k < kChunkK / kUmmaK; ++k)
+              umma_bf16_ts(s_tmem, a_tmem0 + c * 32 + k * 8, b_lo + c * (kG3ChunkBytes >> 4) + 2 * k, idesc_s,
+                           (c | k) != 0);
+          umma_commit(bar_sfull + (t & 1));
+        }
+        __syncwarp();
+        if (lane == 0 && t < 16) TR(64 + t);
+        if (++st == NSL) { st = 0; ph ^= 1; }
+      }
+      if (t >= 1) {
+        const int u = t - 1;
+        mbar_wait(bar_gfull + (u & 1), (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t b_lo = mn_lo0 + st_g * (Cfg::kSlotBytes >> 4);
+        const uint32_t g_tmem = tmem_base + kGCol + (u & 1) * 32;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kG3Cols / kUmmaK; ++k)   // A: 8 packed columns per K step; B: 16 tile rows = 2 KiB
+            umma_bf16_ts(acc_tmem, g_tmem + k * 8, b_lo + k * (2048 >> 4), idesc_g, (u | k) != 0);
+          umma_commit(bar_empty + st_g);   // the tile slot is free once S(u) and G.V(u) have retired
+        }
+        __syncwarp();
+        if (lane == 0 && u < 16) TR(112 + u);
+        if (++st_g == NSL) st_g = 0;
+      }
+    }
+    if (elect_one()) umma_commit(bar_accfull);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int e = (warp - 2) >> 2;           // 0..3
+    const int grp = e >> 1;                  // tiles t = grp (mod 2)
+    const int cc = e & 1;                    // which 32-column chunk of the 64-column tile
+    const int r = q * 32 + lane;
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    float rrs = 0.f;
+    constexpr bool siglip = SIG;
+    if (i < n_rows) {
+      bucket_range(gi, bs, n_cols, lo, hi);
+      if (!siglip) rrs = 1.0f / g.rs[i];
+    }
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : (kShiftK - s) * kLog2e;
+    const bool want_gs = g.gs != nullptr;
+    float gs_local = 0.f, gsum_local = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    {  // park this thread's owned row (16-bit operand, padded to KD*64) in TMEM as packed pairs: the A operand
+       // of S.  Source: the swizzled staging slots (rows past n_rows were zero-filled by the TMA unit).
+      mbar_wait(bar_afull, 0);
+      for (int c = e; c < KD; c += 4) {
+        const uint8_t* rowp = sm_ring + Cfg::kAStage + c * kChunkBytes + r * 128;
+        uint32_t pk[32];
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) {
+          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
+        }
+        tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+      if (threadIdx.x == 64) TR(2);
+    }
+    // 1/cs of the group's NEXT tile is fetched one tile ahead and parked in the other buffer of rcs_s
+    const bool filler = (cc == 0) && (q < 2);          // 64 threads per group: one per tile column
+    float* rcs_g = rcs_s + grp * 128;
+    float rc_next = 0.f;
+    if (filler && !siglip && grp < T) {
+      const int64_t jc = jlo + (int64_t)(t_begin + grp) * kG3Cols + r;
+      rcs_g[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+    }
+    for (int t = grp; t < T; t += 2) {
+      const int it = t >> 1;                           // tile ordinal inside the group
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kG3Cols;
+      named_barrier_sync(1 + grp, kEpiThreads / 2);    // rcs of this tile visible; the group is done with tile t-2
+      if (filler && !siglip && t + 2 < T) {
+        const int64_t jc = j0 + 2 * kG3Cols + r;
+        rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
+      }
+      mbar_wait(bar_sfull + grp, it & 1);
+      tc_fence_after();
+      if (threadIdx.x == 64 && t < 16) TR(80 + t);
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + kSCol + cc * 32, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sempty + grp);    // the logits buffer goes back to the MMA warp right away
+      uint32_t packed[16];
+      grad_chunk_dispatch<F16>(raw, packed, rcs_g + (it & 1) * 64 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
+                               want_gs, gs_local, siglip, gsum_local);
+      tmem_st16(tmem_base + lane_addr + kGCol + (t & 1) * 32 + cc * 16, packed);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_gfull + grp);
+      if (threadIdx.x == 64 && t < 16) TR(96 + t);
+      if (filler && !siglip && t + 2 < T) rcs_g[((it + 1) & 1) * 64 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+    }
+    mbar_wait(bar_accfull, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) TR(2);
+    // With an overlapped launch everything above only read what the forward left behind; global writes
+    // start here, after the kernel queued before this one has completed.
+    griddep_wait();
+    if (g.use_tacc) {
+      // Drain through shared memory + TMA stores (see infonce_grad_tc2): 128-byte swizzled rows staged in the
+      // idle tile slots, one bulk store of full lines per 32-column chunk.
+#pragma unroll 1
+      for (int ch = e; ch < 2 * KD; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        uint8_t* stage = sm_ring + ch * kChunkBytes;     // 128 rows x 128 B
+        uint8_t* rowp = stage + r * 128;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
+              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+        fence_proxy_async_smem();
+        named_barrier_sync(3 + e, 128);
+        if (q == 0 && lane == 0 && i0 < n_rows) {
+          tma_store_3d(&g.tacc, stage, ch * 32, (int)i0, (int)blockIdx.x);
+          tma_store_commit();
+        }
+      }
+      if (q == 0 && lane == 0) tma_store_wait_all();
+    } else {
+#pragma unroll 1
+      for (int ch = e; ch < 2 * KD; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        const int64_t col0 = (int64_t)ch * 32;
+        if (i < n_rows) {
+          float* dst = acc_out + i * d + col0;
+          if (col0 + 32 <= d && (d & 3) == 0) {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4)
+              *reinterpret_cast<float4*>(dst + x) =
+                  make_float4(__uint_as_float(raw[x]), __uint_as_float(raw[x + 1]),
+                              __uint_as_float(raw[x + 2]), __uint_as_float(raw[x + 3]));
+          } else {
+#pragma unroll
+            for (int x = 0; x < 32; ++x)
+              if (col0 + x < d) dst[x] = __uint_as_float(raw[x]);
+          }
+        }
+      }
+    }
+    if (want_gs) {
+      gs_local *= s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+        gsum_local += __shfl_xor_sync(0xffffffffu, gsum_local, o);
+      }
+      if (lane == 0) {
+        atomicAdd(g.gs, gs_local);   // zeroed by the forward's last kernel (waited for above)
+        if (siglip) atomicAdd(g.gs + 1, gsum_local);
+      }
+    }
+  }
+  griddep_wait();   // no thread block outlives the kernel queued before it (see launch_kernel_ex)
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) TR(5);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -1133,12 +1478,44 @@ static int launch_grad2(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
              : launch_grad2_m<KD, CS, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
 }
 
+template <int KD, bool F16, bool SIG>
+static int launch_grad3_m(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                          int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  auto kern = infonce_grad_tc3<KD, F16, SIG>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad3Cfg<KD>::kSmem));
+    configured = true;
+  }
+  int rc = launch_kernel_ex(kern, grid, dim3(kNumThreads), Grad3Cfg<KD>::kSmem, st, 1, overlap_prev, ga, n_rows,
+                            row_offset, n_cols, d, bs, tps, ls);
+  if (rc) return rc;
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+template <int KD, bool F16>
+static int launch_grad3(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  return ga.bias != nullptr
+             ? launch_grad3_m<KD, F16, true>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev)
+             : launch_grad3_m<KD, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
+}
+
+// PLK_GRAD_TC2=1 selects the previous d <= 256 backward (owned rows read from shared memory, 128-column
+// tiles) for A/B measurements; the default is infonce_grad_tc3.
+static bool use_grad_tc2() {
+  static const bool v = getenv("PLK_GRAD_TC2") != nullptr && getenv("PLK_GRAD_TC2")[0] == '1';
+  return v;
+}
+// logits columns per tile of the backward that serves a padded width of kd 64-element chunks
+static int grad_tile_cols(int kd) { return (kd <= 4 && !use_grad_tc2()) ? kG3Cols : kTileRows; }
+
 // number of partial accumulators per direction for this shape (bf16 path); ndir = 1 or 2 directions per launch
 int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir) {
   const int64_t ld = ceil_div(d, kChunkK) * kChunkK;
   const int z = (ld > 256 ? 2 : 1) * ndir;
   const int64_t row_blocks = ceil_div(n_rows, kTileRows);
-  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
+  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols((int)(ld / kChunkK)));
   return pick_segments(row_blocks, max_tiles, z);
 }
 
@@ -1161,12 +1538,10 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
   const int csz = pick_cluster(row_blocks, bs, n_cols);
   const int kd = (int)(ld / kChunkK);
   const int z = (kd > 4 ? 2 : 1) * ga.ndir;
-  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), kTileRows);
+  const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols(kd));
   const int nseg = pick_segments(row_blocks, max_tiles, z);
   const int tps = (int)ceil_div(max_tiles, nseg);
-  row_blocks = ceil_div(row_blocks, csz) * csz;
-  dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
-  if (kd <= 4) {   // the streamed tile fits next to the resident rows: tile-buffer kernel, G in TMEM
+  if (kd <= 4) {   // d <= 256: the whole [128 x d] accumulator is TMEM-resident, G never leaves tensor memory
     if (d % 32 == 0) {   // accumulator drain by TMA store (full 128-byte lines)
       for (int k = 0; k < ga.ndir; ++k) {
         if (((uintptr_t)ga.dir[k].acc & 15) != 0) continue;
@@ -1176,6 +1551,19 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
       }
       if (ga.ndir == 1) ga.dir[1] = ga.dir[0];
     }
+    if (!use_grad_tc2()) {   // both GEMMs in TS mode, 64-column tiles, no clusters
+      dim3 grid3((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
+      switch (kd) {
+#define PLK_CASE3(KD) \
+  case KD: return launch_grad3<KD, F16>(ga, grid3, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
+        PLK_CASE3(1) PLK_CASE3(2) PLK_CASE3(3) PLK_CASE3(4)
+#undef PLK_CASE3
+      }
+    }
+  }
+  row_blocks = ceil_div(row_blocks, csz) * csz;
+  dim3 grid((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
+  if (kd <= 4) {
     switch (kd) {
 #define PLK_CASE2(KD)                                                                                   \
   case KD:                                                                                              \

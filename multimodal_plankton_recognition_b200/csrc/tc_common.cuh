@@ -122,6 +122,23 @@ __device__ __forceinline__ void cluster_sync_all() {  // every thread of every C
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  The MMA-issuing warps run their loops with all 32 lanes
+// and predicate only the tcgen05 instructions on this: inside `if (lane == 0) { loop }` the control flow
+// is divergent, ptxas keeps every descriptor in per-lane registers and moves it to the uniform
+// registers the instruction needs through an elect / R2UR.BROADCAST / branch sequence -- ~12 SASS
+// instructions and ~95 cycles per tcgen05.mma, more than the 64 (32) cycles a 128x128x16 (128x64x16)
+// MMA occupies the tensor pipe.  In warp-uniform control flow the address arithmetic stays on the
+// uniform datapath.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // TMEM + tcgen05
 // ------------------------------------------------------------------------------------------

@@ -121,22 +121,24 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
-      mbar_wait(bar_a, 0);     // the epilogue warps have parked the query rows in TMEM
+    // All 32 lanes run this loop (warp-uniform control flow, see elect_one); one elected lane issues.
+    const uint32_t idesc = umma_idesc_16(128, 128, 0, 0, f16);
+    mbar_wait(bar_a, 0);     // the epilogue warps have parked the query rows in TMEM
+    tc_fence_after();
+    const uint32_t a_tmem0 = tmem_base + 256;
+    const uint32_t b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
+    int st = 0; uint32_t ph = 0;
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t a_tmem0 = tmem_base + 256;
-      const uint32_t b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
-      int st = 0; uint32_t ph = 0;
-      for (int t = 0; t < T; ++t) {
-        const int buf = t & 1;
-        mbar_wait(bar_sempty + buf, ((t >> 1) & 1) ^ 1);
+      const uint32_t d_tmem = tmem_base + buf * 128;
+#pragma unroll 1
+      for (int c = 0; c < KD; c += CPS) {
+        mbar_wait(bar_full + st, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 128;
-        for (int c = 0; c < KD; c += CPS) {
-          mbar_wait(bar_full + st, ph);
-          tc_fence_after();
-          const uint32_t b_lo = b_lo0 + st * (Cfg::kStageBytes >> 4);
+        const uint32_t b_lo = b_lo0 + st * (Cfg::kStageBytes >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int cs = 0; cs < CPS; ++cs)
 #pragma unroll
@@ -144,12 +146,12 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
               umma_bf16_ts(d_tmem, a_tmem0 + (c + cs) * 32 + k * 8, b_lo + cs * (kChunkBytes >> 4) + 2 * k, idesc,
                            (c | cs | k) != 0);
           ring_release<CS>(bar_empty + st);
-          if (++st == NST) { st = 0; ph ^= 1; }
+          if (c + CPS >= KD) umma_commit(bar_sfull + buf);
         }
-        umma_commit(bar_sfull + buf);
+        __syncwarp();
+        if (++st == NST) { st = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;

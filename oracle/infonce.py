@@ -117,3 +117,41 @@ def clip_loss_materialised(image_emb, profile_emb, logit_scale, buckets=1):
     fwd = torch.stack([F.cross_entropy(lg, target) for lg in logits]).mean()
     rev = torch.stack([F.cross_entropy(lg.T, target) for lg in logits]).mean()
     return (fwd + rev) / 2
+
+
+def clip_loss_grads_rounded_operands(image_emb, profile_emb, logit_scale=1.0, buckets=1, op_fmt="bf16",
+                                     g_fmt="bf16"):
+    """Floor of a 16-bit tensor-core evaluation of the same gradients: the closed form above with (a) the
+    normalised operands of the similarity GEMM and (b) the softmax weights G (diagonal excluded) rounded to
+    `op_fmt` / `g_fmt` ("bf16", "fp16" or "f64" = not rounded); sums, exponentials, the diagonal term and
+    the normalisation backward stay in fp64.  What it returns is the error a kernel with that operand
+    format cannot go below -- tests use it to show that the bf16-mode deviation is the format's, not the
+    kernel's (tests/test_oracle_golden.py, tools/bf16_error_budget.py).  -> (d_image, d_profile)"""
+    import torch
+
+    def rnd(t, fmt):
+        if fmt == "f64":
+            return t
+        return t.float().to({"bf16": torch.bfloat16, "fp16": torch.float16}[fmt]).double()
+
+    x, y = torch.tensor(np.asarray(image_emb)).double(), torch.tensor(np.asarray(profile_emb)).double()
+    B = x.shape[0]
+    bs = B // buckets
+    nx, ny = x.norm(dim=1).clamp_min(EPS), y.norm(dim=1).clamp_min(EPS)
+    u, v = x / nx[:, None], y / ny[:, None]
+    ub, vb = rnd(u, op_fmt), rnd(v, op_fmt)
+    s = float(np.exp(logit_scale))
+    S = s * (ub @ vb.T)
+    mask = (torch.arange(B)[:, None] // bs) == (torch.arange(B)[None, :] // bs)
+    S = torch.where(mask, S, torch.full_like(S, -float("inf")))
+    G = torch.softmax(S, dim=1) + torch.softmax(S, dim=0)
+    Gd = torch.diagonal(G).clone()
+    G.fill_diagonal_(0)
+    Gb = rnd(G, g_fmt)
+    coef = s / (2 * B)
+    dU = coef * (Gb @ vb + (Gd - 2)[:, None] * v)
+    dV = coef * (Gb.T @ ub + (Gd - 2)[:, None] * u)
+    dx = (dU - u * (u * dU).sum(1, keepdim=True)) / nx[:, None]
+    dy = (dV - v * (v * dV).sum(1, keepdim=True)) / ny[:, None]
+    return dx.numpy(), dy.numpy()
+

@@ -4,13 +4,15 @@ bf16 mode.  "Relative" for a gradient tensor:
   fp32 mode: max-abs error / max-abs of the reference gradient  <= 1e-5
   fp16 mode: max-abs error / max-abs AND ||got - ref||_2 / ||ref||_2, both <= 2e-3 at every temperature.
   bf16 mode: the same two metrics <= 2e-3 at the reference's temperature (logit_scale <= 1, the BASELINE
-             configuration; measured 3e-4) and <= BF16_TRAINED_BOUND = 3.2e-3 at the trained temperature
+             configuration; measured 3e-4) and <= BF16_TRAINED_BOUND = 4.5e-3 at the trained temperature
              logit_scale = 2.659 (s = 14.3) -- a DECLARED DEVIATION from the flat 2e-3:
              rounding the unit-norm operands of the similarity GEMM to 8 mantissa bits perturbs every logit
-             by ~s * 1e-4, which alone costs 2.3e-3..2.8e-3 there whatever the format of the recomputed
-             softmax weights (tools/bf16_error_budget.py emulates the path on the CPU: bf16 operands with
-             exact weights 2.8e-3, with fp16 weights 2.9e-3, fp16 operands 3.5e-4).  The bounds are
-             constants: no assertion scales with the temperature."""
+             by ~s * 1e-4, which alone costs 2.3e-3..3.6e-3 there whatever the format of the recomputed
+             softmax weights.  That floor is computed per case by the oracle
+             (oracle.infonce.clip_loss_grads_rounded_operands: fp64 everywhere except the rounded operands;
+             it reproduces the measured GPU errors to three digits) and the kernels must stay within
+             20 % of it: the deviation is the format's, not the kernel's.  The bounds are constants: no
+             assertion scales with the temperature."""
 import math
 import os
 
@@ -23,7 +25,7 @@ from oracle import infonce as oinf
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-5, "bf16": 2e-3, "fp16": 2e-3}
-BF16_TRAINED_BOUND = 3.2e-3     # bf16 operands at logit_scale = 2.659: declared deviation, see the module docstring
+BF16_TRAINED_BOUND = 4.5e-3     # bf16 operands at logit_scale = 2.659: declared deviation, see the module docstring
 
 
 def grad_bound(precision, ls):
@@ -56,7 +58,13 @@ def _rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
-def _check(got, ref, tol, clamp_rows=None, ls=1.0, precision="bf16"):
+def _floor(img, pro, ls, buckets, precision):
+    if precision != "bf16" or ls <= 1.0:
+        return None
+    return oinf.clip_loss_grads_rounded_operands(img, pro, ls, buckets, "bf16", "bf16")
+
+
+def _check(got, ref, tol, clamp_rows=None, ls=1.0, precision="bf16", floor=None):
     loss, dx, dy, dls = got
     tol_max = grad_bound(precision, ls)
     assert abs(loss - ref["loss"]) / abs(ref["loss"]) < tol, ("loss", loss, ref["loss"])
@@ -71,6 +79,10 @@ def _check(got, ref, tol, clamp_rows=None, ls=1.0, precision="bf16"):
     assert _rel(dx, rx) < tol_max, ("d_image", _rel(dx, rx))
     assert _rel(dy, ry) < tol_max, ("d_profile", _rel(dy, ry))
     assert _rel_l2(dx, rx) < tol_max and _rel_l2(dy, ry) < tol_max, ("l2", _rel_l2(dx, rx), _rel_l2(dy, ry))
+    if floor is not None:    # bf16 at a trained temperature: within 20 % of what bf16 operands allow at all
+        fx, fy = floor
+        assert _rel(dx, rx) < 1.2 * _rel(fx, rx) + 2e-4, ("d_image vs bf16 floor", _rel(dx, rx), _rel(fx, rx))
+        assert _rel(dy, ry) < 1.2 * _rel(fy, ry) + 2e-4, ("d_profile vs bf16 floor", _rel(dy, ry), _rel(fy, ry))
     assert abs(dls - ref["d_logit_scale"]) <= tol * max(abs(ref["d_logit_scale"]), 1e-3), \
         ("d_logit_scale", dls, ref["d_logit_scale"])
 
@@ -83,7 +95,8 @@ def test_golden_reference_vectors(path, precision):
     ref = dict(loss=float(g["loss_f64"]), d_image=g["d_image_f64"], d_profile=g["d_profile_f64"],
                d_logit_scale=float(g["d_logit_scale_f64"]))
     clamp = [3, 5] if "edge" in path else None
-    _check(got, ref, TOL[precision], clamp, float(g["logit_scale"]), precision)
+    _check(got, ref, TOL[precision], clamp, float(g["logit_scale"]), precision,
+           None if clamp else _floor(g["image"], g["profile"], float(g["logit_scale"]), int(g["buckets"]), precision))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
@@ -103,7 +116,8 @@ def test_against_oracle(B, d, buckets, ls, precision):
     img = (cent[lab] + 0.5 * z + 0.3 * r.standard_normal((B, d))).astype(np.float32)
     pro = (cent[lab] + 0.5 * z + 0.3 * r.standard_normal((B, d))).astype(np.float32)
     ref = oinf.clip_loss_closed_form(img, pro, ls, buckets)
-    _check(_run(img, pro, ls, buckets, precision), ref, TOL[precision], ls=ls, precision=precision)
+    _check(_run(img, pro, ls, buckets, precision), ref, TOL[precision], ls=ls, precision=precision,
+           floor=_floor(img, pro, ls, buckets, precision))
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])

@@ -16,7 +16,7 @@ from oracle import siglip as osig
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-5, "bf16": 2e-3, "fp16": 2e-3}
-BF16_TRAINED_BOUND = 3.2e-3
+BF16_TRAINED_BOUND = 4.5e-3
 
 
 def _rel(a, b):
