@@ -44,6 +44,18 @@ def _peaks():
         return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
 
 
+def _ncu_traffic(kernel, n, d, precision):
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(kernel)
+        if e and (e.get("B"), e.get("d"), e.get("precision")) == (n, d, precision):
+            return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """Polls NVML (SM clock + throttle reasons) in a thread while the timed regions run."""
 
@@ -380,14 +392,14 @@ def main():
                 "serial_ms_per_step": serial_ms, "serial_value": Bg / (serial_ms * 1e-3)},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
-        "roofline": {"bound": "tensor", "kernel": "infonce_grad_tc2 (recompute backward, both directions in one launch)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "infonce_grad_tc3 (recompute backward, both directions in one launch)", "achieved": achieved,
                      "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                      "peak_source": f"{peaks['source']} burst", "kernel_ms": k_ms,
                      "algorithmic_flops_per_launch": algo_flops,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, one
-                     # `ncu --set full` capture (profiles/r1_ncu_full_summary.txt): the 4 MiB of 16-bit
-                     # operands; the partial-gradient slabs stay in L2
-                     "traffic": 4287232 if (n, d, args.precision) == (4096, 256, "bf16") else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape,
+                     # parsed from the committed `ncu --set full` capture (profiles/r2_traffic.json, written
+                     # by tools/ncu_summary.py); null when there is no capture of the current kernel
+                     "traffic": _ncu_traffic("infonce_grad_tc3", n, d, args.precision),
                      "executed_flops_per_launch": 2.0 * algo_flops,
                      "executed_tflops": 2.0 * achieved,
                      "note": "the recompute backward executes S = a.b^T once per direction on top of the two "
@@ -416,10 +428,13 @@ def main():
             line["retrieval"] = {"error": repr(e)}
 
         if world == 1:
-            try:
-                line["siglip"] = bench_siglip(args, dev, mode, flush, sync_all, peaks)
-            except Exception as e:
-                line["siglip"] = {"error": repr(e)}
+            for key, fn in (("siglip", lambda: bench_siglip(args, dev, mode, flush, sync_all, peaks)),
+                            ("c1", lambda: bench_c1(args, dev, mode, flush, sync_all)),
+                            ("c5", lambda: bench_c5(args, dev))):
+                try:
+                    line[key] = fn()
+                except Exception as e:
+                    line[key] = {"error": repr(e)}
 
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -430,25 +445,60 @@ def main():
 
 def bench_c3(args, world, rank, dev, mode, flush, sync_all, max_over_ranks, peaks):
     """BASELINE config[2]: global batch 32768, d=512, one bucket, rows sharded across the ranks
-    (all-gather of normalised embeddings, all-reduce of column sums; both backward passes local)."""
+    (all-gather of normalised embeddings, all-reduce of column sums; both backward passes local).
+    N > 1 adds `parity` (rank 0 recomputes the WHOLE batch unsharded on its GPU and compares the global loss,
+    d logit_scale and the gradients of its own rows) and `efficiency_vs_n1` against that unsharded run."""
     import torch
+    import torch.distributed as dist
     from multimodal_plankton_recognition_b200 import CLIPLoss, synth
     n = B_C3 // world
     img, pro, _ = synth.pairs(n, D_C3, 4321 + rank, dev)
     mod = CLIPLoss(precision=args.precision, sharded=world > 1).to(dev)
     x, y = img.requires_grad_(), pro.requires_grad_()
+    last = {}
 
     def step():
         x.grad = y.grad = mod.logit_scale.grad = None
-        mod(image_emb=x, profile_emb=y, buckets=1).backward()
+        loss = mod(image_emb=x, profile_emb=y, buckets=1)
+        loss.backward()
+        last["loss"] = loss.detach()
 
     steps = 10
     ms = max_over_ranks(timed_steps(step, steps, 3, flush, sync_all)) / steps
     flops = 6.0 * B_C3 * B_C3 * D_C3
-    return {"workload": f"InfoNCE fwd+bwd global batch {B_C3}, d={D_C3}, row-block sharded over {world} GPU(s)",
-            "value": B_C3 / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "scaling": "strong",
-            "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
-            "frac_of_peak_all_gpus": flops / (ms * 1e-3) / 1e12 / (peaks["bf16_sustained"] * world)}
+    out = {"workload": f"InfoNCE fwd+bwd global batch {B_C3}, d={D_C3}, row-block sharded over {world} GPU(s)",
+           "value": B_C3 / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "scaling": "strong",
+           "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+           "frac_of_peak_all_gpus": flops / (ms * 1e-3) / 1e12 / (peaks["bf16_sustained"] * world)}
+    if world > 1:
+        # grad_scale="ddp" (the module's default) pre-multiplies the embedding gradients by the world size
+        got = (float(last["loss"]), x.grad.detach().clone() / world, y.grad.detach().clone() / world,
+               float(mod.logit_scale.grad))
+        if rank == 0:
+            parts = [synth.pairs(n, D_C3, 4321 + r, dev) for r in range(world)]
+            fx = torch.cat([p[0] for p in parts]).requires_grad_()
+            fy = torch.cat([p[1] for p in parts]).requires_grad_()
+            del parts
+            one = CLIPLoss(precision=args.precision).to(dev)
+
+            def step1():
+                fx.grad = fy.grad = one.logit_scale.grad = None
+                loss1 = one(image_emb=fx, profile_emb=fy, buckets=1)
+                loss1.backward()
+                last["loss1"] = loss1.detach()
+
+            ms1 = timed_steps(step1, 3, 2, flush, torch.cuda.synchronize) / 3
+            rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+            out["parity"] = {"against": "unsharded single-GPU run of the same kernels on the concatenated batch (rank 0)",
+                             "loss_rel": abs(got[0] - float(last["loss1"])) / abs(float(last["loss1"])),
+                             "d_image_rel": rel(got[1], fx.grad[:n]), "d_profile_rel": rel(got[2], fy.grad[:n]),
+                             "d_logit_scale_rel": abs(got[3] - float(one.logit_scale.grad)) / max(abs(float(one.logit_scale.grad)), 1e-12),
+                             "rows_compared": n}
+            out["ms_per_step_n1"] = ms1
+            out["efficiency_vs_n1"] = ms1 / (world * ms)
+            del fx, fy
+        dist.barrier()
+    return out
 
 
 def bench_siglip(args, dev, mode, flush, sync_all, peaks):
@@ -503,17 +553,22 @@ def bench_siglip(args, dev, mode, flush, sync_all, peaks):
 
 
 def bench_retrieval(args, world, rank, dev, sync_all, max_over_ranks, peaks):
-    """BASELINE config[3]: 1M-row gallery (sharded over the ranks), 100k queries, d=512, top-10."""
+    """BASELINE config[3]: 1M-row gallery (sharded over the ranks), 100k queries, d=512, top-10.
+    `value`: queries resident in HBM, search (+ all-gather / merge of the shard lists) timed with CUDA events;
+    `roofline`: the candidate kernel (topk_tc_kernel + its list merge) alone; `e2e`: the reference-facing call
+    `kneighbors(numpy queries) -> numpy (idx, dist)` with the H2D of the queries and the D2H of the result
+    inside the timed region; `cpu_baseline` (N = 1): exact brute force on the host cores for a 1000-query
+    subsample; N > 1: `parity` + `efficiency_vs_n1` against the unsharded index built on rank 0."""
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from multimodal_plankton_recognition_b200 import synth
+    from multimodal_plankton_recognition_b200 import ANNClassifier, _lib, synth
     from multimodal_plankton_recognition_b200.ann import GpuExactIndex
     ng, nq, d, k = 1_000_000, 100_000, 512, 10
     shard = ng // world
-    gal, _ = synth.unit_embeddings(shard, d, 99 + rank, dev, modality=1)
+    gal, lab = synth.unit_embeddings(shard, d, 99 + rank, dev, modality=1)
     q, _ = synth.unit_embeddings(nq, d, 7, dev, modality=0)
     index = GpuExactIndex.from_device(gal, precision="bf16", gallery_offset=rank * shard)
-    del gal
 
     def search():
         idx, dst = index.search_device(q, k)
@@ -522,22 +577,266 @@ def bench_retrieval(args, world, rank, dev, sync_all, max_over_ranks, peaks):
             idx, dst = merge_shard_results(idx, dst, k, None)
         return idx, dst
 
-    search()
-    sync_all()
-    steps = 3
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for a, b in evs:
-        a.record()
-        search()
-        b.record()
-    sync_all()
-    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / steps
+    def timed(fn, steps, sync):
+        fn()
+        sync()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        sync()
+        return sum(a.elapsed_time(b) for a, b in evs) / steps
+
+    steps = 10
+    ms = max_over_ranks(timed(search, steps, sync_all))
     flops = 2.0 * nq * ng * d
-    return {"workload": f"cosine/euclidean top-{k}: {ng} gallery rows sharded over {world} GPU(s), {nq} queries, d={d}, "
-                        f"bf16 candidates + exact fp32 re-score",
-            "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_search": ms,
-            "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
-            "frac_of_peak_all_gpus": flops / (ms * 1e-3) / 1e12 / (peaks["bf16_sustained"] * world)}
+    out = {"workload": f"cosine/euclidean top-{k}: {ng} gallery rows sharded over {world} GPU(s), {nq} queries, d={d}, "
+                       f"bf16 candidates + exact fp32 re-score",
+           "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_search": ms, "searches_timed": steps,
+           "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+           "frac_of_peak_all_gpus": flops / (ms * 1e-3) / 1e12 / (peaks["bf16_sustained"] * world)}
+
+    # roofline: the tensor-core candidate search of this rank's shard alone (plk_topk_candidates)
+    lib = _lib.load()
+    from multimodal_plankton_recognition_b200 import ops
+    kc = 16
+    q_op = ops.l2norm(q, index.mode, normalise=False)[0]
+    ci = torch.empty((nq, kc), device=dev, dtype=torch.int32)
+    ck = torch.empty((nq, kc), device=dev, dtype=torch.float32)
+    wsb = lib.plk_topk_workspace_bytes(nq, index.n, d, kc, index.mode)
+    ws = torch.empty(max(wsb, 16), device=dev, dtype=torch.uint8)
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def cand():
+        lib.check(lib.plk_topk_candidates(q_op.data_ptr(), index.g_op.data_ptr(), index.mode, q_op.stride(0),
+                                          index.g_sqn.data_ptr(), nq, index.n, d, kc, index.gallery_offset,
+                                          ci.data_ptr(), ck.data_ptr(), ws.data_ptr(), wsb, st), "plk_topk_candidates")
+
+    k_ms = timed(cand, 5, torch.cuda.synchronize)
+    ach = 2.0 * nq * index.n * d / (k_ms * 1e-3) / 1e12
+    out["roofline"] = {"bound": "tensor", "kernel": "topk_tc_kernel (+ select_kernel merging the per-chunk lists)",
+                       "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                       "frac": ach / peaks["bf16_sustained"], "frac_of_burst": ach / peaks["bf16"],
+                       "peak_source": f"{peaks['source']} sustained (the kernel runs for {k_ms:.0f} ms)",
+                       "kernel_ms": k_ms, "algorithmic_flops_per_launch": 2.0 * nq * index.n * d,
+                       "traffic": _ncu_traffic("topk_tc_kernel", nq, d, "bf16")}
+    del q_op, ci, ck, ws
+
+    # e2e: numpy in, numpy out through the reference-facing class
+    q_np = q.cpu().numpy()
+    if world == 1:
+        clf = ANNClassifier.from_index(index, lab.cpu().numpy())
+    else:
+        from multimodal_plankton_recognition_b200.dist import ShardedANNClassifier
+        clf = ShardedANNClassifier.from_device(gal, lab, precision="bf16")
+    e2e_steps = 3
+    clf.kneighbors(q_np, k=k, epsilon=.3)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = clf.kneighbors(q_np, k=k, epsilon=.3)
+    sync_all()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    out["e2e"] = {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_search": e2e_ms,
+                  "h2d_bytes_per_step": int(q_np.nbytes), "d2h_bytes_per_step": int(res[0][0].nbytes + res[0][1].nbytes),
+                  "path": ("ANNClassifier" if world == 1 else "dist.ShardedANNClassifier") +
+                          ".kneighbors(numpy [100000, 512] fp32) -> numpy (idx int32, dist fp32); pageable host "
+                          "arrays, synchronous, as scripts/benchmark_cross.py calls it"}
+
+    if world == 1 and rank == 0:
+        try:
+            from oracle import ann as oann
+            torch.set_num_threads(os.cpu_count() or 1)
+            sub = 1000
+            g_cpu, q_cpu = gal.cpu(), q[:sub].cpu()
+            oann.brute_force_topk_blas(q_cpu[:100], g_cpu, k)
+            t0 = time.perf_counter()
+            bi, bd = oann.brute_force_topk_blas(q_cpu, g_cpu, k)
+            dt = time.perf_counter() - t0
+            gi, _ = index.search_device(q[:sub], k)
+            agree = float((gi.cpu().long() == bi).float().mean())
+            out["cpu_baseline"] = {"value": sub / dt, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{sub} of the {nq} queries against the full {ng}-row gallery: exact fp32 "
+                                             f"brute force (BLAS matmul + topk, oracle.ann.brute_force_topk_blas), "
+                                             f"{dt:.2f} s; the reference's pynndescent search is absent from this image",
+                                   "index_agreement_with_gpu": agree}
+            del g_cpu, q_cpu
+        except Exception as e:
+            out["cpu_baseline"] = {"error": repr(e)}
+
+    if world > 1:
+        got_i, got_d = search()
+        if rank == 0:
+            full = torch.cat([synth.unit_embeddings(shard, d, 99 + r, dev, modality=1)[0] for r in range(world)])
+            one = GpuExactIndex.from_device(full, precision="bf16")
+            del full
+            ms1 = timed(lambda: one.search_device(q, k), 3, torch.cuda.synchronize)
+            sub = 1024
+            wi, wd = one.search_device(q[:sub], k)
+            same = wi == got_i[:sub]
+            out["parity"] = {"against": "unsharded index over the concatenated gallery (rank 0), first 1024 queries",
+                             "dist_max_abs_diff": float((wd - got_d[:sub]).abs().max()),
+                             "index_mismatch_frac": float(1.0 - same.float().mean()),
+                             "mismatches_only_at_equal_distance": bool((wd[~same] == got_d[:sub][~same]).all())}
+            out["ms_per_search_n1"] = ms1
+            out["efficiency_vs_n1"] = ms1 / (world * ms)
+            del one
+        dist.barrier()
+    return out
+
+
+def bench_c1(args, dev, mode, flush, sync_all):
+    """BASELINE config[0] (model_cards/example_multi.yaml scale): batch 256, d=512 -- coordination loss fwd+bwd
+    plus top-10 retrieval over the batch (profile embeddings as gallery, image embeddings as queries).  Launch /
+    latency bound (0.2 GFLOP): microseconds, no roofline fraction.  CPU port beside it."""
+    import numpy as np
+    import torch
+    from multimodal_plankton_recognition_b200 import ops, synth
+    from multimodal_plankton_recognition_b200.ann import GpuExactIndex
+    B, d, k = 256, 512, 10
+    img, pro, _ = synth.pairs(B, d, 11, dev)
+    ls = torch.ones((), device=dev)
+    go = torch.ones(1, device=dev)
+
+    def raw_step():
+        loss, state = ops.clip_loss_forward_state(img, pro, ls, B, mode)
+        return (loss,) + tuple(ops.clip_loss_backward_state(go, img, pro, ls, state, B, mode))
+
+    def graph_of(fn):
+        fn()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = fn()
+        g.keep = keep
+        return g.replay
+
+    steps = min(args.steps, 100)
+    loss_us = 1e3 * timed_steps(graph_of(raw_step), steps, 3, flush, sync_all) / steps
+    un = torch.nn.functional.normalize
+    gal, qry = un(pro), un(img)
+    index = GpuExactIndex.from_device(gal, precision=args.precision if args.precision != "fp32" else "fp32")
+    topk_us = 1e3 * timed_steps(graph_of(lambda: index.search_device(qry, k)), steps, 3, flush, sync_all) / steps
+    out = {"workload": f"batch {B}, d={d}, {args.precision}: InfoNCE fwd+bwd + top-{k} retrieval over the batch",
+           "loss_fwd_bwd_us": loss_us, "top10_us": topk_us, "us_per_step": loss_us + topk_us,
+           "value": B / ((loss_us + topk_us) * 1e-6), "unit": "pairs/s",
+           "timed_path": "CUDA-graph replays (loss: plk_clip_loss_forward + backward; retrieval: candidate search + "
+                         "exact re-score), L2 flushed between steps"}
+    try:
+        from oracle import ann as oann
+        from oracle.infonce import clip_loss_materialised
+        torch.set_num_threads(os.cpu_count() or 1)
+        xc, yc = img.cpu().requires_grad_(), pro.cpu().requires_grad_()
+        lc = torch.ones((), requires_grad=True)
+        tl, tk = [], []
+        gal_np, q_np = gal.cpu().numpy(), qry.cpu().numpy()
+        for _ in range(5):
+            xc.grad = yc.grad = lc.grad = None
+            t0 = time.perf_counter()
+            clip_loss_materialised(xc, yc, lc, 1).backward()
+            t1 = time.perf_counter()
+            want = oann.ExactIndex(gal_np).query(q_np, k=k)
+            t2 = time.perf_counter()
+            tl.append(t1 - t0)
+            tk.append(t2 - t1)
+        gi, gd = index.search_device(qry, k)
+        out["cpu_baseline"] = {"value": B / (min(tl) + min(tk)), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                               "loss_fwd_bwd_us": 1e6 * min(tl), "top10_us": 1e6 * min(tk),
+                               "sample": "5 repetitions of the same batch, best of 5 (oracle port of CLIPLoss + exact index)"}
+        out["parity"] = {"top10_dist_equal": bool(np.array_equal(gd.cpu().numpy(), want[1])),
+                         "top10_index_mismatch_frac": float((gi.cpu().numpy() != want[0]).mean())}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
+
+
+def bench_c5(args, dev):
+    """BASELINE config[4]: the 5-fold few-shot k-NN benchmark of reference scripts/benchmark_cross_folds.py on
+    synthetic CytoSense-shaped embeddings (9250 samples, 27 long-tailed classes, d=512, StratifiedKFold(5,
+    shuffle, seed 0); galleries of n in (2,4,8,12,16) per class, K = (1,3,5,7,9) and the BASELINE k = 10, eight
+    set-ups incl. image->profile and profile->image) through `harness.cross_benchmark_folds`.  The CPU port
+    (oracle.ann.fold_benchmark_port, the reference's loop over the oracle's exact index) runs one fold at n = 16
+    beside it; its labels must be IDENTICAL to the GPU harness's on that fold."""
+    import random
+    import numpy as np
+    import torch
+    from sklearn.model_selection import StratifiedKFold
+    from sklearn.preprocessing import LabelEncoder
+    from multimodal_plankton_recognition_b200 import harness, synth
+    N, d = 9250, 512
+    NS, K, repeats = (2, 4, 8, 12, 16), (1, 3, 5, 7, 9, 10), 1
+    img, pro, lab = synth.pairs(N, d, 2024, "cpu", separation=0.15)     # k-NN accuracy 80-90 %: votes are contested
+    un = torch.nn.functional.normalize
+    img, pro, lab = un(img).numpy(), un(pro).numpy(), lab.numpy()
+    names = np.array([f"class_{c:02d}" for c in lab])
+    coder = LabelEncoder().fit(names)
+    folds = list(StratifiedKFold(5, shuffle=True, random_state=0).split(img, lab))
+
+    def fold_data(i):
+        tr, te = folds[i]
+        return (img[tr], pro[tr], names[tr]), (img[te], pro[te], names[te])
+
+    def run_gpu():
+        random.seed(0)
+        res = {}
+        for i in range(len(folds)):
+            train, test = fold_data(i)
+            res[i] = {n: harness.cross_benchmark_folds(train, test, coder, n, repeats, K, plk_precision="bf16")
+                      for n in NS}
+        return res
+
+    run_gpu()                          # warm-up (module load, allocator)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = run_gpu()
+    torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    n_pred = len(folds) * len(NS) * repeats * len(K) * 8
+    queries = sum(len(folds[i][1]) for i in range(len(folds))) * len(NS) * repeats * len(K) * 8
+    acc = {}
+    for setup in ("I - P", "P - I", "I+P - I"):
+        hit = tot = 0
+        for i in res:
+            r = res[i][16][0]
+            hit += int((r["pred"][10][setup] == r["true"]).sum())
+            tot += len(r["true"])
+        acc[setup] = hit / tot
+    out = {"workload": f"5-fold few-shot k-NN benchmark (scripts/benchmark_cross_folds.py): {N} samples, 27 classes, d={d}, "
+                       f"n per class in {NS}, K={K}, 8 set-ups, {repeats} repeat(s) per fold",
+           "seconds": gpu_s, "predict_calls_replaced": n_pred, "value": queries / gpu_s, "unit": "classified queries/s",
+           "accuracy_k10_n16": acc,
+           "timed_path": "harness.cross_benchmark_folds (numpy in, class names out; one search per set-up at max(K), "
+                         "prefix votes per k), all folds, wall clock"}
+    try:
+        from oracle import ann as oann
+        train, test = fold_data(0)
+        sub = 600                                  # bounded CPU sample: the first 600 queries of fold 0
+        test = tuple(t[:sub] for t in test)
+        random.seed(0)
+        gpu0 = harness.cross_benchmark_folds(train, test, coder, 16, 1, K, plk_precision="bf16")
+        random.seed(0)
+        t0 = time.perf_counter()
+        cpu0 = oann.fold_benchmark_port(train, test, coder, 16, 1, K)
+        cpu_s = time.perf_counter() - t0
+        same = all(np.array_equal(gpu0[0]["pred"][kk][sname], cpu0[0]["pred"][kk][sname])
+                   for kk in K for sname in cpu0[0]["pred"][kk])
+        assert same, "k-NN fold labels differ from the CPU port"
+        q0 = len(test[2]) * len(K) * 8
+        out["cpu_baseline"] = {"value": q0 / cpu_s, "unit": "classified queries/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"fold 0, n = 16, first {sub} test samples, K = {K}, 8 set-ups ({q0} classified "
+                                         f"queries) through oracle.ann.fold_benchmark_port (one predict per k, as the "
+                                         f"reference's loop), {cpu_s:.1f} s"}
+        out["parity"] = {"labels_identical_to_cpu_port": bool(same), "labels_compared": q0}
+    except Exception as e:
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
 
 
 if __name__ == "__main__":

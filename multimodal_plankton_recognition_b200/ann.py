@@ -157,6 +157,17 @@ class ANNClassifier:
         self.index.prepare()
         self._labels_dev = torch.from_numpy(self.y_.astype(np.int64)).to(self.index.device)
 
+    @classmethod
+    def from_index(cls, index: GpuExactIndex, y):
+        """An ANNClassifier over a gallery that is already resident in HBM (`GpuExactIndex.from_device`)."""
+        self = cls.__new__(cls)
+        self.y_ = np.asarray(y).copy()
+        if len(self.y_) != index.n:
+            raise ValueError(f"{len(self.y_)} labels for a gallery of {index.n} rows")
+        self.index = index
+        self._labels_dev = torch.from_numpy(self.y_.astype(np.int64)).to(index.device)
+        return self
+
     def kneighbors(self, *X, **query_args):
         return tuple(self.index.query(x, **query_args) for x in X)
 

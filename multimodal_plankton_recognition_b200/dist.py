@@ -216,16 +216,35 @@ class ShardedANNClassifier:
         precision = nndescent_args.pop("plk_precision", "bf16")
         device = nndescent_args.pop("plk_device", None)
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._exchange_layout(len(X), dev)
+        self.index = ann.GpuExactIndex(X, precision=precision, device=dev, gallery_offset=self.offset)
+        self._exchange_labels(y, dev)
+
+    @classmethod
+    def from_device(cls, g32: torch.Tensor, y, group=None, precision: str = "bf16"):
+        """Same over a gallery shard that already lives in HBM (fp32 [n, d] on this rank's GPU)."""
+        from . import ann
+        self = cls.__new__(cls)
+        self.group = group
+        self._exchange_layout(g32.shape[0], g32.device)
+        self.index = ann.GpuExactIndex.from_device(g32, precision=precision, gallery_offset=self.offset)
+        self._exchange_labels(y, g32.device)
+        return self
+
+    def _exchange_layout(self, n_local, dev):
+        R, r = _world(self.group)
         counts = torch.zeros(R, dtype=torch.int64, device=dev)
-        counts[r] = len(X)
-        dist.all_reduce(counts, group=group)
+        counts[r] = n_local
+        dist.all_reduce(counts, group=self.group)
         self.counts = counts.cpu().tolist()
         self.offset = int(sum(self.counts[:r]))
         self.total = int(sum(self.counts))
-        self.index = ann.GpuExactIndex(X, precision=precision, device=dev, gallery_offset=self.offset)
+
+    def _exchange_labels(self, y, dev):
+        y = y.detach().cpu().numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
         labels = torch.zeros(self.total, dtype=torch.int64, device=dev)
-        labels[self.offset:self.offset + len(X)] = torch.from_numpy(np.asarray(y).astype(np.int64)).to(dev)
-        dist.all_reduce(labels, group=group)
+        labels[self.offset:self.offset + len(y)] = torch.from_numpy(y.astype(np.int64)).to(dev)
+        dist.all_reduce(labels, group=self.group)
         self._labels_dev = labels
         self.y_ = labels.cpu().numpy()
 

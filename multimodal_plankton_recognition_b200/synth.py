@@ -23,14 +23,16 @@ def labels_for(n: int, seed: int, n_classes: int = N_CLASSES) -> np.ndarray:
     return lab
 
 
-def pairs(n: int, d: int, seed: int = 1234, device="cpu", n_classes: int = N_CLASSES):
-    """-> (image_emb [n,d] fp32, profile_emb [n,d] fp32, labels [n] int64) on `device`."""
+def pairs(n: int, d: int, seed: int = 1234, device="cpu", n_classes: int = N_CLASSES, separation: float = 1.0):
+    """-> (image_emb [n,d] fp32, profile_emb [n,d] fp32, labels [n] int64) on `device`.
+    `separation` scales the class centroids: 1.0 gives well separated classes, ~0.15 a k-NN accuracy of
+    80-90 % at d = 512 (the few-shot benchmark wants votes that are not unanimous)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     cent = torch.randn(n_classes, d, generator=g)
     lab = torch.from_numpy(labels_for(n, seed, n_classes))
     dev = torch.device(device)
     gd = torch.Generator(device=dev).manual_seed(seed + 1)
-    c = cent.to(dev)[lab.to(dev)]
+    c = separation * cent.to(dev)[lab.to(dev)]
     z = torch.randn(n, d, device=dev, generator=gd)
     img = c + 0.5 * z + 0.3 * torch.randn(n, d, device=dev, generator=gd)
     pro = c + 0.5 * z + 0.3 * torch.randn(n, d, device=dev, generator=gd)

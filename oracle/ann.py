@@ -107,3 +107,65 @@ class OracleANNClassifier:
         dist = np.hstack([p[1] for p in pairs])
         w = inverse_distance_weights(dist)
         return weighted_vote(self.y_[idx], w).ravel()
+
+
+def draw_gallery(labels, n):
+    """reference scripts/benchmark_cross_folds.py:14-21 (`sample`): n members of every class, drawn with Python's
+    `random.sample` from the ascending positions of the class, classes in sorted order."""
+    import random
+    labels = np.asarray(labels)
+    positions = np.arange(len(labels))
+    picked = []
+    for cls in np.unique(labels):
+        picked.extend(random.sample(list(positions[labels == cls]), n))
+    return np.array(picked)
+
+
+def fold_benchmark_port(train, test, coder, n, repeats, K, classifier=None, **index_args):
+    """Restatement of `benchmark()` of reference scripts/benchmark_cross_folds.py:24-85 over the oracle's
+    classifier: per run a gallery of n per class drawn from the train fold, one index per gallery kind
+    (image / profile / both), one `predict` PER k and set-up (the reference's loop order), the whole test
+    fold queried.  -> {run: {"pred": {k: {setup: class names}}, "true": class names}}.
+    Consumes Python's `random` stream exactly like the reference, so with the same seed it sees the same
+    galleries as `multimodal_plankton_recognition_b200.harness.cross_benchmark_folds`."""
+    classifier = classifier or OracleANNClassifier
+    image_train, profile_train, name_train = train
+    image_test, profile_test, name_test = test
+    label_train, label_test = coder.transform(name_train), coder.transform(name_test)
+    results = {}
+    for run in range(repeats):
+        idx = draw_gallery(label_train, n)
+        img, pro, lab = image_train[idx], profile_train[idx], label_train[idx]
+        res = {"pred": {k: {} for k in K}, "true": coder.inverse_transform(label_test)}
+        plans = ((img, lab, ("I - I", "I - P", "I - I+P"),
+                  ((image_test,), (profile_test,), (image_test, profile_test))),
+                 (pro, lab, ("P - I", "P - P", "P - I+P"),
+                  ((image_test,), (profile_test,), (image_test, profile_test))),
+                 (np.concatenate((img, pro)), np.tile(lab, (2,)), ("I+P - I", "I+P - P"),
+                  ((image_test,), (profile_test,))))
+        for gx, gy, names, queries in plans:
+            clf = classifier(gx, gy, **index_args)
+            for k in K:
+                for name, X in zip(names, queries):
+                    res["pred"][k][name] = coder.inverse_transform(clf.predict(*X, k=k, epsilon=.3))
+        results[run] = res
+    return results
+
+
+def brute_force_topk_blas(q, g, k, block=250):
+    """Timed CPU baseline for the 1M-gallery configuration ("fp32 numpy/torch brute
+    force ... time a 1 000-query subsample and scale linearly"): euclidean top-k through the expansion
+    |q|^2 + |g|^2 - 2 q.g in fp32 with a multi-threaded BLAS matmul per query block, then `topk`.  This is
+    the fastest exact CPU formulation, NOT the parity oracle (ExactIndex above evaluates the direct form in
+    fp64); the reference itself calls pynndescent's approximate search, which is absent from this image.
+    q [nq, d], g [ng, d] torch fp32 CPU tensors -> (idx int64 [nq, k], dist fp32 [nq, k])."""
+    import torch
+    gn = (g * g).sum(1)
+    out_i, out_d = [], []
+    for s in range(0, q.shape[0], block):
+        qb = q[s:s + block]
+        d2 = (qb * qb).sum(1, keepdim=True) + gn[None, :] - 2.0 * (qb @ g.T)
+        val, idx = torch.topk(d2, k, dim=1, largest=False, sorted=True)
+        out_i.append(idx)
+        out_d.append(val.clamp_min(0).sqrt())
+    return torch.cat(out_i), torch.cat(out_d)
