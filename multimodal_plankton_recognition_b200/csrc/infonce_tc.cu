@@ -1343,6 +1343,325 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc3(
 
 
 // =============================================================================================
+// backward, d <= 256, logits in TS mode at N = 128 and G through shared memory ("tc4").
+//
+// Measured on B200 (tools/trace_tc.py): a TS-mode tcgen05.mma takes 64 cycles however small N is, and an
+// SS-mode 128x128x16 MMA 128 cycles (both operands through the 64 B/clk shared-memory operand port).  So
+// S = a . b_t^T costs 16 x 128 cycles per 128-column tile with the owned rows in shared memory
+// (infonce_grad_tc2: 3100 cycles per tile together with G . b_t), and 2 x 16 x 64 when the columns are
+// halved to make room in TMEM (infonce_grad_tc3: the same 3070).  Here the owned rows sit in TMEM and S
+// keeps N = 128 (16 x 64 = 1024 cycles); what no longer fits in TMEM is a second logits buffer or G, so the
+// epilogue hands the logits buffer back right after its tcgen05.ld and writes the packed 16-bit G to a
+// 32 KiB shared-memory buffer, from where G . b_t runs in SS mode against the whole [128 x d] tile as ONE
+// MN-major operand (8 MMAs of N = d, ~1100 cycles).
+//     TMEM  [0,128) S | [128,256) owned rows (packed pairs) | [256,512) acc [128 x d] fp32
+//     smem  3 tile buffers [128 x d] (a 64 KiB tile takes ~1450 cycles to arrive and is held from S(t) to the
+//           end of GV(t): with two buffers the refill was exposed every tile) | G [128 x 128] 16-bit
+//           (3 x 64 + 32 KiB + 2 KiB of barriers = exactly the 227 KiB a CTA may have at d = 256)
+// Issue order S(0) | S(1) GV(0) | S(2) GV(1) | ...: S(t+1) needs the logits buffer back (tcgen05.ld of tile
+// t, ~400 cycles into GV(t-1)); GV(t) needs G(t), which the epilogue stores after GV(t-1) has released the
+// G buffer; the commit behind GV(t) also releases tile buffer t % 3 for tile t + 3.
+// =============================================================================================
+constexpr int kG4Aux = 2048;
+template <int KD>
+struct Grad4Cfg {
+  static constexpr int kTileBuf = KD * kChunkBytes;
+  static constexpr int kNBuf = 3;
+  static constexpr int kGBuf = 2 * kChunkBytes;            // [128 x 128] 16-bit as two K-major [128 x 64] sub-tiles
+  static constexpr int kSmem = 1024 + kNBuf * kTileBuf + kGBuf + kG4Aux;
+  static_assert(kSmem <= kMaxSmem, "tc4 needs d <= 256");
+};
+
+template <int KD, bool F16, bool SIG>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
+    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+    int64_t d, int64_t bs, int tiles_per_seg, const float* __restrict__ ls) {
+  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
+  using Cfg = Grad4Cfg<KD>;
+  constexpr int NB = Cfg::kNBuf;
+  constexpr int DN = KD * 64;  // accumulator columns = padded d
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_y = smem;                                    // [NB][KD chunks]
+  uint8_t* sm_g = smem + NB * Cfg::kTileBuf;               // [2 sub-tiles]
+  uint8_t* aux = sm_g + Cfg::kGBuf;
+  uint64_t* bar_afull = reinterpret_cast<uint64_t*>(aux);  // [1] owned rows landed in the last tile buffer
+  uint64_t* bar_a = bar_afull + 1;                         // [1] owned rows parked in TMEM
+  uint64_t* bar_yfull = bar_a + 1;                         // [NB] tile landed
+  uint64_t* bar_yempty = bar_yfull + NB;                   // [NB] tile consumed by S and G.V
+  uint64_t* bar_sfull = bar_yempty + NB;                   // [1] logits complete
+  uint64_t* bar_sempty = bar_sfull + 1;                    // [1] logits read by the epilogue
+  uint64_t* bar_gfull = bar_sempty + 1;                    // [1] G written
+  uint64_t* bar_gempty = bar_gfull + 1;                    // [1] G consumed by G.V
+  uint64_t* bar_accfull = bar_gempty + 1;                  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
+  float* rcs_s = reinterpret_cast<float*>(aux + 512);      // [2][128]
+  uint8_t* sm_astage = sm_y + (NB - 1) * Cfg::kTileBuf;    // owned rows arrive here (first used by tile NB-1)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
+  int64_t jlo = 0, jhi = n_cols;
+  row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
+  const int t_begin = blockIdx.x * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;
+  float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
+  if (T == 0) {
+    griddep_wait();   // global writes only after the kernel queued before this one is done
+    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DN; e += kNumThreads) {
+      const int64_t rr = i0 + e / DN, col = e % DN;
+      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) TR(0);
+  pdl_trigger();   // the gradient-tail kernel may become resident; it waits for this grid's completion
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.ta);
+    tma_prefetch_desc(&g.tb);
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_a, kEpiThreads);
+    for (int b = 0; b < NB; ++b) {
+      mbar_init(bar_yfull + b, 1);
+      mbar_init(bar_yempty + b, 1);
+    }
+    mbar_init(bar_sfull, 1);
+    mbar_init(bar_sempty, kEpiThreads / 32);   // one elected arrival per epilogue warp
+    mbar_init(bar_gfull, kEpiThreads / 32);
+    mbar_init(bar_gempty, 1);
+    mbar_init(bar_accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kSCol = 0, kACol = 128, kAccCol = 256;
+  if (threadIdx.x == 0) TR(1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_afull, KD * kChunkBytes);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_astage + c * kChunkBytes, &g.ta, bar_afull, c * kChunkK, (int)i0);
+      int b = 0; uint32_t ph = 0;
+      for (int t = 0; t < T; ++t) {
+        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+        if (t == NB - 1) mbar_wait(bar_a, 0);   // the staged owned rows have left the last buffer
+        mbar_wait(bar_yempty + b, ph ^ 1);
+        mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
+        for (int c = 0; c < KD; ++c)
+          tma_load_2d(sm_y + (b * KD + c) * kChunkBytes, &g.tb, bar_yfull + b, c * kChunkK, j0);
+        if (t < 16) TR(48 + t);
+        if (++b == NB) { b = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // All 32 lanes run this loop (warp-uniform control flow, see elect_one); one elected lane issues.
+    constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
+    constexpr uint32_t idesc_g = umma_idesc_16(128, DN, 0, 1, F16);   // A = G (K-major, smem), B = tile MN-major
+    mbar_wait(bar_a, 0);     // the epilogue warps have parked the owned rows in TMEM
+    tc_fence_after();
+    if (lane == 0) TR(3);
+    const uint32_t s_tmem = tmem_base + kSCol, a_tmem0 = tmem_base + kACol, acc_tmem = tmem_base + kAccCol;
+    const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);               // K-major view (S)
+    const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y), kChunkBytes);     // MN-major view (G.V), LBO = chunk
+    const uint32_t g_lo0 = umma_desc_lo(smem_u32(sm_g), 16);
+    int b = 0; uint32_t ph = 0;   // buffer / phase of tile t (S side)
+    int bg = 0;                   // buffer of tile t-1 (G.V side)
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        mbar_wait(bar_yfull + b, ph);
+        if (t >= 1) mbar_wait(bar_sempty, (t - 1) & 1);
+        tc_fence_after();
+        const uint32_t b_lo = y_lo0 + b * KD * (kChunkBytes >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < KD; ++c)
+#pragma unroll
+            for (int k = 0; k < kChunkK / kUmmaK; ++k)
+              umma_bf16_ts(s_tmem, a_tmem0 + c * 32 + k * 8, b_lo + c * (kChunkBytes >> 4) + 2 * k, idesc_s,
+                           (c | k) != 0);
+          umma_commit(bar_sfull);
+        }
+        __syncwarp();
+        if (lane == 0 && t < 16) TR(64 + t);
+        if (++b == NB) { b = 0; ph ^= 1; }
+      }
+      if (t >= 1) {
+        const int u = t - 1;
+        mbar_wait(bar_gfull, u & 1);
+        tc_fence_after();
+        const uint32_t b_lo = y2_lo0 + bg * KD * (kChunkBytes >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTileRows / kUmmaK; ++k)
+            // A = G[128 x 128] K-major: K 0..63 in sub-tile 0, 64..127 in sub-tile 1 (32 bytes per K step)
+            // B = tile[128 j x d] read MN-major: 16 K-rows (j) = 2048 bytes per step
+            umma_bf16_lo(acc_tmem, g_lo0 + (k >> 2) * (kChunkBytes >> 4) + (k & 3) * 2, b_lo + k * (2048 >> 4), idesc_g,
+                         (u | k) != 0);
+          umma_commit(bar_yempty + bg);   // tile buffer free once S(u) and G.V(u) have retired
+          umma_commit(bar_gempty);        // ... and so is the G buffer
+        }
+        __syncwarp();
+        if (lane == 0 && u < 16) TR(112 + u);
+        if (++bg == NB) bg = 0;
+      }
+    }
+    if (elect_one()) umma_commit(bar_accfull);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int cc = (warp - 2) >> 2;          // which 32-column chunk of the tile this warp owns
+    const int r = q * 32 + lane;
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    float rrs = 0.f;
+    constexpr bool siglip = SIG;
+    if (i < n_rows) {
+      bucket_range(gi, bs, n_cols, lo, hi);
+      if (!siglip) rrs = 1.0f / g.rs[i];
+    }
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : (kShiftK - s) * kLog2e;
+    const bool want_gs = g.gs != nullptr;
+    float gs_local = 0.f, gsum_local = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    {  // park this thread's owned row in TMEM as packed pairs (A operand of S); source: the staged rows
+      mbar_wait(bar_afull, 0);
+      for (int c = cc; c < KD; c += 4) {
+        const uint8_t* rowp = sm_astage + c * kChunkBytes + r * 128;
+        uint32_t pk[32];
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) {
+          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
+        }
+        tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+      if (threadIdx.x == 64) TR(2);
+    }
+    // 1/cs of the NEXT tile is fetched one tile ahead and parked in the other half of rcs_s
+    float rc_next = 0.f;
+    if (cc == 0 && !siglip) {
+      const int64_t jc = jlo + (int64_t)t_begin * kTileRows + r;
+      rcs_s[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+    }
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      named_barrier_sync(1, kEpiThreads);   // rcs_s[buf] visible; everyone is done with tile t-1
+      if (cc == 0 && t + 1 < T && !siglip) {
+        const int64_t jc = j0 + kTileRows + r;
+        rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
+      }
+      mbar_wait(bar_sfull, t & 1);
+      tc_fence_after();
+      if (threadIdx.x == 64 && t < 16) TR(80 + t);
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + kSCol + cc * 32, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sempty);   // the logits buffer goes back to the MMA warp right away
+      uint32_t packed[16];
+      grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
+                               want_gs, gs_local, siglip, gsum_local);
+      if (t >= 1) mbar_wait(bar_gempty, (t - 1) & 1);   // G.V of the previous tile has read the G buffer
+      // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
+      uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
+        *reinterpret_cast<uint4*>(grow + chunk * 16) =
+            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_gfull);
+      if (threadIdx.x == 64 && t < 16) TR(96 + t);
+      if (cc == 0 && t + 1 < T) rcs_s[(buf ^ 1) * 128 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+    }
+    mbar_wait(bar_accfull, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) TR(2);
+    griddep_wait();   // global writes start here (see infonce_grad_tc2)
+    if (g.use_tacc) {
+#pragma unroll 1
+      for (int ch = cc; ch < 2 * KD; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        uint8_t* stage = sm_y + ch * kChunkBytes;     // 128 rows x 128 B in the idle tile buffers
+        uint8_t* rowp = stage + r * 128;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
+              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+        fence_proxy_async_smem();
+        named_barrier_sync(2 + cc, 128);
+        if (q == 0 && lane == 0 && i0 < n_rows) {
+          tma_store_3d(&g.tacc, stage, ch * 32, (int)i0, (int)blockIdx.x);
+          tma_store_commit();
+        }
+      }
+      if (q == 0 && lane == 0) tma_store_wait_all();
+    } else {
+#pragma unroll 1
+      for (int ch = cc; ch < 2 * KD; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        const int64_t col0 = (int64_t)ch * 32;
+        if (i < n_rows) {
+          float* dst = acc_out + i * d + col0;
+          if (col0 + 32 <= d && (d & 3) == 0) {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4)
+              *reinterpret_cast<float4*>(dst + x) =
+                  make_float4(__uint_as_float(raw[x]), __uint_as_float(raw[x + 1]),
+                              __uint_as_float(raw[x + 2]), __uint_as_float(raw[x + 3]));
+          } else {
+#pragma unroll
+            for (int x = 0; x < 32; ++x)
+              if (col0 + x < d) dst[x] = __uint_as_float(raw[x]);
+          }
+        }
+      }
+    }
+    if (want_gs) {
+      gs_local *= s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+        gsum_local += __shfl_xor_sync(0xffffffffu, gsum_local, o);
+      }
+      if (lane == 0) {
+        atomicAdd(g.gs, gs_local);   // zeroed by the forward's last kernel (waited for above)
+        if (siglip) atomicAdd(g.gs + 1, gsum_local);
+      }
+    }
+  }
+  griddep_wait();   // no thread block outlives the kernel queued before it (see launch_kernel_ex)
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) TR(5);
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+  if (threadIdx.x == 0) TR(6);
+}
+
+// =============================================================================================
 // host launchers
 // =============================================================================================
 // widest column range [jlo, jhi) a 128-row block can need: the union of the buckets its rows touch
@@ -1501,14 +1820,42 @@ static int launch_grad3(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
              : launch_grad3_m<KD, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
 }
 
+template <int KD, bool F16, bool SIG>
+static int launch_grad4_m(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                          int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  auto kern = infonce_grad_tc4<KD, F16, SIG>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad4Cfg<KD>::kSmem));
+    configured = true;
+  }
+  int rc = launch_kernel_ex(kern, grid, dim3(kNumThreads), Grad4Cfg<KD>::kSmem, st, 1, overlap_prev, ga, n_rows,
+                            row_offset, n_cols, d, bs, tps, ls);
+  if (rc) return rc;
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+template <int KD, bool F16>
+static int launch_grad4(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  return ga.bias != nullptr
+             ? launch_grad4_m<KD, F16, true>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev)
+             : launch_grad4_m<KD, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
+}
+
 // PLK_GRAD_TC2=1 selects the previous d <= 256 backward (owned rows read from shared memory, 128-column
 // tiles) for A/B measurements; the default is infonce_grad_tc3.
 static bool use_grad_tc2() {
   static const bool v = getenv("PLK_GRAD_TC2") != nullptr && getenv("PLK_GRAD_TC2")[0] == '1';
   return v;
 }
+// PLK_GRAD_TC3=1: infonce_grad_tc3 (64-column tiles, G in TMEM); default for d <= 256: infonce_grad_tc4
+static bool use_grad_tc3() {
+  static const bool v = getenv("PLK_GRAD_TC3") != nullptr && getenv("PLK_GRAD_TC3")[0] == '1';
+  return v;
+}
 // logits columns per tile of the backward that serves a padded width of kd 64-element chunks
-static int grad_tile_cols(int kd) { return (kd <= 4 && !use_grad_tc2()) ? kG3Cols : kTileRows; }
+static int grad_tile_cols(int kd) { return (kd <= 4 && use_grad_tc3() && !use_grad_tc2()) ? kG3Cols : kTileRows; }
 
 // number of partial accumulators per direction for this shape (bf16 path); ndir = 1 or 2 directions per launch
 int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int ndir) {
@@ -1550,6 +1897,15 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
         ga.dir[k].use_tacc = 1;
       }
       if (ga.ndir == 1) ga.dir[1] = ga.dir[0];
+    }
+    if (!use_grad_tc2() && !use_grad_tc3()) {   // S in TS mode at N = 128, G through shared memory, no clusters
+      dim3 grid4((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
+      switch (kd) {
+#define PLK_CASE4(KD) \
+  case KD: return launch_grad4<KD, F16>(ga, grid4, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
+        PLK_CASE4(1) PLK_CASE4(2) PLK_CASE4(3) PLK_CASE4(4)
+#undef PLK_CASE4
+      }
     }
     if (!use_grad_tc2()) {   // both GEMMs in TS mode, 64-column tiles, no clusters
       dim3 grid3((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);
