@@ -338,11 +338,19 @@ def main():
         # one GPU: forward and backward of the module replay CUDA graphs (CLIPLoss.graphed =
         # torch.cuda.make_graphed_callables), which takes the host out of the critical path
         step_fn_e2e = None
-        if world == 1 and os.environ.get("PLK_BENCH_GRAPHED_E2E", "1") == "1":
+        if os.environ.get("PLK_BENCH_GRAPHED_E2E", "1") == "1":
+            # N > 1: bucket-aligned sharding with the in-kernel scalar exchange has no collective launch,
+            # so the module's forward and backward can be graphed there as well
             try:
-                step_fn_e2e = mod.graphed(img, pro)
+                step_fn_e2e = mod.graphed(img, pro, buckets=world)
             except Exception as e:
-                print(f"bench: CLIPLoss.graphed unavailable ({e!r}); eager e2e", file=sys.stderr)
+                if rank == 0:
+                    print(f"bench: CLIPLoss.graphed unavailable ({e!r}); eager e2e", file=sys.stderr)
+            if world > 1:      # every rank must take the same path
+                ok = torch.tensor([1 if step_fn_e2e is not None else 0], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok) == 0:
+                    step_fn_e2e = None
 
         def streamed_step():
             x, y = next(feed)
@@ -464,12 +472,50 @@ def bench_c3(args, world, rank, dev, mode, flush, sync_all, max_over_ranks, peak
         last["loss"] = loss.detach()
 
     steps = 10
-    ms = max_over_ranks(timed_steps(step, steps, 3, flush, sync_all)) / steps
+    ms_module = max_over_ranks(timed_steps(step, steps, 3, flush, sync_all)) / steps
+    ms, path = ms_module, "CLIPLoss(sharded) module, eager (autograd + NCCL launches from the host)"
+    if world > 1 and os.environ.get("PLK_BENCH_C3_GRAPH", "1") == "1":
+        # the same step (dist.sharded_fwd + dist.sharded_bwd: kernels AND the three NCCL collectives) captured
+        # in one CUDA graph: the host queues a single launch per step
+        try:
+            from multimodal_plankton_recognition_b200 import dist as pdist
+            ls, go = mod.logit_scale.detach(), torch.ones(1, device=dev)
+            xd, yd = img.detach(), pro.detach()
+
+            def raw():
+                loss, state = pdist.sharded_fwd(xd, yd, ls, 1, mode, None)
+                return (loss,) + tuple(pdist.sharded_bwd(state, go, "ddp"))
+
+            raw()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    raw()
+            torch.cuda.current_stream().wait_stream(side)
+            sync_all()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                keep = raw()
+            ms_graph = max_over_ranks(timed_steps(graph.replay, steps, 3, flush, sync_all)) / steps
+            # the replayed step reproduces the module's result
+            assert abs(float(keep[0]) - float(last["loss"])) <= 1e-5 * abs(float(last["loss"])), \
+                f"graph replay loss {float(keep[0])} != module loss {float(last['loss'])}"
+            if ms_graph < ms:
+                ms, path = ms_graph, "CUDA-graph replay of dist.sharded_fwd + dist.sharded_bwd (kernels + 3 NCCL collectives)"
+            last["ms_graph"] = ms_graph
+        except Exception as e:
+            import traceback
+            last["graph_error"] = repr(e) + " | " + traceback.format_exc()[-600:]
     flops = 6.0 * B_C3 * B_C3 * D_C3
     out = {"workload": f"InfoNCE fwd+bwd global batch {B_C3}, d={D_C3}, row-block sharded over {world} GPU(s)",
-           "value": B_C3 / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "scaling": "strong",
+           "value": B_C3 / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "scaling": "strong", "timed_path": path,
+           "ms_per_step_module_eager": ms_module,
            "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
            "frac_of_peak_all_gpus": flops / (ms * 1e-3) / 1e12 / (peaks["bf16_sustained"] * world)}
+    for k_ in ("ms_graph", "graph_error"):
+        if k_ in last:
+            out[k_] = last[k_]
     if world > 1:
         # grad_scale="ddp" (the module's default) pre-multiplies the embedding gradients by the world size
         got = (float(last["loss"]), x.grad.detach().clone() / world, y.grad.detach().clone() / world,

@@ -44,7 +44,8 @@ class CLIPLoss(Module):
         self._xgpu_tried = False
 
     def forward(self, image_emb: Tensor, profile_emb: Tensor, buckets: int = 1) -> Tensor:
-        assert image_emb.size(0) % buckets == 0, \
+        # sharded: `buckets` counts the buckets of the GLOBAL batch; dist.sharded_fwd asserts on that
+        assert self.sharded or image_emb.size(0) % buckets == 0, \
             "Batch size must be divisible by number of buckets!"
         if image_emb.dim() != 2 or image_emb.shape != profile_emb.shape:
             raise ValueError(f"expected two [B, d] embeddings of equal shape, got "
@@ -80,28 +81,37 @@ class CLIPLoss(Module):
                 self._xgpu = None
         return self._xgpu
 
-    def graphed(self, image_emb: Tensor, profile_emb: Tensor):
+    def graphed(self, image_emb: Tensor, profile_emb: Tensor, buckets: int = 1):
         """-> callable ``f(image_emb, profile_emb) -> loss`` whose forward AND backward replay CUDA graphs
         (`torch.cuda.make_graphed_callables`): ~40 us of host time per step instead of ~150.  The sample
-        tensors fix shape and dtype (buckets = 1; single GPU -- collectives are kept out of captures)."""
+        tensors fix shape and dtype; `buckets` is fixed too.  A sharded loss can be graphed in the bucket-aligned
+        case (every bucket on one rank) when the peer-memory scalar exchange is available: the step then contains
+        no collective launch -- the sums over the ranks run inside the kernels over NVLink.  Every rank must call
+        this, and later the returned callable, the same number of times."""
+        buckets = int(buckets)
         if self.sharded:
-            raise RuntimeError("graphed() is for the single-GPU loss; the sharded path issues collectives")
+            if self._peer_scalars(image_emb, buckets) is None:
+                raise RuntimeError("graphed() on a sharded loss needs the bucket-aligned case with the peer-memory "
+                                   "scalar exchange (d % 128 == 0, NVLink symmetric memory): the general row-sharded "
+                                   "step issues NCCL collectives, which are kept out of these captures")
         # a positional wrapper is graphed (make_graphed_callables rebinds the forward of the module it is
         # given and passes tensors positionally); `self` stays usable in eager mode and shares logit_scale
-        return torch.cuda.make_graphed_callables(_Positional(self), (image_emb.detach().clone().requires_grad_(),
-                                                                     profile_emb.detach().clone().requires_grad_()))
+        return torch.cuda.make_graphed_callables(_Positional(self, buckets),
+                                                 (image_emb.detach().clone().requires_grad_(),
+                                                  profile_emb.detach().clone().requires_grad_()))
 
     def extra_repr(self) -> str:
         return f"precision={self.precision}, sharded={self.sharded}"
 
 
 class _Positional(Module):
-    def __init__(self, inner: Module) -> None:
+    def __init__(self, inner: Module, buckets: int = 1) -> None:
         super().__init__()
         self.inner = inner
+        self.buckets = buckets
 
     def forward(self, image_emb: Tensor, profile_emb: Tensor) -> Tensor:
-        return self.inner(image_emb=image_emb, profile_emb=profile_emb, buckets=1)
+        return self.inner(image_emb=image_emb, profile_emb=profile_emb, buckets=self.buckets)
 
 
 class SigLIPLoss(Module):

@@ -35,6 +35,12 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
+def _all_gather_rows_pair(a: torch.Tensor, b: torch.Tensor, group):
+    """all-gather two row blocks (two collectives: c10d's coalescing manager gave wrong data intermittently
+    with all_gather_into_tensor on this stack, so the two launches are not grouped)."""
+    return _all_gather_rows(a, group), _all_gather_rows(b, group)
+
+
 class XGpuScalars:
     """Peer-mapped symmetric buffer for the fused cross-GPU exchange of the two per-rank scalars
     (loss partial, d logit_scale partial) inside plk_infonce_grad_finish_pair_xgpu -- torch's
@@ -93,20 +99,25 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
             if reduce_scalars:
                 dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
         return loss, (x, y, ls, st, scal, (True, n, d, B, bs, off, mode, group))
+    # General case: one exchange each way.  Four collectives per step instead of seven:
+    #   the two all-gathers of u_hat, v_hat; ONE all-reduce of [3, B] statistics -- partial
+    #   column sums, and the row sums / diagonal logits scattered at the owned offsets (zeros elsewhere), which
+    #   turns their all-gathers into the same sum; the scalar loss needs no collective at all: every rank
+    #   evaluates it over the B global rows from the reduced statistics (identical bits everywhere).
     st4 = torch.empty((4, n), device=x.device, dtype=torch.float32)
-    rs = torch.empty(n, device=x.device, dtype=torch.float32)
-    cs_all = torch.empty(B, device=x.device, dtype=torch.float32)
-    dg = torch.empty(n, device=x.device, dtype=torch.float32)
-    u, v = ops.l2norm_pair(x, y, mode, st4, rs, cs_all)      # also zero-fills the two sum-exp accumulators
+    stats = torch.empty((3, B), device=x.device, dtype=torch.float32)      # cs | rs | diag, global row order
+    cs_all, rs_all, dg_all = stats.unbind(0)
+    rs, dg = rs_all[off:off + n], dg_all[off:off + n]
+    u, v = ops.l2norm_pair(x, y, mode, st4, stats)            # also zero-fills `stats`
+    u_all, v_all = _all_gather_rows_pair(u, v, group)
     idx, nx, idy, ny = st4.unbind(0)
-    u_all = _all_gather_rows(u, group)
-    v_all = _all_gather_rows(v, group)
     ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls, rs, cs_all, dg, sums_zeroed=True)
-    dist.all_reduce(cs_all, op=dist.ReduceOp.SUM, group=group)
-    rs_all = _all_gather_rows(rs, group)
-    loss, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B, scal[0])
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    part, aux = ops.infonce_loss_local(rs, cs_all[off:off + n], dg, ls, B, scal[0])    # owned rows: partial + sum of own diagonal
     if reduce_scalars:
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        loss, _ = ops.infonce_loss_local(rs_all, cs_all, dg_all, ls, B)                  # all rows: the global loss
+    else:
+        loss = part
     state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal,
              (False, n, d, B, bs, off, mode, group))
     return loss, state
