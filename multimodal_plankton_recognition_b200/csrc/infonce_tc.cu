@@ -1662,6 +1662,335 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
 }
 
 // =============================================================================================
+// backward, 448 < d <= 512 (eight 64-element chunks): "tc8".
+//
+// The [128 x 512] fp32 accumulator alone is all of TMEM, so a CTA owns one 256-column half of d (blockIdx.z)
+// and recomputes the logits for it, as infonce_grad_tc does.  What changes against that kernel (8300 cycles per
+// 128 x 128 tile) follows from the measured operand rates (see infonce_grad_tc4):
+//   * the first four K chunks of the owned rows are parked in TMEM (128 columns) and used in TS mode (64 cycles
+//     per MMA), only the last four stay in shared memory (SS mode, 128 cycles): S costs 3072 cycles, not 4096;
+//   * ONE logits buffer, handed back right after the epilogue's tcgen05.ld, makes room for them;
+//   * G . b_t consumes the streamed chunks in PAIRS, as MN-major operands of N = 128 (adjacent ring slots,
+//     LBO = one slot): 2 x 8 MMAs of 128 cycles instead of 4 x 8 of 96;
+//   * G is double buffered in shared memory, so the epilogue of tile t+1 never waits for G . b_t.
+//     TMEM  [0,128) S | [128,256) owned rows, K chunks 0..3 | [256,512) acc [128 x 256] fp32
+//     smem  owned rows, K chunks 4..7 (64 KiB) | 2 G buffers (64 KiB; K chunks 0..3 are staged here first)
+//           | ring of six 16 KiB chunks (cluster multicast) | 2 KiB barriers  = 227 KiB
+// Ring order (producer and MMA agree): S(0), S(1), GV(0), S(2), GV(1), ..., GV(T-1), eight chunks per S,
+// four per GV -- the slot index stays even at every pair.
+// =============================================================================================
+struct Grad8Cfg {
+  static constexpr int KD = 8, KA = 4, DNC = 4, NST = 6;
+  static constexpr int kAHi = (KD - KA) * kChunkBytes;
+  static constexpr int kGBuf = 2 * kChunkBytes;
+  static constexpr int kAux = 2048;
+  static constexpr int kSmem = 1024 + kAHi + 2 * kGBuf + NST * kChunkBytes + kAux;
+  static_assert(kSmem <= kMaxSmem, "tc8 shared memory");
+  static_assert(KA * kChunkBytes <= 2 * kGBuf, "K chunks 0..3 of the owned rows are staged in the G buffers");
+  static_assert(2 * kGBuf + NST * kChunkBytes >= kTileRows * DNC * 64 * 4, "accumulator drain staging");
+};
+
+template <int CS, bool F16>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc8(
+    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols, int64_t d, int64_t bs,
+    int tiles_per_seg, const float* __restrict__ ls) {
+  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
+  using Cfg = Grad8Cfg;
+  constexpr int KD = Cfg::KD, KA = Cfg::KA, DNC = Cfg::DNC, NST = Cfg::NST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_a = smem;                                   // K chunks KA..KD-1 of the owned rows
+  uint8_t* sm_g = smem + Cfg::kAHi;                       // [2] G buffers
+  uint8_t* sm_ring = sm_g + 2 * Cfg::kGBuf;
+  uint8_t* aux = sm_ring + NST * kChunkBytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(aux);  // [NST]
+  uint64_t* bar_empty = bar_full + NST;                   // [NST]
+  uint64_t* bar_afull = bar_empty + NST;                  // [1] K chunks 0..3 landed in the G buffers
+  uint64_t* bar_ahi = bar_afull + 1;                      // [1] K chunks 4..7 resident
+  uint64_t* bar_a = bar_ahi + 1;                          // [1] K chunks 0..3 parked in TMEM
+  uint64_t* bar_sfull = bar_a + 1;                        // [1]
+  uint64_t* bar_sempty = bar_sfull + 1;                   // [1]
+  uint64_t* bar_gfull = bar_sempty + 1;                   // [2]
+  uint64_t* bar_accfull = bar_gfull + 2;                  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
+  float* rcs_s = reinterpret_cast<float*>(aux + 512);     // [2][128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)blockIdx.y * kTileRows;
+  const int h = blockIdx.z / ga.ndir;  // which 256-column half of d
+  int64_t jlo = 0, jhi = n_cols;  // clusters are only launched for the single-bucket case
+  if constexpr (CS == 1) row_block_cols(i0, n_rows, row_offset, bs, n_cols, jlo, jhi);
+  const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
+  const int t_begin = blockIdx.x * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;
+  const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
+  float* acc_out = g.acc + (int64_t)blockIdx.x * n_rows * d;
+  if (T == 0) {  // this segment has no tiles: its partial is zero (uniform across the CTA and the cluster)
+    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DNC * 64; e += kNumThreads) {
+      const int64_t rr = i0 + e / (DNC * 64), col = (int64_t)h * DNC * 64 + e % (DNC * 64);
+      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.ta);
+    tma_prefetch_desc(&g.tb);
+    for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_ahi, 1);
+    mbar_init(bar_a, kEpiThreads);
+    mbar_init(bar_sfull, 1);
+    mbar_init(bar_sempty, kEpiThreads / 32);   // one elected arrival per epilogue warp
+    mbar_init(bar_gfull, kEpiThreads / 32);
+    mbar_init(bar_gfull + 1, kEpiThreads / 32);
+    mbar_init(bar_accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kSCol = 0, kACol = 128, kAccCol = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_afull, KA * kChunkBytes);
+      for (int c = 0; c < KA; ++c) tma_load_2d(sm_g + c * kChunkBytes, &g.ta, bar_afull, c * kChunkK, (int)i0);
+      mbar_expect_tx(bar_ahi, Cfg::kAHi);
+      for (int c = KA; c < KD; ++c)
+        tma_load_2d(sm_a + (c - KA) * kChunkBytes, &g.ta, bar_ahi, c * kChunkK, (int)i0);
+      int st = 0; uint32_t ph = 0;
+      auto push = [&](int col_chunk, int j0) {
+        mbar_wait(bar_empty + st, ph ^ 1);
+        ring_load<CS>(sm_ring + st * kChunkBytes, &g.tb, &g.tbp, bar_full + st, col_chunk * kChunkK, j0, cta_rank);
+        if (++st == NST) { st = 0; ph ^= 1; }
+      };
+      for (int t = 0; t <= T; ++t) {
+        if (t < T) {
+          const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+          for (int c = 0; c < KD; ++c) push(c, j0);
+        }
+        if (t >= 1) {
+          const int j0 = (int)(jlo + (int64_t)(t_begin + t - 1) * kTileRows);
+          for (int dc = 0; dc < DNC; ++dc) push(h * DNC + dc, j0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // All 32 lanes run this loop (warp-uniform control flow, see elect_one); one elected lane issues.
+    constexpr uint32_t idesc_s = umma_idesc_16(128, 128, 0, 0, F16);
+    constexpr uint32_t idesc_g = umma_idesc_16(128, 128, 0, 1, F16);  // B = two adjacent chunks, MN-major
+    mbar_wait(bar_a, 0);
+    mbar_wait(bar_ahi, 0);
+    tc_fence_after();
+    const uint32_t s_tmem = tmem_base + kSCol, a_tmem0 = tmem_base + kACol;
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(sm_a), 16), b_lo0 = umma_desc_lo(smem_u32(sm_ring), 16);
+    const uint32_t g_lo0 = umma_desc_lo(smem_u32(sm_g), 16);
+    const uint32_t b2_lo0 = umma_desc_lo(smem_u32(sm_ring), kChunkBytes);   // LBO = the next ring slot
+    int st = 0; uint32_t ph = 0;
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        if (t >= 1) mbar_wait(bar_sempty, (t - 1) & 1);
+#pragma unroll 1
+        for (int c = 0; c < KD; ++c) {
+          mbar_wait(bar_full + st, ph);
+          tc_fence_after();
+          const uint32_t b_lo = b_lo0 + st * (kChunkBytes >> 4);
+          if (elect_one()) {
+            if (c < KA) {
+#pragma unroll
+              for (int k = 0; k < kChunkK / kUmmaK; ++k)
+                umma_bf16_ts(s_tmem, a_tmem0 + c * 32 + k * 8, b_lo + 2 * k, idesc_s, (c | k) != 0);
+            } else {
+              const uint32_t a_lo = a_lo0 + (c - KA) * (kChunkBytes >> 4);
+#pragma unroll
+              for (int k = 0; k < kChunkK / kUmmaK; ++k)
+                umma_bf16_lo(s_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_s, 1u);
+            }
+            ring_release<CS>(bar_empty + st);
+            if (c == KD - 1) umma_commit(bar_sfull);
+          }
+          __syncwarp();
+          if (++st == NST) { st = 0; ph ^= 1; }
+        }
+      }
+      if (t >= 1) {
+        const int u = t - 1;
+        mbar_wait(bar_gfull + (u & 1), (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_lo = g_lo0 + (u & 1) * (Cfg::kGBuf >> 4);
+#pragma unroll 1
+        for (int p = 0; p < DNC / 2; ++p) {
+          mbar_wait(bar_full + st, ph);
+          mbar_wait(bar_full + st + 1, ph);        // NST is even and st is even here: the pair never wraps
+          tc_fence_after();
+          const uint32_t b_lo = b2_lo0 + st * (kChunkBytes >> 4);
+          const uint32_t d_tmem = tmem_base + kAccCol + p * 128;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kTileRows / kUmmaK; ++k)
+              // A = G[128 x 128] K-major: K 0..63 in sub-tile 0, 64..127 in sub-tile 1
+              // B = two chunks [128 j x 64 cols] read MN-major as N = 128: 16 K-rows (j) = 2048 bytes per step
+              umma_bf16_lo(d_tmem, a_lo + (k >> 2) * (kChunkBytes >> 4) + (k & 3) * 2, b_lo + k * (2048 >> 4), idesc_g,
+                           (u | k) != 0);
+            ring_release<CS>(bar_empty + st);
+            ring_release<CS>(bar_empty + st + 1);
+          }
+          __syncwarp();
+          st += 2;
+          if (st == NST) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    if (elect_one()) umma_commit(bar_accfull);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int cc = (warp - 2) >> 2;          // which 32-column chunk of the tile this warp owns
+    const int r = q * 32 + lane;
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    float rrs = 0.f;
+    const bool siglip = ga.bias != nullptr;
+    if (i < n_rows) {
+      bucket_range(gi, bs, n_cols, lo, hi);
+      if (!siglip) rrs = 1.0f / g.rs[i];
+    }
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : (kShiftK - s) * kLog2e;
+    const bool want_gs = (g.gs != nullptr) && (h == 0);
+    float gs_local = 0.f, gsum_local = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    {  // park K chunks 0..3 of this thread's owned row in TMEM as packed pairs
+      mbar_wait(bar_afull, 0);
+      for (int c = cc; c < KA; c += 4) {
+        const uint8_t* rowp = sm_g + c * kChunkBytes + r * 128;
+        uint32_t pk[32];
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) {
+          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
+        }
+        tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+    }
+    float rc_next = 0.f;
+    if (cc == 0 && !siglip) {
+      const int64_t jc = jlo + (int64_t)t_begin * kTileRows + r;
+      rcs_s[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+    }
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      named_barrier_sync(1, kEpiThreads);   // rcs_s[buf] visible; everyone is done with tile t-1
+      if (cc == 0 && t + 1 < T && !siglip) {
+        const int64_t jc = j0 + kTileRows + r;
+        rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
+      }
+      mbar_wait(bar_sfull, t & 1);
+      tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + kSCol + cc * 32, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sempty);   // the logits buffer goes back to the MMA warp right away
+      uint32_t packed[16];
+      grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
+                               want_gs, gs_local, siglip, gsum_local);
+      // G buffer t&1 was last read by G.V(t-2), which the in-order tensor pipe ran before S(t) completed
+      uint8_t* grow = sm_g + buf * Cfg::kGBuf + (cc >> 1) * kChunkBytes + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
+        *reinterpret_cast<uint4*>(grow + chunk * 16) =
+            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_gfull + buf);
+      if (cc == 0 && t + 1 < T) rcs_s[(buf ^ 1) * 128 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+    }
+    // drain the resident accumulator: 2*DNC 32-column chunks over the four warps of a lane quadrant
+    mbar_wait(bar_accfull, 0);
+    tc_fence_after();
+    if (g.use_tacc) {
+#pragma unroll 1
+      for (int ch = cc; ch < DNC * 2; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        uint8_t* stage = sm_g + ch * kChunkBytes;     // 128 rows x 128 B in the idle G buffers + ring
+        uint8_t* rowp = stage + r * 128;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
+              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+        fence_proxy_async_smem();
+        named_barrier_sync(2 + cc, 128);
+        if (q == 0 && lane == 0 && i0 < n_rows) {
+          tma_store_3d(&g.tacc, stage, h * DNC * 64 + ch * 32, (int)i0, (int)blockIdx.x);
+          tma_store_commit();
+        }
+      }
+      if (q == 0 && lane == 0) tma_store_wait_all();
+    } else {
+#pragma unroll 1
+      for (int ch = cc; ch < DNC * 2; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        const int64_t col0 = (int64_t)h * DNC * 64 + ch * 32;
+        if (i < n_rows) {
+          float* dst = acc_out + i * d + col0;
+          if (col0 + 32 <= d && (d & 3) == 0) {
+#pragma unroll
+            for (int x = 0; x < 32; x += 4)
+              *reinterpret_cast<float4*>(dst + x) =
+                  make_float4(__uint_as_float(raw[x]), __uint_as_float(raw[x + 1]),
+                              __uint_as_float(raw[x + 2]), __uint_as_float(raw[x + 3]));
+          } else {
+#pragma unroll
+            for (int x = 0; x < 32; ++x)
+              if (col0 + x < d) dst[x] = __uint_as_float(raw[x]);
+          }
+        }
+      }
+    }
+    if (want_gs) {
+      gs_local *= s;  // sum G * S with S = s * (u.v)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+        gsum_local += __shfl_xor_sync(0xffffffffu, gsum_local, o);
+      }
+      if (lane == 0) {
+        atomicAdd(g.gs, gs_local);
+        if (siglip) atomicAdd(g.gs + 1, gsum_local);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+
+// =============================================================================================
 // host launchers
 // =============================================================================================
 // widest column range [jlo, jhi) a 128-row block can need: the union of the buckets its rows touch
@@ -1670,12 +1999,22 @@ static int64_t max_col_span(int64_t bs, int64_t n_cols) {
   return span > n_cols ? n_cols : span;
 }
 
-static int pick_segments(int64_t row_blocks, int64_t max_tiles, int z) {
-  // enough (row block, column segment) work items to cover the 148 SMs once
-  int64_t nseg = 148 / (row_blocks * z);
-  if (nseg < 1) nseg = 1;
-  if (nseg > max_tiles) nseg = max_tiles;
-  return (int)nseg;
+static int pick_segments(int64_t row_blocks, int64_t max_tiles, int z, int64_t cap = 16) {
+  // Column segments per (row block, direction / d-half) work item.  A CTA costs its tiles plus a fixed
+  // set-up + drain of about four tiles; the grid runs in waves of 148 CTAs (one per SM).  Pick the split
+  // that minimises waves x (tiles per CTA + 4): it fills the SMs at small batches (C2: 32 row blocks ->
+  // 4 segments forward, 2 x 2 backward) and trims the last partial wave at large ones (512 items: one
+  // segment = 3.46 -> 4 waves of 260, two segments = 6.92 -> 7 waves of 132).
+  const int64_t items = row_blocks * z;
+  int64_t best = 1, best_cost = -1;
+  // `cap`: the backward writes one fp32 partial slab per segment, which the gradient tail reads back
+  const int64_t nmax = max_tiles < cap ? max_tiles : cap;
+  for (int64_t n = 1; n <= nmax; ++n) {
+    const int64_t waves = ceil_div(items * n, 148);
+    const int64_t cost = waves * (ceil_div(max_tiles, n) + 4);
+    if (best_cost < 0 || cost < best_cost) { best = n; best_cost = cost; }
+  }
+  return (int)best;
 }
 
 static int check_tc_shape(int64_t ld, int64_t d) {
@@ -1843,6 +2182,27 @@ static int launch_grad4(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
              : launch_grad4_m<KD, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
 }
 
+template <int CS, bool F16>
+static int launch_grad8(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st) {
+  auto kern = infonce_grad_tc8<CS, F16>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad8Cfg::kSmem));
+    configured = true;
+  }
+  int rc = launch_kernel(kern, grid, dim3(kNumThreads), Grad8Cfg::kSmem, st, CS, ga, n_rows, row_offset, n_cols, d, bs,
+                         tps, ls);
+  if (rc) return rc;
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+// PLK_GRAD_TC8=0: the previous streaming kernel (infonce_grad_tc<8,4>) for 448 < d <= 512
+static bool use_grad_tc8() {
+  static const bool v = getenv("PLK_GRAD_TC8") == nullptr || getenv("PLK_GRAD_TC8")[0] != '0';
+  return v;
+}
+
 // PLK_GRAD_TC2=1 selects the previous d <= 256 backward (owned rows read from shared memory, 128-column
 // tiles) for A/B measurements; the default is infonce_grad_tc3.
 static bool use_grad_tc2() {
@@ -1863,7 +2223,7 @@ int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int n
   const int z = (ld > 256 ? 2 : 1) * ndir;
   const int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols((int)(ld / kChunkK)));
-  return pick_segments(row_blocks, max_tiles, z);
+  return pick_segments(row_blocks, max_tiles, z, 4);
 }
 
 static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_t n_rows,
@@ -1886,7 +2246,7 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
   const int kd = (int)(ld / kChunkK);
   const int z = (kd > 4 ? 2 : 1) * ga.ndir;
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols(kd));
-  const int nseg = pick_segments(row_blocks, max_tiles, z);
+  const int nseg = pick_segments(row_blocks, max_tiles, z, 4);
   const int tps = (int)ceil_div(max_tiles, nseg);
   if (kd <= 4) {   // d <= 256: the whole [128 x d] accumulator is TMEM-resident, G never leaves tensor memory
     if (d % 32 == 0) {   // accumulator drain by TMA store (full 128-byte lines)
@@ -1928,6 +2288,19 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
       PLK_CASE2(1) PLK_CASE2(2) PLK_CASE2(3) PLK_CASE2(4)
 #undef PLK_CASE2
     }
+  }
+  if (kd == 8 && use_grad_tc8()) {
+    if (d % 32 == 0) {   // accumulator drain by TMA store (full 128-byte lines)
+      for (int k = 0; k < ga.ndir; ++k) {
+        if (((uintptr_t)ga.dir[k].acc & 15) != 0) continue;
+        int rc = make_tmap_f32_slabs(&ga.dir[k].tacc, ga.dir[k].acc, nseg, n_rows, d);
+        if (rc) return rc;
+        ga.dir[k].use_tacc = 1;
+      }
+      if (ga.ndir == 1) ga.dir[1] = ga.dir[0];
+    }
+    return csz == 2 ? launch_grad8<2, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st)
+                    : launch_grad8<1, F16>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st);
   }
   switch (kd) {
 #define PLK_CASE(KD, DNC)                                                                               \
