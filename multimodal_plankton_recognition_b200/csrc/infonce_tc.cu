@@ -2223,7 +2223,7 @@ int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int n
   const int z = (ld > 256 ? 2 : 1) * ndir;
   const int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols((int)(ld / kChunkK)));
-  return pick_segments(row_blocks, max_tiles, z, 4);
+  return pick_segments(row_blocks, max_tiles, z, 8);
 }
 
 static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_t n_rows,
@@ -2246,7 +2246,7 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
   const int kd = (int)(ld / kChunkK);
   const int z = (kd > 4 ? 2 : 1) * ga.ndir;
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols(kd));
-  const int nseg = pick_segments(row_blocks, max_tiles, z, 4);
+  const int nseg = pick_segments(row_blocks, max_tiles, z, 8);
   const int tps = (int)ceil_div(max_tiles, nseg);
   if (kd <= 4) {   // d <= 256: the whole [128 x d] accumulator is TMEM-resident, G never leaves tensor memory
     if (d % 32 == 0) {   // accumulator drain by TMA store (full 128-byte lines)

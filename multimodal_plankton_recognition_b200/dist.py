@@ -109,7 +109,11 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
     cs_all, rs_all, dg_all = stats.unbind(0)
     rs, dg = rs_all[off:off + n], dg_all[off:off + n]
     u, v = ops.l2norm_pair(x, y, mode, st4, stats)            # also zero-fills `stats`
-    u_all, v_all = _all_gather_rows_pair(u, v, group)
+    # the forward needs the gathered v_hat only; u_hat (the streamed operand of the backward's second
+    # direction) is gathered asynchronously under the forward kernel and waited for in sharded_bwd
+    v_all = _all_gather_rows(v, group)
+    u_all = torch.empty((B,) + tuple(u.shape[1:]), device=u.device, dtype=u.dtype)
+    u_work = dist.all_gather_into_tensor(u_all, u, group=group, async_op=True)
     idx, nx, idy, ny = st4.unbind(0)
     ops.infonce_fwd_local(u, v_all, mode, d, off, bs, ls, rs, cs_all, dg, sums_zeroed=True)
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
@@ -118,7 +122,7 @@ def sharded_fwd(image_emb, profile_emb, logit_scale, buckets, mode, group, reduc
         loss, _ = ops.infonce_loss_local(rs_all, cs_all, dg_all, ls, B)                  # all rows: the global loss
     else:
         loss = part
-    state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal,
+    state = (x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal, u_work,
              (False, n, d, B, bs, off, mode, group))
     return loss, state
 
@@ -148,15 +152,26 @@ def sharded_bwd(state, grad_out, grad_scale="ddp", out_dtypes=(torch.float32, to
                                                    loss_partial=scal[0:1] if xgpu is not None else None)
     else:
         go_emb = go * scale if scale != 1.0 else go
-        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal = state[:-1]
+        x, y, ls, u, v, u_all, v_all, idx, nx, idy, ny, rs_all, cs_all, dg, aux, scal, u_work = state[:-1]
+        if u_work is not None:
+            u_work.wait()        # the asynchronous all-gather of u_hat issued in sharded_fwd
         rs_own, cs_own = rs_all[off:off + n], cs_all[off:off + n]
         gs = aux[1:]
         acc_x, acc_y = ops.infonce_grad_pair_local(u, v_all, v, u_all, mode, d, off, bs, ls, rs_own, cs_all,
                                                    cs_own, rs_all, gs)
+        dls_work = None
+        if reduce_scalars and xgpu is None:
+            # d logit_scale is final once the recompute kernel has added sum G*S: reduce it over the ranks
+            # under the gradient tail instead of after it
+            dls_early = ops.infonce_dls(gs, aux[0:1], go, B)
+            dls_work = dist.all_reduce(dls_early, op=dist.ReduceOp.SUM, group=group, async_op=True)
         dx, dy, dls = ops.infonce_grad_finish_pair(acc_x, acc_y, x, y, (idx, nx), (idy, ny), dg, rs_own, cs_own, ls,
                                                    go_emb, go, B, gs, aux[0:1],
                                                    scal[1] if not reduce_scalars else None,
                                                    xgpu=xgpu, loss_partial=scal[0:1] if xgpu is not None else None)
+        if dls_work is not None:
+            dls_work.wait()
+            return dx.to(out_dtypes[0]), dy.to(out_dtypes[1]), dls_early
     dx, dy = dx.to(out_dtypes[0]), dy.to(out_dtypes[1])
     if reduce_scalars:
         if xgpu is not None and aligned:
