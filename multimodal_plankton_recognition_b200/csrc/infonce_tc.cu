@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, CS); }
-    mbar_init(bar_a, kEpiThreads);
+    // owned rows parked in TMEM -- in EVERY CTA of the cluster: a peer's multicast writes into this CTA's
+    // ring slots as well, including the tail slots the owned rows are staged in
+    mbar_init(bar_a, CS * (kEpiThreads / 32));
     mbar_init(bar_afull, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
     fence_barrier_init();
@@ -335,7 +337,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(bar_a);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_a);
+        if constexpr (CS > 1) mbar_arrive_cluster(bar_a, cta_rank ^ 1);
+      }
       if (threadIdx.x == 64) TR(2);
     }
     for (int t = 0; t < T; ++t) {
