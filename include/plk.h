@@ -282,6 +282,21 @@ int plk_siglip_grad_finish_pair(const float* acc_x, const float* acc_y, int part
                                 float* dbias_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * N1. Bias-free projection Linear fused with the normalisation that opens the loss:
+ *        replaces: nn.Linear(dim_out, dim_embed, bias=False) + F.normalize
+ *                  reference src/model.py:29-30,:38-39,:80-83 and src/coordination.py:33-34
+ *   emb_i = sum_k feat[i,k] w[j,k]  (16-bit operands, fp32 accumulation);  u = emb / max(||emb||, 1e-12)
+ *   feat16 [n, ldf], w16 [d, ldw]   op_dtype (PLK_BF16 / PLK_F16) rows, zero-padded to ceil(f/64)*64 columns
+ *   u16    [n, ldu] OUT  normalised operand of plk_infonce_fwd / plk_infonce_grad, ldu = ceil(d/64)*64
+ *   emb    [n, d]   OUT  raw fp32 embedding (the `x` / `partner` rows of plk_infonce_grad_finish)
+ *   inv_den, nrm [n] OUT as plk_l2norm_fwd.
+ * One tcgen05 kernel: accumulator [128 x d] in TMEM (d <= 512), squared norms taken in the epilogue.
+ * ------------------------------------------------------------------------------------------ */
+int plk_project_normalise(const void* feat16, int64_t ldf, const void* w16, int64_t ldw, int op_dtype,
+                          int64_t n, int64_t f, int64_t d, void* u16, int64_t ldu, float* emb,
+                          float* inv_den, float* nrm, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Staging host-resident batches into HBM under the running step (no reference counterpart: the
  * reference hands each batch to the device serially through Lightning's loop,
  * reference scripts/train_multi.py:78-85).  A stager owns a copy stream and per-slot events:

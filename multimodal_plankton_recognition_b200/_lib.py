@@ -19,7 +19,7 @@ _TRACE = os.environ.get("PLK_TRACE", "0") == "1"
 LIB_PATH = os.path.join(HERE, "libplk_trace.so" if _TRACE else "libplk.so")
 OBJ_DIR = os.path.join(HERE, "build_trace" if _TRACE else "build")
 SOURCES = ["api.cu", "elementwise.cu", "infonce_simt.cu", "topk_simt.cu", "tc_host.cu", "stager.cu",
-           "infonce_tc.cu", "topk_tc.cu"]
+           "infonce_tc.cu", "topk_tc.cu", "proj_tc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"] + (["-DPLK_TRACE"] if _TRACE else [])
 
@@ -114,6 +114,7 @@ SIGNATURES = {
     "plk_siglip_loss": (_int, [_vp, _i64, _vp, _vp]),
     "plk_siglip_grad_finish_pair": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "plk_project_normalise": (_int, [_vp, _i64, _vp, _i64, _int, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp]),
     "plk_stager_create": (_vp, [_int, _int]),
     "plk_stager_destroy": (None, [_vp]),
     "plk_stager_issue": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp, _sz]),

@@ -57,6 +57,25 @@ class CLIPLoss(Module):
                                           self.process_group, xgpu=self._peer_scalars(image_emb, int(buckets)))
         return ops.clip_loss(image_emb, profile_emb, self.logit_scale, int(buckets), mode)
 
+    def forward_projected(self, image_feat: Tensor, profile_feat: Tensor, image_projection: Module,
+                          profile_projection: Module, buckets: int = 1) -> Tensor:
+        """the loss of ``image_projection(image_feat)`` / ``profile_projection(
+        profile_feat)`` -- the two bias-free ``nn.Linear`` of reference src/model.py:29-30,:38-39 applied at
+        :80-83 -- with each projection GEMM and the normalisation that opens the loss fused in one tcgen05
+        kernel (`ops.project_normalise`).  Gradients flow to both feature tensors, both weights and
+        ``logit_scale``.  Single GPU; `INTEGRATION.md` shows the call in ``training_step``."""
+        for proj in (image_projection, profile_projection):
+            if getattr(proj, "bias", None) is not None:
+                raise ValueError("forward_projected fuses bias-free projections (the reference's nn.Linear(bias=False))")
+        if image_feat.dim() != 2 or profile_feat.dim() != 2 or image_feat.size(0) != profile_feat.size(0):
+            raise ValueError("expected [B, f_image] and [B, f_profile] features")
+        assert image_feat.size(0) % buckets == 0, \
+            "Batch size must be divisible by number of buckets!"
+        if self.sharded:
+            raise RuntimeError("forward_projected is single-GPU; project first and call the sharded loss")
+        return ops.clip_loss_projected(image_feat, profile_feat, image_projection.weight, profile_projection.weight,
+                                       self.logit_scale, int(buckets), ops.MODES[self.precision])
+
     def _peer_scalars(self, image_emb: Tensor, buckets: int):
         """The peer-memory scalar exchange for the bucket-aligned sharded case (every rank takes the same
         decision from the same shapes; creating it is a collective).  None -> NCCL all-reduces."""

@@ -459,6 +459,93 @@ def siglip_loss(image_emb, profile_emb, logit_scale, bias, buckets: int = 1, mod
     return _SigLipLossFn.apply(image_emb, profile_emb, logit_scale, bias, int(buckets), int(mode))
 
 
+# ---------------------------------------------------------------------------------------------
+# N1 (SURVEY section 8f): projection Linears fused with the normalisation that opens the loss
+# ---------------------------------------------------------------------------------------------
+def _pad64_cast(t: torch.Tensor, dtype) -> torch.Tensor:
+    """[r, f] -> 16-bit [r, ceil(f/64)*64], zero padded (one cast pass; the TMA boxes are 64 elements wide)."""
+    r, f = t.shape
+    fp = (f + 63) // 64 * 64
+    if fp == f:
+        return t.detach().to(dtype).contiguous()
+    out = torch.zeros((r, fp), device=t.device, dtype=dtype)
+    out[:, :f] = t.detach()
+    return out
+
+
+def project_normalise(feat: torch.Tensor, weight: torch.Tensor, mode: int):
+    """emb = feat @ weight.T (nn.Linear without bias) and u = emb / max(||emb||, eps) in one tcgen05 kernel
+    (plk_project_normalise).  -> (u [n, ld] operand dtype, emb [n, d] fp32, inv_den [n], nrm [n]).
+    fp32 mode: the projection is a plain fp32 matmul followed by plk_l2norm_fwd."""
+    lib = _lib.load()
+    n, f = feat.shape
+    d = weight.shape[0]
+    if mode == PLK_F32:
+        emb = torch.matmul(feat.detach().float(), weight.detach().float().t()).contiguous()
+        u, inv_den, nrm, _ = l2norm(emb, mode)
+        return u, emb, inv_den, nrm
+    odt = OP_TORCH_DTYPE[mode]
+    x16, w16 = _pad64_cast(feat, odt), _pad64_cast(weight, odt)
+    ld = padded_width(d, mode)
+    u = torch.empty((n, ld), device=feat.device, dtype=odt)
+    emb = torch.empty((n, d), device=feat.device, dtype=torch.float32)
+    inv_den = torch.empty(n, device=feat.device, dtype=torch.float32)
+    nrm = torch.empty(n, device=feat.device, dtype=torch.float32)
+    with torch.cuda.device(feat.device):
+        lib.check(lib.plk_project_normalise(x16.data_ptr(), x16.stride(0), w16.data_ptr(), w16.stride(0), mode, n, f, d,
+                                            u.data_ptr(), ld, emb.data_ptr(), inv_den.data_ptr(), nrm.data_ptr(),
+                                            _stream(feat)), "plk_project_normalise")
+    return u, emb, inv_den, nrm
+
+
+class _ProjectedClipLossFn(torch.autograd.Function):
+    """loss(image_feat @ Wi^T, profile_feat @ Wp^T): fused projection + normalisation forward, the loss kernels
+    on the resulting operands, and in the backward dW = d_emb^T feat, d_feat = d_emb W from the embedding
+    gradients the gradient tail produces (two library GEMMs per modality: off the similarity path)."""
+
+    @staticmethod
+    def forward(ctx, image_feat, profile_feat, w_i, w_p, logit_scale, buckets, mode):
+        _require_cuda(image_feat, profile_feat, w_i, w_p, logit_scale)
+        B = image_feat.shape[0]
+        d = w_i.shape[0]
+        bs = B // buckets
+        ls = logit_scale.detach().float()
+        u, x, idx, nx = project_normalise(image_feat, w_i, mode)
+        v, y, idy, ny = project_normalise(profile_feat, w_p, mode)
+        sums = torch.zeros((2, B), device=x.device, dtype=torch.float32)
+        dg = torch.empty(B, device=x.device, dtype=torch.float32)
+        infonce_fwd_local(u, v, mode, d, 0, bs, ls, sums[0], sums[1], dg, sums_zeroed=True)
+        loss, aux = infonce_loss_local(sums[0], sums[1], dg, ls, B)
+        ctx.save_for_backward(image_feat, profile_feat, w_i, w_p, ls, u, v, x, y, idx, nx, idy, ny, sums, dg, aux)
+        ctx.meta = (bs, mode, logit_scale.dtype)
+        return loss
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_loss):
+        image_feat, profile_feat, w_i, w_p, ls, u, v, x, y, idx, nx, idy, ny, sums, dg, aux = ctx.saved_tensors
+        bs, mode, dtl = ctx.meta
+        B, d = x.shape
+        go = g_loss.detach().float().reshape(1).contiguous()
+        gs = aux[1:].clone()
+        acc_x, acc_y = infonce_grad_pair_local(u, v, v, u, mode, d, 0, bs, ls, sums[0], sums[1], sums[1], sums[0], gs)
+        dx, dy, dls = infonce_grad_finish_pair(acc_x, acc_y, x, y, (idx, nx), (idy, ny), dg, sums[0], sums[1], ls, go,
+                                               go, B, gs, aux[0:1])
+        out = []
+        for demb, feat, w in ((dx, image_feat, w_i), (dy, profile_feat, w_p)):
+            out.append((torch.matmul(demb, w.detach().float()).to(feat.dtype),              # d feat  [B, f]
+                        torch.matmul(demb.t(), feat.detach().float()).to(w.dtype)))         # d W     [d, f]
+        return out[0][0], out[1][0], out[0][1], out[1][1], dls.to(dtl), None, None
+
+
+def clip_loss_projected(image_feat, profile_feat, image_weight, profile_weight, logit_scale, buckets: int = 1,
+                        mode: int = PLK_BF16) -> torch.Tensor:
+    """Symmetric InfoNCE of the PROJECTED features: reference src/model.py:80-83 (the two bias-free
+    `nn.Linear`) followed by src/coordination.py:26-47, with projection + normalisation in one kernel."""
+    return _ProjectedClipLossFn.apply(image_feat, profile_feat, image_weight, profile_weight, logit_scale,
+                                      int(buckets), int(mode))
+
+
 def clip_loss(image_emb, profile_emb, logit_scale, buckets: int = 1, mode: int = PLK_BF16) -> torch.Tensor:
     """Symmetric InfoNCE of reference src/coordination.py:26-47 on the fused CUDA path.  Under
     torch.compile the registered custom ops are used (traceable); in eager mode the lean path."""

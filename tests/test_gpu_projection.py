@@ -1,0 +1,101 @@
+"""GPU parity of SURVEY section 8f row N1: the bias-free projection Linears (reference src/model.py:29-30,:38-39,:80-83)
+fused with the normalisation that opens the loss (`CLIPLoss.forward_projected` -> plk_project_normalise).
+Oracle: fp64 `feat @ W.T` followed by the closed form of the reference loss, chain rule for the weights and
+the features.  Tolerances as for the loss: 1e-5 relative in fp32 mode, 2e-3 with 16-bit operands."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import infonce as oinf
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-5, "bf16": 2e-3, "fp16": 2e-3}
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _oracle(fi, fp, wi, wp, ls, buckets):
+    x = fi.astype(np.float64) @ wi.astype(np.float64).T
+    y = fp.astype(np.float64) @ wp.astype(np.float64).T
+    ref = oinf.clip_loss_closed_form(x, y, ls, buckets)
+    return dict(loss=ref["loss"], d_fi=ref["d_image"] @ wi, d_fp=ref["d_profile"] @ wp,
+                d_wi=ref["d_image"].T @ fi, d_wp=ref["d_profile"].T @ fp, d_ls=ref["d_logit_scale"], x=x, y=y)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
+@pytest.mark.parametrize("B,f_i,f_p,d,buckets", [
+    (512, 1280, 192, 256, 1),      # EfficientNet-B0 / small profile encoder widths, the BASELINE d
+    (256, 192, 256, 512, 1),       # d = 512: the accumulator is all of TMEM, two MMAs per K step
+    (300, 200, 72, 96, 3),         # nothing a multiple of the tile
+    (384, 320, 64, 320, 2),        # width between 256 and 512 (second weight box narrower than the first)
+])
+def test_projected_loss_matches_oracle(B, f_i, f_p, d, buckets, precision):
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    r = np.random.default_rng(B + d)
+    z = r.standard_normal((B, 64))
+    fi = (z @ r.standard_normal((64, f_i)) / 8 + 0.3 * r.standard_normal((B, f_i))).astype(np.float32)
+    fp = (z @ r.standard_normal((64, f_p)) / 8 + 0.3 * r.standard_normal((B, f_p))).astype(np.float32)
+    wi = (r.standard_normal((d, f_i)) / np.sqrt(f_i)).astype(np.float32)
+    wp = (r.standard_normal((d, f_p)) / np.sqrt(f_p)).astype(np.float32)
+    ref = _oracle(fi, fp, wi, wp, 1.0, buckets)
+    dev = torch.device("cuda:0")
+    mod = CLIPLoss(precision=precision).to(dev)
+    pi = torch.nn.Linear(f_i, d, bias=False).to(dev)
+    pp = torch.nn.Linear(f_p, d, bias=False).to(dev)
+    with torch.no_grad():
+        pi.weight.copy_(torch.tensor(wi))
+        pp.weight.copy_(torch.tensor(wp))
+    xi = torch.tensor(fi, device=dev, requires_grad=True)
+    xp = torch.tensor(fp, device=dev, requires_grad=True)
+    loss = mod.forward_projected(xi, xp, pi, pp, buckets=buckets)
+    loss.backward()
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    assert abs(float(loss) - ref["loss"]) / abs(ref["loss"]) < tol, (float(loss), ref["loss"])
+    for name, got, want in (("d_feat_image", xi.grad, ref["d_fi"]), ("d_feat_profile", xp.grad, ref["d_fp"]),
+                            ("d_W_image", pi.weight.grad, ref["d_wi"]), ("d_W_profile", pp.weight.grad, ref["d_wp"])):
+        assert _rel(got.float().cpu().numpy(), want) < tol, (name, _rel(got.float().cpu().numpy(), want))
+    assert abs(float(mod.logit_scale.grad) - ref["d_ls"]) <= tol * max(abs(ref["d_ls"]), 1e-3)
+    # same numbers as projecting with nn.Linear and calling the module the reference way (fp32: same kernels)
+    if precision == "fp32":
+        x2, p2 = xi.detach().clone().requires_grad_(), xp.detach().clone().requires_grad_()
+        loss2 = mod(image_emb=pi(x2), profile_emb=pp(p2), buckets=buckets)
+        assert float(loss2) == pytest.approx(float(loss), rel=1e-5)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_project_normalise_kernel_outputs(precision):
+    """plk_project_normalise alone: raw embedding vs the fp64 product of the ROUNDED operands (fp32 accumulation:
+    1e-5), statistics, and the normalised 16-bit operand incl. its zero padding."""
+    from multimodal_plankton_recognition_b200 import ops
+    r = np.random.default_rng(4)
+    n, f, d = 333, 200, 96
+    dev = torch.device("cuda:0")
+    feat = torch.tensor(r.standard_normal((n, f)), device=dev, dtype=torch.float32)
+    w = torch.tensor(r.standard_normal((d, f)) / np.sqrt(f), device=dev, dtype=torch.float32)
+    mode = ops.MODES[precision]
+    u, emb, inv_den, nrm = ops.project_normalise(feat, w, mode)
+    torch.cuda.synchronize()
+    odt = ops.OP_TORCH_DTYPE[mode]
+    want = feat.to(odt).double() @ w.to(odt).double().t()
+    assert float((emb.double() - want).abs().max() / want.abs().max()) < 1e-5
+    wn = want.norm(dim=1)
+    assert float((nrm.double() - wn).abs().max() / wn.max()) < 1e-5
+    assert float((inv_den.double() - 1 / wn).abs().max() * wn.max()) < 1e-4
+    assert u.shape == (n, 128) and float(u[:, d:].abs().max()) == 0.0
+    un = (want / wn[:, None])
+    assert float((u[:, :d].double() - un).abs().max()) < (4e-3 if precision == "bf16" else 5e-4)
+
+
+def test_projection_error_behaviour():
+    from multimodal_plankton_recognition_b200 import CLIPLoss
+    dev = torch.device("cuda:0")
+    mod = CLIPLoss().to(dev)
+    x = torch.randn(12, 8, device=dev)
+    with pytest.raises(ValueError, match="bias-free"):
+        mod.forward_projected(x, x, torch.nn.Linear(8, 4).to(dev), torch.nn.Linear(8, 4, bias=False).to(dev))
+    with pytest.raises(AssertionError, match="divisible"):
+        mod.forward_projected(x, x, torch.nn.Linear(8, 4, bias=False).to(dev), torch.nn.Linear(8, 4, bias=False).to(dev),
+                              buckets=5)
