@@ -1,7 +1,10 @@
 """GPU parity of SURVEY section 8f row N1: the bias-free projection Linears (reference src/model.py:29-30,:38-39,:80-83)
 fused with the normalisation that opens the loss (`CLIPLoss.forward_projected` -> plk_project_normalise).
 Oracle: fp64 `feat @ W.T` followed by the closed form of the reference loss, chain rule for the weights and
-the features.  Tolerances as for the loss: 1e-5 relative in fp32 mode, 2e-3 with 16-bit operands."""
+the features.  Tolerances: 1e-5 relative in fp32 mode, 2e-3 with fp16 operands (the reference's own '16-mixed'
+precision); bf16 mode chains TWO bf16-operand GEMMs (features x weight, then the similarity of the rounded
+normalised embeddings), each perturbing the logits by ~s * 1e-4: its gradients are asserted at the declared
+bf16 constant of tests/test_gpu_loss.py (4.5e-3; measured 3.0e-3), the loss at 2e-3."""
 import numpy as np
 import pytest
 import torch
@@ -10,6 +13,7 @@ from oracle import infonce as oinf
 
 pytestmark = pytest.mark.gpu
 TOL = {"fp32": 1e-5, "bf16": 2e-3, "fp16": 2e-3}
+GRAD_TOL = {"fp32": 1e-5, "bf16": 4.5e-3, "fp16": 2e-3}
 
 
 def _rel(a, b):
@@ -53,7 +57,8 @@ def test_projected_loss_matches_oracle(B, f_i, f_p, d, buckets, precision):
     loss.backward()
     torch.cuda.synchronize()
     tol = TOL[precision]
-    assert abs(float(loss) - ref["loss"]) / abs(ref["loss"]) < tol, (float(loss), ref["loss"])
+    assert abs(float(loss.detach()) - ref["loss"]) / abs(ref["loss"]) < tol, (float(loss.detach()), ref["loss"])
+    tol = GRAD_TOL[precision]
     for name, got, want in (("d_feat_image", xi.grad, ref["d_fi"]), ("d_feat_profile", xp.grad, ref["d_fp"]),
                             ("d_W_image", pi.weight.grad, ref["d_wi"]), ("d_W_profile", pp.weight.grad, ref["d_wp"])):
         assert _rel(got.float().cpu().numpy(), want) < tol, (name, _rel(got.float().cpu().numpy(), want))
