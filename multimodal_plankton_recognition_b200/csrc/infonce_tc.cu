@@ -969,7 +969,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
           tma_store_commit();
         }
       }
-      if (q == 0 && lane == 0) tma_store_wait_all();
+      if (q == 0 && lane == 0) tma_store_wait_read();
     } else {
 #pragma unroll 1
     for (int ch = cc; ch < 2 * KD; ch += 4) {
@@ -1299,7 +1299,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc3(
           tma_store_commit();
         }
       }
-      if (q == 0 && lane == 0) tma_store_wait_all();
+      if (q == 0 && lane == 0) tma_store_wait_read();
     } else {
 #pragma unroll 1
       for (int ch = e; ch < 2 * KD; ch += 4) {
@@ -1619,7 +1619,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
           tma_store_commit();
         }
       }
-      if (q == 0 && lane == 0) tma_store_wait_all();
+      if (q == 0 && lane == 0) tma_store_wait_read();
     } else {
 #pragma unroll 1
       for (int ch = cc; ch < 2 * KD; ch += 4) {
@@ -1949,7 +1949,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc8(
           tma_store_commit();
         }
       }
-      if (q == 0 && lane == 0) tma_store_wait_all();
+      if (q == 0 && lane == 0) tma_store_wait_read();
     } else {
 #pragma unroll 1
       for (int ch = cc; ch < DNC * 2; ch += 4) {

@@ -100,6 +100,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Only until the staged shared memory has been READ: the CTA may then reuse it or exit; the global writes
+// finish on their own and are complete, like every other write of the grid, when the grid is.
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // Multicast variant: the box is written at the same CTA-relative offset in every CTA of `mask`
 // and complete_tx is signalled on the mbarrier at the same offset in each of them.

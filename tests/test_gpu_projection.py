@@ -62,7 +62,10 @@ def test_projected_loss_matches_oracle(B, f_i, f_p, d, buckets, precision):
     for name, got, want in (("d_feat_image", xi.grad, ref["d_fi"]), ("d_feat_profile", xp.grad, ref["d_fp"]),
                             ("d_W_image", pi.weight.grad, ref["d_wi"]), ("d_W_profile", pp.weight.grad, ref["d_wp"])):
         assert _rel(got.float().cpu().numpy(), want) < tol, (name, _rel(got.float().cpu().numpy(), want))
-    assert abs(float(mod.logit_scale.grad) - ref["d_ls"]) <= tol * max(abs(ref["d_ls"]), 1e-3)
+    # d logit_scale = sum G S - 2 sum S_ii is a small difference of O(1) sums on this data (|ref| ~ 5e-3): the
+    # 16-bit modes are held to an absolute error of tol x 2e-2, i.e. tol relative to the scale of its terms
+    floor = 1e-3 if precision == "fp32" else 2e-2
+    assert abs(float(mod.logit_scale.grad) - ref["d_ls"]) <= tol * max(abs(ref["d_ls"]), floor)
     # same numbers as projecting with nn.Linear and calling the module the reference way (fp32: same kernels)
     if precision == "fp32":
         x2, p2 = xi.detach().clone().requires_grad_(), xp.detach().clone().requires_grad_()
