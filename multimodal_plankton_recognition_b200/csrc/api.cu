@@ -117,8 +117,8 @@ int plk_infonce_grad_pair(const void* a0, const void* b0, const void* a1, const 
 // ---- the whole single-GPU loss step: layout of the saved state + the two composite calls ----
 namespace {
 struct ClipState {
-  size_t u, v, stats, aux, bytes;
-  int64_t ld;
+  size_t u, v, stats, aux, cnt, bytes;
+  int64_t ld, n_cnt;
   ClipState(int op_dtype, int64_t B, int64_t d) {
     const size_t esz = op_dtype == PLK_F32 ? 4 : 2;
     ld = op_dtype == PLK_F32 ? d : (d + 63) / 64 * 64;
@@ -127,7 +127,9 @@ struct ClipState {
     v = up((size_t)B * ld * esz);
     stats = v + up((size_t)B * ld * esz);
     aux = stats + up((size_t)7 * B * 4);
-    bytes = aux + 256;
+    cnt = aux + 256;                               // counters of the fused gradient tail (zero between calls)
+    n_cnt = 2 * ((B + 127) / 128) + 1;
+    bytes = cnt + up((size_t)n_cnt * 4);
   }
 };
 int clip_parts(int op_dtype, int64_t B, int64_t d, int64_t bs) {
@@ -160,8 +162,9 @@ static int clip_forward_impl(const float* x, const float* y, int64_t batch, int6
   float* st = (float*)(base + L.stats);     // rows: 1/den_x, |x|, 1/den_y, |y|, row sum-exp, col sum-exp, diag
   float* aux = (float*)(base + L.aux);      // (sum of diagonal logits, gs accumulator)
   const int64_t B = batch;
+  // one launch also zero-fills the two sum-exp rows (adjacent: 2B floats) and the fused tail's counters
   int rc = plk_l2norm_pair_fwd(x, y, B, d, ldx, base + L.u, base + L.v, op_dtype, L.ld, st, st + B, st + 2 * B,
-                               st + 3 * B, st + 4 * B, B, st + 5 * B, B, stream);
+                               st + 3 * B, st + 4 * B, 2 * B, (float*)(base + L.cnt), L.n_cnt, stream);
   if (rc) return rc;
   rc = plk_infonce_fwd(base + L.u, base + L.v, op_dtype, L.ld, B, 0, B, d, bucket_size, logit_scale, st + 4 * B,
                        st + 5 * B, st + 6 * B, 1, stream);
@@ -211,6 +214,20 @@ static int clip_backward_impl(const float* grad_out, const float* grad_out_emb, 
   const float *rs = st + 4 * B, *cs = st + 5 * B;
   int rc;
   static const bool overlap = getenv("PLK_PDL") == nullptr || getenv("PLK_PDL")[0] != '0';
+  if (op_dtype != PLK_F32 && peer_bufs == nullptr && batch_global == batch &&
+      grad_tail_fusable(B, B, d, bucket_size, ldx, x, y, dx, dy, workspace)) {
+    // d <= 256, one bucket: the gradient tail runs inside the recompute kernel (the last column segment of a
+    // row block adds the partial slabs and finishes its 128 rows; the last tail produces d logit_scale) --
+    // no second launch, and the slabs are read back while they are still being produced elsewhere
+    GradTailHost th;
+    th.x = x; th.y = y; th.ldx = ldx; th.batch = batch_global;
+    th.inv_den_x = st; th.nrm_x = st + B; th.inv_den_y = st + 2 * B; th.nrm_y = st + 3 * B; th.diag = st + 6 * B;
+    th.grad_out_emb = grad_out_emb; th.grad_out = grad_out; th.emb_scale = emb_scale;
+    th.diag_sum = aux; th.dx = dx; th.dy = dy; th.dls_out = dls; th.counters = (int*)(base + L.cnt);
+    return infonce_grad_pair_tc16_tail(base + L.u, base + L.v, base + L.v, base + L.u, op_dtype == PLK_F16, L.ld, B, d,
+                                       logit_scale, rs, cs, cs, rs, acc_x, acc_y, aux + 1, (cudaStream_t)stream,
+                                       overlap ? 1 : 0, th);
+  }
   if (op_dtype != PLK_F32) {
     // Everything this launch reads was produced by the forward call, at least one kernel back in the
     // stream; only the sum G*S accumulator is zeroed by the forward's last kernel.  The grid may

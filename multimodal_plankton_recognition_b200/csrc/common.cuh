@@ -61,6 +61,58 @@ __device__ __forceinline__ void tail_terms(const float* bias, float diag_i, cons
     coef = go * s / (2.0f * (float)batch);
   }
 }
+// One row of the gradient tail, the row (width NV*128 fp32) held in the registers of ONE warp:
+//   acc_i = sum of the `parts` partial slabs;  dU = coef (acc_i + dterm p / den_p);
+//   dx = (dU - u (u . dU)) / den   (no projection term below the eps clamp of F.normalize)
+// Shared by the stand-alone tail kernels (elementwise.cu) and the tail fused into infonce_grad_tc4.
+template <int NV>
+__device__ __forceinline__ void finish_row_vec(const float* __restrict__ acc_row, int parts, int64_t slab4,
+                                               const float* __restrict__ x_row, const float* __restrict__ p_row,
+                                               float coef, float dterm, float idx_, float idp, bool clamped,
+                                               float* __restrict__ dx_row, int lane) {
+  const float4* ar = reinterpret_cast<const float4*>(acc_row);
+  const float4* xr = reinterpret_cast<const float4*>(x_row);
+  const float4* pr = reinterpret_cast<const float4*>(p_row);
+  // every load of the row (first two partial slabs, own row, partner row) is issued before the first use
+  float4 acc[NV], acc1[NV], xv[NV], pv[NV];
+  const bool two = parts > 1;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i] = ar[lane + 32 * i];
+    acc1[i] = two ? ar[lane + 32 * i + slab4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    xv[i] = xr[lane + 32 * i];
+    pv[i] = pr[lane + 32 * i];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i].x += acc1[i].x; acc[i].y += acc1[i].y; acc[i].z += acc1[i].z; acc[i].w += acc1[i].w;
+  }
+  for (int p = 2; p < parts; ++p) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 t = ar[lane + 32 * i + p * slab4];
+      acc[i].x += t.x; acc[i].y += t.y; acc[i].z += t.z; acc[i].w += t.w;
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc[i].x = coef * fmaf(dterm, pv[i].x * idp, acc[i].x);
+    acc[i].y = coef * fmaf(dterm, pv[i].y * idp, acc[i].y);
+    acc[i].z = coef * fmaf(dterm, pv[i].z * idp, acc[i].z);
+    acc[i].w = coef * fmaf(dterm, pv[i].w * idp, acc[i].w);
+    xv[i].x *= idx_; xv[i].y *= idx_; xv[i].z *= idx_; xv[i].w *= idx_;
+    dot = fmaf(xv[i].x, acc[i].x, fmaf(xv[i].y, acc[i].y, fmaf(xv[i].z, acc[i].z, fmaf(xv[i].w, acc[i].w, dot))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if (clamped) dot = 0.f;
+  float4* dr = reinterpret_cast<float4*>(dx_row);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    dr[lane + 32 * i] = make_float4((acc[i].x - xv[i].x * dot) * idx_, (acc[i].y - xv[i].y * dot) * idx_,
+                                    (acc[i].z - xv[i].z * dot) * idx_, (acc[i].w - xv[i].w * dot) * idx_);
+}
 #endif
 
 // ---- programmatic dependent launch (sm_90+) ---------------------------------------------------
@@ -127,6 +179,23 @@ int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1, const
                            int64_t bs, const float* ls, const float* rs0, const float* cs0,
                            const float* rs1, const float* cs1, float* acc0, float* acc1, float* gs,
                            cudaStream_t st, int overlap_prev = 0, const float* siglip_bias = nullptr);
+// gradient tail fused into the d <= 256 recompute backward (infonce_tc.cu)
+struct GradTailHost {
+  const float *x, *y;                       // raw fp32 rows [B, ldx]
+  int64_t ldx, batch;
+  const float *inv_den_x, *nrm_x, *inv_den_y, *nrm_y, *diag;
+  const float *grad_out_emb, *grad_out;
+  float emb_scale;
+  const float* diag_sum;
+  float *dx, *dy, *dls_out;
+  int* counters;                            // 2 * ceil(B/128) + 1 ints, zero on entry, left zero
+};
+bool grad_tail_fusable(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int64_t ldx, const void* x, const void* y,
+                       const void* dx, const void* dy, const void* acc);
+int infonce_grad_pair_tc16_tail(const void* a0, const void* b0, const void* a1, const void* b1, int f16, int64_t ld,
+                                int64_t n_rows, int64_t d, const float* ls, const float* rs0, const float* cs0,
+                                const float* rs1, const float* cs1, float* acc0, float* acc1, float* gs, cudaStream_t st,
+                                int overlap_prev, const GradTailHost& th);
 // SigLIP variants (reference src/coordination.py:67-95): fp32 CUDA-core path / tensor-core forward
 int siglip_fwd_f32(const float* u, const float* v, int64_t ld, int64_t n_rows, int64_t row_offset, int64_t n_cols,
                    int64_t d, int64_t bs, const float* ls, const float* bias, float* diag, double* sums,

@@ -549,53 +549,11 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
-  const float4* ar = reinterpret_cast<const float4*>(a.acc[m] + row * d);
-  const float4* xr = reinterpret_cast<const float4*>(a.x[m] + row * ldx);
-  const float4* pr = reinterpret_cast<const float4*>(a.x[1 - m] + row * ldx);
-  const int64_t slab4 = n * d / 4;
-  // every load of the row (first two partial slabs, own row, partner row) is issued before the first use
-  float4 acc[NV], acc1[NV], xv[NV], pv[NV];
-  const bool two = parts > 1;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    acc[i] = ar[lane + 32 * i];
-    acc1[i] = two ? ar[lane + 32 * i + slab4] : make_float4(0.f, 0.f, 0.f, 0.f);
-    xv[i] = xr[lane + 32 * i];
-    pv[i] = pr[lane + 32 * i];
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    acc[i].x += acc1[i].x; acc[i].y += acc1[i].y; acc[i].z += acc1[i].z; acc[i].w += acc1[i].w;
-  }
-  for (int p = 2; p < parts; ++p) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 t = ar[lane + 32 * i + p * slab4];
-      acc[i].x += t.x; acc[i].y += t.y; acc[i].z += t.z; acc[i].w += t.w;
-    }
-  }
   const float s = expf(*ls);
   float coef, dterm;
   tail_terms(a.bias, diag[row], rs, cs, row, s, (*grad_out) * a.emb_scale, batch, coef, dterm);
-  const float idx_ = a.inv_den[m][row], idp = a.inv_den[1 - m][row];
-  const bool clamped = !(a.nrm[m][row] > kNormEps);
-  float dot = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    acc[i].x = coef * fmaf(dterm, pv[i].x * idp, acc[i].x);
-    acc[i].y = coef * fmaf(dterm, pv[i].y * idp, acc[i].y);
-    acc[i].z = coef * fmaf(dterm, pv[i].z * idp, acc[i].z);
-    acc[i].w = coef * fmaf(dterm, pv[i].w * idp, acc[i].w);
-    xv[i].x *= idx_; xv[i].y *= idx_; xv[i].z *= idx_; xv[i].w *= idx_;
-    dot = fmaf(xv[i].x, acc[i].x, fmaf(xv[i].y, acc[i].y, fmaf(xv[i].z, acc[i].z, fmaf(xv[i].w, acc[i].w, dot))));
-  }
-  dot = warp_sum(dot);
-  if (clamped) dot = 0.f;
-  float4* dr = reinterpret_cast<float4*>(a.dx[m] + row * d);
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-    dr[lane + 32 * i] = make_float4((acc[i].x - xv[i].x * dot) * idx_, (acc[i].y - xv[i].y * dot) * idx_,
-                                    (acc[i].z - xv[i].z * dot) * idx_, (acc[i].w - xv[i].w * dot) * idx_);
+  finish_row_vec<NV>(a.acc[m] + row * d, parts, n * d / 4, a.x[m] + row * ldx, a.x[1 - m] + row * ldx, coef, dterm,
+                     a.inv_den[m][row], a.inv_den[1 - m][row], !(a.nrm[m][row] > kNormEps), a.dx[m] + row * d, lane);
 }
 
 template <typename TI>

@@ -469,10 +469,32 @@ struct GradDir {
   float* acc;                // [nseg][n_rows][d] partial accumulators
   float* gs;                 // nullable: += sum G*S
 };
+// Gradient tail fused into infonce_grad_tc4 (InfoNCE, single bucket, d % 128 == 0): the LAST column segment of a
+// (row block, direction) to finish adds the partial slabs and runs the tail on the 128 rows; the last tail of
+// the grid produces d logit_scale.  Counters are zero on entry and left zero.
+struct GradTail {
+  int enabled;
+  int nseg;                 // column segments (= partial slabs) per row block and direction
+  int64_t ldx, batch;
+  const float* x[2];        // RAW rows of direction k's own modality (the partner is x[1 - k])
+  const float* inv_den[2];
+  const float* nrm[2];
+  float* dx[2];
+  const float* diag;        // S_ii, row sums R and column sums C of the owned rows (plk_infonce_grad_finish)
+  const float* R;
+  const float* C;
+  const float* grad_out_emb;
+  const float* grad_out;
+  float emb_scale;
+  const float* diag_sum;
+  float* dls_out;
+  int* counters;            // [ndir * row_blocks] arrivals per (direction, row block), then [1] finished tails
+};
 struct GradArgs {
   GradDir dir[2];
   int ndir;
   const float* bias;   // non-null: SigLIP weights (rs / cs unused, gs -> float[2] = (sum G*S, sum G))
+  GradTail tail;
 };
 template <int KD, int DNC>
 struct GradCfg {
@@ -1619,7 +1641,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
           tma_store_commit();
         }
       }
-      if (q == 0 && lane == 0) tma_store_wait_read();
+      if (q == 0 && lane == 0) {
+        if (ga.tail.enabled) tma_store_wait_all();   // the slab must be complete before this segment is counted
+        else tma_store_wait_read();
+      }
     } else {
 #pragma unroll 1
       for (int ch = cc; ch < 2 * KD; ch += 4) {
@@ -1653,6 +1678,54 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
       if (lane == 0) {
         atomicAdd(g.gs, gs_local);   // zeroed by the forward's last kernel (waited for above)
         if (siglip) atomicAdd(g.gs + 1, gsum_local);
+      }
+    }
+    if constexpr (!SIG && (KD % 2 == 0)) {
+      if (ga.tail.enabled) {
+        // ---- fused gradient tail: count this segment; the last one of the (direction, row block) finishes it
+        const GradTail& tl = ga.tail;
+        const int kdir = blockIdx.z % ga.ndir;
+        int* flag_s = reinterpret_cast<int*>(aux + 256);
+        named_barrier_sync(1, kEpiThreads);      // every warp's stores are complete, every sum G*S is added
+        if (threadIdx.x == 64) {
+          __threadfence();
+          const int old = atomicAdd(tl.counters + kdir * gridDim.y + blockIdx.y, 1);
+          *flag_s = (old == tl.nseg - 1);
+        }
+        named_barrier_sync(1, kEpiThreads);
+        if (*flag_s) {
+          __threadfence();
+          constexpr int NV = KD / 2;
+          const float go = (*tl.grad_out_emb) * tl.emb_scale;
+          const float* xo = tl.x[kdir];
+          const float* xp = tl.x[1 - kdir];
+          const int64_t slab4 = n_rows * d / 4;
+#pragma unroll 1
+          for (int rr = warp - 2; rr < kTileRows; rr += kEpiThreads / 32) {
+            const int64_t row = i0 + rr;
+            if (row >= n_rows) break;
+            float coef, dterm;
+            tail_terms(nullptr, tl.diag[row], tl.R, tl.C, row, s, go, tl.batch, coef, dterm);
+            finish_row_vec<NV>(g.acc + row * d, tl.nseg, slab4, xo + row * tl.ldx, xp + row * tl.ldx, coef, dterm,
+                               tl.inv_den[kdir][row], tl.inv_den[1 - kdir][row], !(tl.nrm[kdir][row] > kNormEps),
+                               tl.dx[kdir] + row * d, lane);
+          }
+          named_barrier_sync(1, kEpiThreads);
+          if (threadIdx.x == 64) {
+            const int total = ga.ndir * (int)gridDim.y;
+            __threadfence();
+            const int done = atomicAdd(tl.counters + total, 1);
+            tl.counters[kdir * gridDim.y + blockIdx.y] = 0;          // left zero for the next backward
+            if (done == total - 1) {   // the last tail of the grid: every sum G*S has been added
+              __threadfence();
+              const float gsv = *reinterpret_cast<volatile float*>(ga.dir[0].gs);
+              *tl.dls_out = (float)((double)(*tl.grad_out) / (2.0 * (double)tl.batch) *
+                                    ((double)gsv - 2.0 * (double)(*tl.diag_sum)));
+              *ga.dir[0].gs = 0.f;     // consumed: the accumulator is back to its zero-initialised state
+              tl.counters[total] = 0;
+            }
+          }
+        }
       }
     }
   }
@@ -2229,7 +2302,8 @@ int grad_parts_tc16(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int n
   const int z = (ld > 256 ? 2 : 1) * ndir;
   const int64_t row_blocks = ceil_div(n_rows, kTileRows);
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols((int)(ld / kChunkK)));
-  return pick_segments(row_blocks, max_tiles, z, 8);
+  const int64_t nseg = pick_segments(row_blocks, max_tiles, z, 8);
+  return (int)ceil_div(max_tiles, ceil_div(max_tiles, nseg));   // no empty trailing segment
 }
 
 static int fill_dir(GradDir& g, const void* a, const void* b, int64_t ld, int64_t n_rows,
@@ -2252,8 +2326,9 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
   const int kd = (int)(ld / kChunkK);
   const int z = (kd > 4 ? 2 : 1) * ga.ndir;
   const int64_t max_tiles = ceil_div(max_col_span(bs, n_cols), grad_tile_cols(kd));
-  const int nseg = pick_segments(row_blocks, max_tiles, z, 8);
+  int nseg = pick_segments(row_blocks, max_tiles, z, 8);
   const int tps = (int)ceil_div(max_tiles, nseg);
+  nseg = (int)ceil_div(max_tiles, tps);   // no empty trailing segment (grad_parts_tc16 reports the same count)
   if (kd <= 4) {   // d <= 256: the whole [128 x d] accumulator is TMEM-resident, G never leaves tensor memory
     if (d % 32 == 0) {   // accumulator drain by TMA store (full 128-byte lines)
       for (int k = 0; k < ga.ndir; ++k) {
@@ -2328,10 +2403,50 @@ int infonce_grad_tc16(const void* a, const void* b, int f16, int64_t ld, int64_t
   GradArgs ga;
   ga.ndir = 1;
   ga.bias = nullptr;
+  ga.tail = GradTail{};
   if ((rc = fill_dir(ga.dir[0], a, b, ld, n_rows, n_cols, rs, cs, acc, gs))) return rc;
   ga.dir[1] = ga.dir[0];
   return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st)
              : grad_launch_16<false>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st);
+}
+
+// Can the gradient tail run inside the backward kernel?  (InfoNCE, one bucket, d <= 256 with d % 128 == 0, fp32
+// rows that the vectorised tail accepts.)  OFF unless PLK_FUSE_TAIL=1: measured at B = 4096, d = 256 the fused
+// step takes 73.0 us against 69.6 us with the separate tail kernel -- the tail is latency-bound row work, and
+// inside the backward only the 64 last-arriving CTAs (1024 warps, eight rows each, one after the other) do it,
+// on the kernel's critical path, where the separate launch spreads 8192 rows over every SM at once.
+bool grad_tail_fusable(int64_t n_rows, int64_t n_cols, int64_t d, int64_t bs, int64_t ldx, const void* x, const void* y,
+                       const void* dx, const void* dy, const void* acc) {
+  static const bool on = getenv("PLK_FUSE_TAIL") != nullptr && getenv("PLK_FUSE_TAIL")[0] == '1';
+  if (!on || use_grad_tc2() || use_grad_tc3()) return false;
+  if (bs < n_cols || n_rows != n_cols || d % 128 != 0 || d > 256 || (ldx & 3)) return false;
+  return ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)dx | (uintptr_t)dy | (uintptr_t)acc) & 15) == 0);
+}
+
+int infonce_grad_pair_tc16_tail(const void* a0, const void* b0, const void* a1, const void* b1, int f16, int64_t ld,
+                                int64_t n_rows, int64_t d, const float* ls, const float* rs0, const float* cs0,
+                                const float* rs1, const float* cs1, float* acc0, float* acc1, float* gs, cudaStream_t st,
+                                int overlap_prev, const GradTailHost& th) {
+  int rc = check_tc_shape(ld, d);
+  if (rc) return rc;
+  GradArgs ga;
+  ga.ndir = 2;
+  ga.bias = nullptr;
+  if ((rc = fill_dir(ga.dir[0], a0, b0, ld, n_rows, n_rows, rs0, cs0, acc0, gs))) return rc;
+  if ((rc = fill_dir(ga.dir[1], a1, b1, ld, n_rows, n_rows, rs1, cs1, acc1, nullptr))) return rc;
+  GradTail& t = ga.tail;
+  t.enabled = 1;
+  t.nseg = grad_parts_tc16(n_rows, n_rows, d, n_rows, 2);
+  t.ldx = th.ldx; t.batch = th.batch;
+  t.x[0] = th.x; t.x[1] = th.y;
+  t.inv_den[0] = th.inv_den_x; t.inv_den[1] = th.inv_den_y;
+  t.nrm[0] = th.nrm_x; t.nrm[1] = th.nrm_y;
+  t.dx[0] = th.dx; t.dx[1] = th.dy;
+  t.diag = th.diag; t.R = rs0; t.C = cs0;
+  t.grad_out_emb = th.grad_out_emb; t.grad_out = th.grad_out; t.emb_scale = th.emb_scale;
+  t.diag_sum = th.diag_sum; t.dls_out = th.dls_out; t.counters = th.counters;
+  return f16 ? grad_launch_16<true>(ga, ld, n_rows, 0, n_rows, d, n_rows, ls, st, overlap_prev != 0)
+             : grad_launch_16<false>(ga, ld, n_rows, 0, n_rows, d, n_rows, ls, st, overlap_prev != 0);
 }
 
 int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1,
@@ -2344,6 +2459,7 @@ int infonce_grad_pair_tc16(const void* a0, const void* b0, const void* a1,
   GradArgs ga;
   ga.ndir = 2;
   ga.bias = bias;
+  ga.tail = GradTail{};
   if ((rc = fill_dir(ga.dir[0], a0, b0, ld, n_rows, n_cols, rs0, cs0, acc0, gs))) return rc;
   if ((rc = fill_dir(ga.dir[1], a1, b1, ld, n_rows, n_cols, rs1, cs1, acc1, nullptr))) return rc;
   return f16 ? grad_launch_16<true>(ga, ld, n_rows, row_offset, n_cols, d, bs, ls, st, overlap_prev != 0)

@@ -318,3 +318,43 @@ def test_graphed_module_matches_eager():
         for a, b in ((got[1], x2.grad), (got[2], y2.grad)):
             assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max())
         assert got[3] == pytest.approx(float(mod.logit_scale.grad), rel=1e-4, abs=1e-7)
+
+
+def test_fused_gradient_tail_variant():
+    """PLK_FUSE_TAIL=1 (read once per process, hence the subprocess): the gradient tail runs inside the recompute
+    backward -- the last column segment of a row block adds the partial slabs and finishes its rows, the last
+    tail of the grid produces d logit_scale.  Same results as the default two-kernel path, incl. a second
+    backward over the same state (the counters and the sum G*S accumulator are left zeroed)."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from multimodal_plankton_recognition_b200 import CLIPLoss, _lib
+from oracle import infonce as oinf
+r = np.random.default_rng(5)
+for B, d in ((1024, 256), (640, 128)):
+    img = r.standard_normal((B, d)).astype(np.float32)
+    pro = (img + 0.8 * r.standard_normal((B, d))).astype(np.float32)
+    ref = oinf.clip_loss_closed_form(img, pro, 1.0, 1)
+    mod = CLIPLoss(precision="bf16").cuda()
+    x = torch.tensor(img, device="cuda", requires_grad=True)
+    y = torch.tensor(pro, device="cuda", requires_grad=True)
+    lib = _lib.load()
+    loss = mod(image_emb=x, profile_emb=y)
+    n0 = lib.plk_launch_count()
+    loss.backward(retain_graph=True)
+    assert lib.plk_launch_count() - n0 == 1, "the fused backward is ONE launch"
+    g1 = (x.grad.clone(), y.grad.clone(), float(mod.logit_scale.grad))
+    x.grad = y.grad = mod.logit_scale.grad = None
+    loss.backward()
+    torch.cuda.synchronize()
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    for g in (g1, (x.grad, y.grad, float(mod.logit_scale.grad))):
+        assert rel(g[0].cpu().numpy(), ref["d_image"]) < 2e-3 and rel(g[1].cpu().numpy(), ref["d_profile"]) < 2e-3
+        assert abs(g[2] - ref["d_logit_scale"]) <= 2e-3 * max(abs(ref["d_logit_scale"]), 1e-3)
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PLK_FUSE_TAIL="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
