@@ -34,6 +34,12 @@ B_C3, D_C3 = 32768, 512
 L2_FLUSH_BYTES = 256 << 20
 
 
+def _workload(n, d, world):
+    """Same string in both arms (the arithmetic type is the line's `dtype`)."""
+    return (f"symmetric InfoNCE fwd+bwd, batch {n} per GPU x d={d} (BASELINE config[1]); "
+            f"N>1: global batch {n * world}, buckets={world} sharded on bucket boundaries")
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -143,10 +149,10 @@ def run_reference(args, rank):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"symmetric InfoNCE fwd+bwd, batch {B_C2} per GPU x d={D_C2}, f32 "
-                               f"(BASELINE config[1]); N>1: global batch {B_C2 * args.gpus}, buckets={args.gpus}",
+        "config": {"workload": _workload(B_C2, D_C2, args.gpus),
                    "global_batch": B_C2 * args.gpus, "d": D_C2, "buckets": args.gpus, "logit_scale": 1.0,
-                   "note": "oracle port of reference CLIPLoss on host cores (/root/reference is Python and does "
+                   "parallelism": f"dp{args.gpus}",
+                   "note": "oracle port of reference CLIPLoss on host cores, fp32 (/root/reference is Python and does "
                            "not travel to the GPU box); each step is one bucket of 4096 pairs -- the buckets "
                            "of the block-diagonal problem are independent, so pairs/s does not depend on N"},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
@@ -381,9 +387,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {
-            "workload": f"symmetric InfoNCE fwd+bwd, batch {n} per GPU x d={d}, {args.precision} "
-                        f"(BASELINE config[1]); N>1: global batch {Bg}, buckets={world} sharded on "
-                        f"bucket boundaries",
+            "workload": _workload(n, d, world),
             "global_batch": Bg, "d": d, "buckets": world, "logit_scale": 1.0,
             "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write)",
             "timed_path": "CUDA-graph replay of plk_clip_loss_forward + plk_clip_loss_backward" if world == 1
