@@ -84,25 +84,44 @@ template <bool F16, bool EDGE, bool GS>
 __device__ __forceinline__ void grad_chunk(const uint32_t (&raw)[32], uint32_t (&packed)[16],
                                            const float* rc_smem, float rrs, float c1, float c0,
                                            int lo_rel, int hi_rel, int dei, float& gs_local) {
+  // element pairs on the packed fp32 pipe: args = a*c1 + c0 (FFMA2), weights = 1/rs + 1/cs (FADD2),
+  // G = E * weights (FMUL2), sum G*a (FFMA2); the two exponentials of a pair stay MUFU.EX2
+  const uint64_t c1p = f2_pack(c1, c1), c0p = f2_pack(c0, c0), rrsp = f2_pack(rrs, rrs);
+  uint64_t gsp = f2_pack(0.f, 0.f);
 #pragma unroll
   for (int e4 = 0; e4 < 8; ++e4) {
     const float4 rc = lds_f4(rc_smem + e4 * 4);
-    const float rcv[4] = {rc.x, rc.y, rc.z, rc.w};
-    float gg[4];
+    const uint64_t rcp[2] = {f2_pack(rc.x, rc.y), f2_pack(rc.z, rc.w)};
 #pragma unroll
-    for (int x = 0; x < 4; ++x) {
-      const int e = e4 * 4 + x;
-      const float a = __uint_as_float(raw[e]);
-      float G = ex2_approx(fmaf(a, c1, c0)) * (rrs + rcv[x]);
-      if constexpr (EDGE) G = (e >= lo_rel && e < hi_rel) ? G : 0.f;
-      if constexpr (GS) gs_local = fmaf(G, a, gs_local);
+    for (int h = 0; h < 2; ++h) {
+      const int e = e4 * 4 + h * 2;
+      const uint64_t a2 = f2_pack_u(raw[e], raw[e + 1]);
+      float x0, x1;
+      f2_unpack(f2_fma(a2, c1p, c0p), x0, x1);
+      uint64_t g2 = f2_mul(f2_pack(ex2_approx(x0), ex2_approx(x1)), f2_add(rcp[h], rrsp));
+      if constexpr (EDGE) {
+        float g0, g1;
+        f2_unpack(g2, g0, g1);
+        g0 = (e >= lo_rel && e < hi_rel) ? g0 : 0.f;
+        g1 = (e + 1 >= lo_rel && e + 1 < hi_rel) ? g1 : 0.f;
+        g2 = f2_pack(g0, g1);
+      }
+      if constexpr (GS) gsp = f2_fma(g2, a2, gsp);
+      float g0, g1;
+      f2_unpack(g2, g0, g1);
       // the j == i term is added in fp32 by plk_infonce_grad_finish (it dominates a peaked softmax
       // and nearly cancels against the -2*delta term): drop it from the 16-bit operand
-      if constexpr (EDGE) G = (e == dei) ? 0.f : G;
-      gg[x] = G;
+      if constexpr (EDGE) {
+        g0 = (e == dei) ? 0.f : g0;
+        g1 = (e + 1 == dei) ? 0.f : g1;
+      }
+      packed[e4 * 2 + h] = pack_16x2<F16>(g0, g1);
     }
-    packed[e4 * 2] = pack_16x2<F16>(gg[0], gg[1]);
-    packed[e4 * 2 + 1] = pack_16x2<F16>(gg[2], gg[3]);
+  }
+  if constexpr (GS) {
+    float s0, s1;
+    f2_unpack(gsp, s0, s1);
+    gs_local += s0 + s1;
   }
 }
 
