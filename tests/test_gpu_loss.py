@@ -358,3 +358,37 @@ print("ok")
     env = dict(os.environ, PLK_FUSE_TAIL="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("env", [{"PLK_GRAD_TC3": "1"}, {"PLK_GRAD_TC2": "1"}, {"PLK_GRAD_TC8": "0"}, {"PLK_PDL": "0"}],
+                         ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
+def test_selectable_backward_kernels(env):
+    """The earlier backward kernels stay selectable for A/B measurements; each must keep
+    matching the oracle.  The switches are read once per process, hence the subprocess."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+from multimodal_plankton_recognition_b200 import CLIPLoss
+from oracle import infonce as oinf
+r = np.random.default_rng(6)
+for B, d, bk in ((1152, 256, 1), (768, 192, 3), (640, 512, 1)):
+    img = r.standard_normal((B, d)).astype(np.float32)
+    pro = (img + 0.8 * r.standard_normal((B, d))).astype(np.float32)
+    ref = oinf.clip_loss_closed_form(img, pro, 1.0, bk)
+    mod = CLIPLoss(precision="bf16").cuda()
+    x = torch.tensor(img, device="cuda", requires_grad=True)
+    y = torch.tensor(pro, device="cuda", requires_grad=True)
+    loss = mod(image_emb=x, profile_emb=y, buckets=bk)
+    loss.backward()
+    torch.cuda.synchronize()
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert abs(float(loss.detach()) - ref["loss"]) < 2e-3 * abs(ref["loss"])
+    assert rel(x.grad.cpu().numpy(), ref["d_image"]) < 2e-3 and rel(y.grad.cpu().numpy(), ref["d_profile"]) < 2e-3
+    assert abs(float(mod.logit_scale.grad) - ref["d_logit_scale"]) <= 2e-3 * max(abs(ref["d_logit_scale"]), 1e-3)
+print("ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
