@@ -404,14 +404,14 @@ def main():
                 "serial_ms_per_step": serial_ms, "serial_value": Bg / (serial_ms * 1e-3)},
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
-        "roofline": {"bound": "tensor", "kernel": "infonce_grad_tc4 (recompute backward, both directions in one launch)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "infonce_grad_tc5 (recompute backward, both directions in one launch, tcgen05 cta_group::2)", "achieved": achieved,
                      "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                      "peak_source": f"{peaks['source']} burst", "kernel_ms": k_ms,
                      "algorithmic_flops_per_launch": algo_flops,
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at this shape,
                      # parsed from the committed `ncu --set full` capture (profiles/r2_traffic.json, written
                      # by tools/ncu_summary.py); null when there is no capture of the current kernel
-                     "traffic": _ncu_traffic("infonce_grad_tc4", n, d, args.precision),
+                     "traffic": _ncu_traffic("infonce_grad_tc5", n, d, args.precision),
                      "executed_flops_per_launch": 2.0 * algo_flops,
                      "executed_tflops": 2.0 * achieved,
                      "note": "the recompute backward executes S = a.b^T once per direction on top of the two "

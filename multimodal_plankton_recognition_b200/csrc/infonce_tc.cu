@@ -29,9 +29,16 @@ __device__ __forceinline__ void trace_stamp(int slot) {
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   g_trace[(size_t)cta * kTraceSlots + slot] = clock64();
 }
+__device__ __forceinline__ void trace_value(int slot, long long v) {
+  if (g_trace == nullptr) return;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  g_trace[(size_t)cta * kTraceSlots + slot] = v;
+}
 #define TR(slot) trace_stamp(slot)
+#define TRV(slot, v) trace_value(slot, v)   // used by the -DPLK_TRACE_PROBE blocks (serialised MMA durations)
 #else
 #define TR(slot) ((void)0)
+#define TRV(slot, v) ((void)0)
 #endif
 
 constexpr int kNumThreads = 576;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
+  if constexpr (CS > 1) cluster_sync_exec();   // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // set-up (barriers, tensor memory, descriptor prefetch) may have run under the tail of the
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar_a);
-        if constexpr (CS > 1) mbar_arrive_cluster(bar_a, cta_rank ^ 1);
+        if constexpr (CS > 1) mbar_arrive_remote(bar_a, cta_rank ^ 1);
       }
       if (threadIdx.x == 64) TR(2);
     }
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TR(5);
-  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
+  if constexpr (CS > 1) cluster_sync_exec();   // no CTA leaves while a peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
+  if constexpr (CS > 1) cluster_sync_exec();   // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kAccCol = 256;
@@ -759,7 +766,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
+  if constexpr (CS > 1) cluster_sync_exec();   // no CTA leaves while a peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -846,7 +853,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();
+  if constexpr (CS > 1) cluster_sync_exec();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kAccCol = 256;
@@ -1051,7 +1058,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) TR(5);
-  if constexpr (CS > 1) cluster_sync_all();
+  if constexpr (CS > 1) cluster_sync_exec();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -1605,7 +1612,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      if (threadIdx.x == 64 && t == 4) TR(14);
       named_barrier_sync(1, kEpiThreads);   // rcs_s[buf] visible; everyone is done with tile t-1
+      if (threadIdx.x == 64 && t == 4) TR(15);
       if (cc == 0 && t + 1 < T && !siglip) {
         const int64_t jc = j0 + kTileRows + r;
         rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
@@ -1616,13 +1625,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
       uint32_t raw[32];
       tmem_ld32(tmem_base + lane_addr + kSCol + cc * 32, raw);
       tmem_ld_wait();
+      if (threadIdx.x == 64 && t == 4) TR(8);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sempty);   // the logits buffer goes back to the MMA warp right away
+      if (threadIdx.x == 64 && t == 4) TR(9);
       uint32_t packed[16];
       grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
                                want_gs, gs_local, siglip, gsum_local);
+      if (threadIdx.x == 64 && t == 4) TR(10);
       if (t >= 1) mbar_wait(bar_gempty, (t - 1) & 1);   // G.V of the previous tile has read the G buffer
+      if (threadIdx.x == 64 && t == 4) TR(11);
       // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
       uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
 #pragma unroll
@@ -1631,7 +1644,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
         *reinterpret_cast<uint4*>(grow + chunk * 16) =
             make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
       }
+      if (threadIdx.x == 64 && t == 4) TR(12);
       fence_proxy_async_smem();
+      if (threadIdx.x == 64 && t == 4) TR(13);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_gfull);
       if (threadIdx.x == 64 && t < 16) TR(96 + t);
@@ -1760,6 +1775,354 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
 }
 
 // =============================================================================================
+// backward, d = 128 or 256, one MMA over a PAIR of row blocks ("tc5", tcgen05.mma.cta_group::2).
+//
+// infonce_grad_tc4 is bound by the shared-memory operand port: G . b_t reads G (4 KiB per K step) and the tile
+// (8 KiB per K step) at 64 B/clk = 192 cycles per MMA, 1536 per tile, after 1024 for S.  With cta_group::2
+// the two CTAs of a cluster own row blocks 2p and 2p+1 and every MMA has M = 256: each CTA contributes ITS
+// 128 rows (A: TMEM for S, its G buffer for G . b_t), the B operand is split along N between the two shared
+// memories, and each CTA's tensor pipe runs its own 128 rows against the whole of B.  Per CTA and K step that
+// halves the B bytes through the operand port: S reads 64 of the 128 logits columns (TS mode: 64 cycles
+// either way), G . b_t reads 4 KiB of G + 4 KiB of tile = 128 cycles: 1024 + 1024 per tile instead of 2560.
+//   per tile each CTA loads  KD x [64 j x 64 k]   its half of the tile's ROWS (= logits columns), all of d  (S)
+//                            KD/2 x [128 j x 64]  all rows of the tile, its half of d                      (G . b_t)
+//   (the same 64 KiB per tile and CTA as tc4 at d = 256; a quarter of it is fetched twice, from L2)
+//   TMEM (both CTAs, allocated as a pair)  [0,128) S | [128,256) owned rows | [256,512) acc [128 x d]
+// The leader (cluster rank 0) issues every MMA; its commits are multicast to the barrier of the same name in
+// both CTAs; the epilogue warps of both CTAs arrive on the LEADER's sempty / gfull barriers; the idle MMA
+// warp of the peer forwards "my operands have landed" to the leader.
+// Needs every row block to sweep the same columns (single bucket), like the multicast clusters.
+// =============================================================================================
+template <int KD>
+struct Grad5Cfg {
+  static_assert(KD == 2 || KD == 4, "tc5: d = 128 or 256");
+  static constexpr int KH = KD / 2;
+  static constexpr int kSBytes = KD * (kChunkBytes / 2);   // [KD][64 x 64]
+  static constexpr int kVBytes = KH * kChunkBytes;         // [KH][128 x 64]
+  static constexpr int kTileBuf = kSBytes + kVBytes;       // = KD * kChunkBytes
+  static constexpr int kNBuf = 3;
+  static constexpr int kGBuf = 2 * kChunkBytes;
+  static constexpr int kSmem = 1024 + kNBuf * kTileBuf + kGBuf + kG4Aux;
+  static_assert(kSmem <= kMaxSmem, "tc5 needs d <= 256");
+};
+
+template <int KD, bool F16, bool SIG>
+__global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
+    const __grid_constant__ GradArgs ga, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+    int64_t d, int64_t bs, int tiles_per_seg, const float* __restrict__ ls) {
+  const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
+  using Cfg = Grad5Cfg<KD>;
+  constexpr int NB = Cfg::kNBuf, KH = Cfg::KH;
+  constexpr int DN = KD * 64;  // accumulator columns = padded d
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sm_y = smem;                                    // [NB] { S part [KD][64 x 64] | V part [KH][128 x 64] }
+  uint8_t* sm_g = smem + NB * Cfg::kTileBuf;               // [2 sub-tiles]
+  uint8_t* aux = sm_g + Cfg::kGBuf;
+  uint64_t* bar_afull = reinterpret_cast<uint64_t*>(aux);  // [1] own rows landed in the last tile buffer
+  uint64_t* bar_aloc = bar_afull + 1;                      // [1] own rows parked in TMEM (this CTA's warps)
+  uint64_t* bar_aall = bar_aloc + 1;                       // [1] leader: both CTAs' rows parked
+  uint64_t* bar_yfull = bar_aall + 1;                      // [NB] own tile operands landed
+  uint64_t* bar_pfull = bar_yfull + NB;                    // [NB] leader: the peer's tile operands landed
+  uint64_t* bar_yempty = bar_pfull + NB;                   // [NB] tile consumed (multicast commit)
+  uint64_t* bar_sfull = bar_yempty + NB;                   // [1] logits complete (multicast commit)
+  uint64_t* bar_sempty = bar_sfull + 1;                    // [1] leader: logits read by both epilogues
+  uint64_t* bar_gfull = bar_sempty + 1;                    // [1] leader: both G buffers written
+  uint64_t* bar_gempty = bar_gfull + 1;                    // [1] G consumed (multicast commit)
+  uint64_t* bar_accfull = bar_gempty + 1;                  // [1] (multicast commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
+  float* rcs_s = reinterpret_cast<float*>(aux + 512);      // [2][128]
+  uint8_t* sm_astage = sm_y + (NB - 1) * Cfg::kTileBuf;    // own rows arrive here (first used by tile NB-1)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader; grid = (row blocks, segments, z),
+                                                           // clusters of {2,1,1}: the pair must be adjacent in x
+  const int64_t i0 = (int64_t)blockIdx.x * kTileRows;
+  const int64_t jlo = 0, jhi = n_cols;                     // single bucket: every row block sweeps every column
+  const int total_tiles = (int)((jhi - jlo + kTileRows - 1) / kTileRows);
+  const int t_begin = blockIdx.y * tiles_per_seg;
+  int t_end = t_begin + tiles_per_seg;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const int T = t_end > t_begin ? t_end - t_begin : 0;     // the same in both CTAs of the pair
+  float* acc_out = g.acc + (int64_t)blockIdx.y * n_rows * d;
+  if (T == 0) {
+    griddep_wait();
+    for (int64_t e = threadIdx.x; e < (int64_t)kTileRows * DN; e += kNumThreads) {
+      const int64_t rr = i0 + e / DN, col = e % DN;
+      if (rr < n_rows && col < d) acc_out[rr * d + col] = 0.f;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) TR(0);
+  pdl_trigger();
+
+  constexpr int kEpiWarps = kEpiThreads / 32;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&g.ta);
+    tma_prefetch_desc(&g.tb);
+    tma_prefetch_desc(&g.tbp);
+    mbar_init(bar_afull, 1);
+    mbar_init(bar_aloc, kEpiWarps);
+    mbar_init(bar_aall, 2 * kEpiWarps);
+    for (int b = 0; b < NB; ++b) {
+      mbar_init(bar_yfull + b, 1);
+      mbar_init(bar_pfull + b, 1);
+      mbar_init(bar_yempty + b, 1);
+    }
+    mbar_init(bar_sfull, 1);
+    mbar_init(bar_sempty, 2 * kEpiWarps);
+    mbar_init(bar_gfull, 2 * kEpiWarps);
+    mbar_init(bar_gempty, 1);
+    mbar_init(bar_accfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_exec();      // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kSCol = 0, kACol = 128, kAccCol = 256;
+  if (threadIdx.x == 0) TR(1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar_afull, KD * kChunkBytes);
+      for (int c = 0; c < KD; ++c) tma_load_2d(sm_astage + c * kChunkBytes, &g.ta, bar_afull, c * kChunkK, (int)i0);
+      int b = 0; uint32_t ph = 0;
+      for (int t = 0; t < T; ++t) {
+        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+        if (t == NB - 1) mbar_wait(bar_aloc, 0);   // the staged rows have left the last buffer
+        mbar_wait(bar_yempty + b, ph ^ 1);
+        uint8_t* buf = sm_y + b * Cfg::kTileBuf;
+        mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
+        for (int c = 0; c < KD; ++c)    // this CTA's 64 logits columns, every K chunk
+          tma_load_2d(buf + c * (kChunkBytes / 2), &g.tbp, bar_yfull + b, c * kChunkK, j0 + 64 * (int)rank);
+        for (int c = 0; c < KH; ++c)    // every tile row, this CTA's half of d
+          tma_load_2d(buf + Cfg::kSBytes + c * kChunkBytes, &g.tb, bar_yfull + b, ((int)rank * KH + c) * kChunkK, j0);
+        if (t < 16) TR(48 + t);
+        if (++b == NB) { b = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && rank != 0) {
+    // peer: tell the leader when this CTA's operands of tile t are in shared memory
+    int b = 0; uint32_t ph = 0;
+    for (int t = 0; t < T; ++t) {
+      mbar_wait(bar_yfull + b, ph);
+      if (lane == 0) mbar_arrive_remote(bar_pfull + b, 0);
+      __syncwarp();
+      if (++b == NB) { b = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc_16(256, 128, 0, 0, F16);
+    constexpr uint32_t idesc_g = umma_idesc_16(256, DN, 0, 1, F16);   // A = G (K-major, smem), B = tile MN-major
+    mbar_wait(bar_aall, 0);     // both CTAs' epilogue warps have parked their rows in TMEM
+    tc_fence_after();
+    if (lane == 0) TR(3);
+    const uint32_t s_tmem = tmem_base + kSCol, a_tmem0 = tmem_base + kACol, acc_tmem = tmem_base + kAccCol;
+    const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);                              // K-major view (S)
+    const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y + Cfg::kSBytes), kChunkBytes);     // MN-major view (G.V)
+    const uint32_t g_lo0 = umma_desc_lo(smem_u32(sm_g), 16);
+    int b = 0; uint32_t ph = 0;
+    int bg = 0;
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        mbar_wait(bar_yfull + b, ph);
+        mbar_wait(bar_pfull + b, ph);
+        if (t >= 1) mbar_wait(bar_sempty, (t - 1) & 1);
+        tc_fence_after();
+        const uint32_t b_lo = y_lo0 + b * (Cfg::kTileBuf >> 4);
+#ifdef PLK_TRACE_PROBE
+        const long long ts0 = clock64();
+#endif
+        if (elect_one()) {
+#pragma unroll
+          for (int c = 0; c < KD; ++c)
+#pragma unroll
+            for (int k = 0; k < kChunkK / kUmmaK; ++k)
+              umma2_bf16_ts(s_tmem, a_tmem0 + c * 32 + k * 8, b_lo + c * (kChunkBytes >> 5) + 2 * k, idesc_s,
+                            (c | k) != 0);
+          umma2_commit(bar_sfull);
+        }
+        __syncwarp();
+        if (lane == 0 && t < 16) TR(64 + t);
+#ifdef PLK_TRACE_PROBE
+        mbar_wait(bar_sfull, t & 1);     // probe: serialise, measure issue -> completion of the 16 S MMAs
+        if (lane == 0 && t < 16) TRV(24 + (t & 7), clock64() - ts0);
+#endif
+        if (++b == NB) { b = 0; ph ^= 1; }
+      }
+      if (t >= 1) {
+        const int u = t - 1;
+        mbar_wait(bar_gfull, u & 1);
+        tc_fence_after();
+        const uint32_t b_lo = y2_lo0 + bg * (Cfg::kTileBuf >> 4);
+#ifdef PLK_TRACE_PROBE
+        const long long tg0 = clock64();
+#endif
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTileRows / kUmmaK; ++k)
+            umma2_bf16_lo(acc_tmem, g_lo0 + (k >> 2) * (kChunkBytes >> 4) + (k & 3) * 2, b_lo + k * (2048 >> 4),
+                          idesc_g, (u | k) != 0);
+          umma2_commit(bar_yempty + bg);
+          umma2_commit(bar_gempty);
+        }
+        __syncwarp();
+        if (lane == 0 && u < 16) TR(112 + u);
+#ifdef PLK_TRACE_PROBE
+        mbar_wait(bar_gempty, u & 1);    // probe: issue -> completion of the 8 G.V MMAs
+        if (lane == 0 && u < 16) TRV(32 + (u & 7), clock64() - tg0);
+#endif
+        if (++bg == NB) bg = 0;
+      }
+    }
+    if (elect_one()) umma2_commit(bar_accfull);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int cc = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int64_t i = i0 + r;
+    const int64_t gi = row_offset + i;
+    int64_t lo = 0, hi = 0;
+    float rrs = 0.f;
+    constexpr bool siglip = SIG;
+    if (i < n_rows) {
+      bucket_range(gi, bs, n_cols, lo, hi);
+      if (!siglip) rrs = 1.0f / g.rs[i];
+    }
+    const float s = expf(*ls);
+    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : (kShiftK - s) * kLog2e;
+    const bool want_gs = g.gs != nullptr;
+    float gs_local = 0.f, gsum_local = 0.f;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    {
+      mbar_wait(bar_afull, 0);
+      for (int c = cc; c < KD; c += 4) {
+        const uint8_t* rowp = sm_astage + c * kChunkBytes + r * 128;
+        uint32_t pk[32];
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) {
+          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
+        }
+        tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_aloc);
+        mbar_arrive_remote(bar_aall, 0);
+      }
+    }
+    float rc_next = 0.f;
+    if (cc == 0 && !siglip) {
+      const int64_t jc = jlo + (int64_t)t_begin * kTileRows + r;
+      rcs_s[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+    }
+    // (Tried: software-pipelining this loop by one tile -- tcgen05.ld of tile t+1 issued before the fence and
+    // the gfull arrive of tile t.  It delays gfull(t) until S(t+1) has completed, which opens a ~900-cycle
+    // bubble in the tensor pipe between S(t+1) and G.V(t): 2900 cycles per tile against 2600.)
+    for (int t = 0; t < T; ++t) {
+      const int buf = t & 1;
+      const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
+      named_barrier_sync(1, kEpiThreads);
+      if (cc == 0 && t + 1 < T && !siglip) {
+        const int64_t jc = j0 + kTileRows + r;
+        rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
+      }
+      mbar_wait(bar_sfull, t & 1);
+      tc_fence_after();
+      if (threadIdx.x == 64 && t < 16) TR(80 + t);
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + lane_addr + kSCol + cc * 32, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(bar_sempty, 0);
+      uint32_t packed[16];
+      grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
+                               want_gs, gs_local, siglip, gsum_local);
+      if (t >= 1) mbar_wait(bar_gempty, (t - 1) & 1);
+      uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < 4; ++c16) {
+        const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
+        *reinterpret_cast<uint4*>(grow + chunk * 16) =
+            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(bar_gfull, 0);
+      if (threadIdx.x == 64 && t < 16) TR(96 + t);
+      if (cc == 0 && t + 1 < T) rcs_s[(buf ^ 1) * 128 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+    }
+    mbar_wait(bar_accfull, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) TR(2);
+    griddep_wait();
+    if (g.use_tacc) {
+#pragma unroll 1
+      for (int ch = cc; ch < 2 * KD; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        uint8_t* stage = sm_y + ch * kChunkBytes;     // 128 rows x 128 B in the idle tile buffers
+        uint8_t* rowp = stage + r * 128;
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
+              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+        fence_proxy_async_smem();
+        named_barrier_sync(2 + cc, 128);
+        if (q == 0 && lane == 0 && i0 < n_rows) {
+          tma_store_3d(&g.tacc, stage, ch * 32, (int)i0, (int)blockIdx.y);
+          tma_store_commit();
+        }
+      }
+      if (q == 0 && lane == 0) tma_store_wait_read();
+    } else {
+#pragma unroll 1
+      for (int ch = cc; ch < 2 * KD; ch += 4) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + lane_addr + kAccCol + ch * 32, raw);
+        tmem_ld_wait();
+        const int64_t col0 = (int64_t)ch * 32;
+        if (i < n_rows) {
+          float* dst = acc_out + i * d + col0;
+#pragma unroll
+          for (int x = 0; x < 32; ++x)
+            if (col0 + x < d) dst[x] = __uint_as_float(raw[x]);
+        }
+      }
+    }
+    if (want_gs) {
+      gs_local *= s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        gs_local += __shfl_xor_sync(0xffffffffu, gs_local, o);
+        gsum_local += __shfl_xor_sync(0xffffffffu, gsum_local, o);
+      }
+      if (lane == 0) {
+        atomicAdd(g.gs, gs_local);
+        if (siglip) atomicAdd(g.gs + 1, gsum_local);
+      }
+    }
+  }
+  griddep_wait();
+  tc_fence_before();
+  if (threadIdx.x == 0) TR(5);
+  cluster_sync_exec();     // neither CTA frees the pair's tensor memory (or exits) while the other still reads it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2<512>(tmem_base);
+  }
+  if (threadIdx.x == 0) TR(6);
+}
+
+// =============================================================================================
 // backward, 448 < d <= 512 (eight 64-element chunks): "tc8".
 //
 // The [128 x 512] fp32 accumulator alone is all of TMEM, so a CTA owns one 256-column half of d (blockIdx.z)
@@ -1850,7 +2213,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc8(
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast
+  if constexpr (CS > 1) cluster_sync_exec();   // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kSCol = 0, kACol = 128, kAccCol = 256;
@@ -2080,7 +2443,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc8(
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();   // no CTA leaves while a peer can still multicast into it
+  if constexpr (CS > 1) cluster_sync_exec();   // no CTA leaves while a peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -2280,6 +2643,47 @@ static int launch_grad4(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t r
              : launch_grad4_m<KD, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
 }
 
+template <int KD, bool F16, bool SIG>
+static int launch_grad5_m(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                          int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  auto kern = infonce_grad_tc5<KD, F16, SIG>;
+  static bool configured = false;
+  if (!configured) {
+    PLK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Grad5Cfg<KD>::kSmem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Grad5Cfg<KD>::kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = overlap_prev ? 2 : 1;
+  PLK_CUDA(cudaLaunchKernelEx(&cfg, kern, ga, n_rows, row_offset, n_cols, d, bs, tps, ls));
+  PLK_LAUNCHED(1);
+  return PLK_OK;
+}
+template <int KD, bool F16>
+static int launch_grad5(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
+                        int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st, bool overlap_prev) {
+  return ga.bias != nullptr
+             ? launch_grad5_m<KD, F16, true>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev)
+             : launch_grad5_m<KD, F16, false>(ga, grid, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
+}
+// The paired-CTA backward (cta_group::2) is the default where it applies (padded d = 128 / 256, one bucket, at
+// least two row blocks); PLK_GRAD_TC5=0 selects infonce_grad_tc4 there.
+static bool use_grad_tc5() {
+  static const bool v = getenv("PLK_GRAD_TC5") == nullptr || getenv("PLK_GRAD_TC5")[0] != '0';
+  return v;
+}
+
 template <int CS, bool F16>
 static int launch_grad8(const GradArgs& ga, dim3 grid, int64_t n_rows, int64_t row_offset, int64_t n_cols,
                         int64_t d, int64_t bs, int tps, const float* ls, cudaStream_t st) {
@@ -2357,6 +2761,12 @@ static int grad_launch_16(const GradArgs& ga_in, int64_t ld, int64_t n_rows, int
         ga.dir[k].use_tacc = 1;
       }
       if (ga.ndir == 1) ga.dir[1] = ga.dir[0];
+    }
+    if (!use_grad_tc2() && !use_grad_tc3() && use_grad_tc5() && (kd == 2 || kd == 4) && csz == 2 &&
+        !ga.tail.enabled) {
+      dim3 grid5((unsigned)(ceil_div(row_blocks, 2) * 2), (unsigned)nseg, (unsigned)z);
+      return kd == 4 ? launch_grad5<4, F16>(ga, grid5, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev)
+                     : launch_grad5<2, F16>(ga, grid5, n_rows, row_offset, n_cols, d, bs, tps, ls, st, overlap_prev);
     }
     if (!use_grad_tc2() && !use_grad_tc3()) {   // S in TS mode at N = 128, G through shared memory, no clusters
       dim3 grid4((unsigned)nseg, (unsigned)row_blocks, (unsigned)z);

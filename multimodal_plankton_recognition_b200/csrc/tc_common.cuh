@@ -47,6 +47,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// The same without the cluster-scope release: `.release.cluster` costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per
+// arrive (~1000 cycles with loads in flight; measured in infonce_grad_tc5: 3300-cycle epilogues against
+// 1900).  Enough when what the arrive publishes is already ordered by its own fence -- tcgen05.fence::
+// before_thread_sync after a tcgen05.ld / st, fence.proxy.async after shared-memory stores that the tensor
+// core of THIS SM will read -- the form CUTLASS's ClusterBarrier::arrive(cta) uses for the same hand-offs.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -66,6 +79,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
       printf("plk: mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// the same wait with cluster-scope acquire: pairs with mbar_arrive_cluster from the OTHER CTA of a pair
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cl(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cl(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 4000000000LL) {
+      printf("plk: cluster mbarrier wait timed out (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
              blockIdx.y, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
@@ -131,6 +169,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {  // every thread of every CTA in the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Execution barrier only (arrive.relaxed: no MEMBAR.ALL.GPU / ERRBAR, ~1000 cycles less per use).  Enough (a)
+// after mbarrier.init + fence.mbarrier_init.release.cluster, which is what publishes the barriers to the
+// peers, and (b) before exit, where the point is only that no CTA leaves while a peer can still write
+// into its shared memory or barriers.
+__device__ __forceinline__ void cluster_sync_exec() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
@@ -201,6 +247,51 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(accumulate)
       : "memory");
 }
+// ---- cta_group::2: one MMA over a PAIR of CTAs (M = 256: each CTA's 128 rows; B split along N between the
+// two CTAs' shared memories at the same offset; D rows in each CTA's own TMEM).  Issued by the leader
+// CTA (cluster rank 0) only; allocation / deallocation by one warp of EACH CTA.
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem) {  // one full warp, in both CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(0x40004040u /* kUmmaDescHi */), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(0x40004040u /* kUmmaDescHi */), "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the pair's previously issued MMAs retired
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
 // mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

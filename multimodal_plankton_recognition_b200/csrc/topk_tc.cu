@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();
+  if constexpr (CS > 1) cluster_sync_exec();
   tc_fence_after();
   const uint32_t cta_rank = CS > 1 ? cluster_ctarank() : 0;
   const uint32_t tmem_base = *tmem_slot;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CS > 1) cluster_sync_all();
+  if constexpr (CS > 1) cluster_sync_exec();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

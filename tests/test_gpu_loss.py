@@ -360,7 +360,8 @@ print("ok")
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("env", [{"PLK_GRAD_TC3": "1"}, {"PLK_GRAD_TC2": "1"}, {"PLK_GRAD_TC8": "0"}, {"PLK_PDL": "0"}],
+@pytest.mark.parametrize("env", [{"PLK_GRAD_TC5": "0"}, {"PLK_GRAD_TC3": "1"}, {"PLK_GRAD_TC2": "1"}, {"PLK_GRAD_TC8": "0"},
+                                 {"PLK_PDL": "0"}],
                          ids=lambda e: "+".join(f"{k}={v}" for k, v in e.items()))
 def test_selectable_backward_kernels(env):
     """The earlier backward kernels stay selectable for A/B measurements; each must keep
@@ -373,7 +374,7 @@ sys.path.insert(0, %r)
 from multimodal_plankton_recognition_b200 import CLIPLoss
 from oracle import infonce as oinf
 r = np.random.default_rng(6)
-for B, d, bk in ((1152, 256, 1), (768, 192, 3), (640, 512, 1)):
+for B, d, bk in ((1152, 256, 1), (896, 128, 1), (768, 192, 3), (640, 512, 1)):
     img = r.standard_normal((B, d)).astype(np.float32)
     pro = (img + 0.8 * r.standard_normal((B, d))).astype(np.float32)
     ref = oinf.clip_loss_closed_form(img, pro, 1.0, bk)

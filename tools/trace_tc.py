@@ -70,6 +70,14 @@ for i in used[:nprint] + used[-1:]:
     r = t[i]
     print(f"--- CTA {i}: setup {rel(r,1)}  A-ready(epi) {rel(r,2)}  mma-start {rel(r,3)}  first-chunk-mma {rel(r,4)}  "
           f"joined {rel(r,5)}  exit {rel(r,6)}")
+    if r[15]:   # epilogue phases of tile 4 (tc4): relative to the named barrier at the top of the iteration
+        names = ("ld done", "sempty sent", "G computed", "gempty seen", "G stored", "fenced")
+        print("   epilogue tile 4: at barrier", rel(r, 14), "passed", rel(r, 15), "got S", rel(r, 84),
+              " ".join(f"{n} +{int(r[8 + i] - r[84])}" for i, n in enumerate(names)))
+    for name, base in (("S exec (probe)", 24), ("GV exec (probe)", 32)):
+        vals = [int(r[base + k]) for k in range(16) if r[base + k]]
+        if vals:
+            print(f"   {name}", " ".join(f"{x:6d}" for x in vals))
     for name, base in (("tma issued   ", 48), ("S committed  ", 64), ("epi got S    ", 80), ("epi done     ", 96),
                        ("GV issued    ", 112)):
         vals = [rel(r, base + k) for k in range(16) if r[base + k]]
