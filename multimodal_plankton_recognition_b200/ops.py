@@ -486,6 +486,14 @@ def project_normalise(feat: torch.Tensor, weight: torch.Tensor, mode: int):
         return u, emb, inv_den, nrm
     odt = OP_TORCH_DTYPE[mode]
     x16, w16 = _pad64_cast(feat, odt), _pad64_cast(weight, odt)
+    return _project_normalise16(x16, w16, n, f, d, mode)
+
+
+def _project_normalise16(x16: torch.Tensor, w16: torch.Tensor, n: int, f: int, d: int, mode: int):
+    """plk_project_normalise on operands that are already 16-bit and zero-padded to a multiple of 64 columns."""
+    lib = _lib.load()
+    odt = OP_TORCH_DTYPE[mode]
+    feat = x16
     ld = padded_width(d, mode)
     u = torch.empty((n, ld), device=feat.device, dtype=odt)
     emb = torch.empty((n, d), device=feat.device, dtype=torch.float32)
@@ -510,21 +518,29 @@ class _ProjectedClipLossFn(torch.autograd.Function):
         d = w_i.shape[0]
         bs = B // buckets
         ls = logit_scale.detach().float()
-        u, x, idx, nx = project_normalise(image_feat, w_i, mode)
-        v, y, idy, ny = project_normalise(profile_feat, w_p, mode)
+        if mode == PLK_F32:
+            u, x, idx, nx = project_normalise(image_feat, w_i, mode)
+            v, y, idy, ny = project_normalise(profile_feat, w_p, mode)
+            ops16 = (image_feat, profile_feat, w_i, w_p)
+        else:   # the 16-bit copies of features and weights feed the forward kernel AND the backward GEMMs
+            odt = OP_TORCH_DTYPE[mode]
+            ops16 = tuple(_pad64_cast(t, odt) for t in (image_feat, profile_feat, w_i, w_p))
+            u, x, idx, nx = _project_normalise16(ops16[0], ops16[2], B, image_feat.shape[1], d, mode)
+            v, y, idy, ny = _project_normalise16(ops16[1], ops16[3], B, profile_feat.shape[1], d, mode)
         sums = torch.zeros((2, B), device=x.device, dtype=torch.float32)
         dg = torch.empty(B, device=x.device, dtype=torch.float32)
         infonce_fwd_local(u, v, mode, d, 0, bs, ls, sums[0], sums[1], dg, sums_zeroed=True)
         loss, aux = infonce_loss_local(sums[0], sums[1], dg, ls, B)
-        ctx.save_for_backward(image_feat, profile_feat, w_i, w_p, ls, u, v, x, y, idx, nx, idy, ny, sums, dg, aux)
-        ctx.meta = (bs, mode, logit_scale.dtype)
+        ctx.save_for_backward(*ops16, ls, u, v, x, y, idx, nx, idy, ny, sums, dg, aux)
+        ctx.meta = (bs, mode, logit_scale.dtype, image_feat.shape[1], profile_feat.shape[1], image_feat.dtype,
+                    profile_feat.dtype, w_i.dtype, w_p.dtype)
         return loss
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_loss):
-        image_feat, profile_feat, w_i, w_p, ls, u, v, x, y, idx, nx, idy, ny, sums, dg, aux = ctx.saved_tensors
-        bs, mode, dtl = ctx.meta
+        f16_i, f16_p, w16_i, w16_p, ls, u, v, x, y, idx, nx, idy, ny, sums, dg, aux = ctx.saved_tensors
+        bs, mode, dtl, f_i, f_p, dt_fi, dt_fp, dt_wi, dt_wp = ctx.meta
         B, d = x.shape
         go = g_loss.detach().float().reshape(1).contiguous()
         gs = aux[1:].clone()
@@ -532,10 +548,26 @@ class _ProjectedClipLossFn(torch.autograd.Function):
         dx, dy, dls = infonce_grad_finish_pair(acc_x, acc_y, x, y, (idx, nx), (idy, ny), dg, sums[0], sums[1], ls, go,
                                                go, B, gs, aux[0:1])
         out = []
-        for demb, feat, w in ((dx, image_feat, w_i), (dy, profile_feat, w_p)):
-            out.append((torch.matmul(demb, w.detach().float()).to(feat.dtype),              # d feat  [B, f]
-                        torch.matmul(demb.t(), feat.detach().float()).to(w.dtype)))         # d W     [d, f]
+        for demb, feat, w, f, dtf, dtw in ((dx, f16_i, w16_i, f_i, dt_fi, dt_wi), (dy, f16_p, w16_p, f_p, dt_fp, dt_wp)):
+            d16 = demb if mode == PLK_F32 else demb.to(OP_TORCH_DTYPE[mode])
+            out.append((_mm_mode(d16, w[:, :f], mode).to(dtf),                              # d feat  [B, f]
+                        _mm_mode(d16.t(), feat[:, :f], mode).to(dtw)))                      # d W     [d, f]
         return out[0][0], out[1][0], out[0][1], out[1][1], dls.to(dtl), None, None
+
+
+def _mm_mode(a: torch.Tensor, b: torch.Tensor, mode: int) -> torch.Tensor:
+    """a @ b for the projection backward (library GEMM, off the similarity path).  fp32 mode: fp32 operands.
+    16-bit modes: operands rounded to the mode's 16-bit type, fp32 accumulation AND fp32 result
+    (`aten::mm.dtype`) -- what the reference's '16-mixed' autocast does to `nn.Linear`'s backward, minus its
+    rounding of the result.  (An fp32 GEMM here cost more than the whole loss step: 90 us at B = 4096, f = 1280.)"""
+    if mode == PLK_F32:
+        return torch.matmul(a.detach().float(), b.detach().float())
+    odt = OP_TORCH_DTYPE[mode]
+    a16, b16 = a.detach().to(odt), b.detach().to(odt)    # no-ops for operands that are already 16-bit
+    try:
+        return torch.mm(a16, b16, out_dtype=torch.float32)
+    except (TypeError, NotImplementedError, RuntimeError):
+        return torch.mm(a16, b16).float()
 
 
 def clip_loss_projected(image_feat, profile_feat, image_weight, profile_weight, logit_scale, buckets: int = 1,

@@ -103,6 +103,8 @@ def _check(got, ref, tol):
     (1536, 192, 3, [384] * 4),                 # a bucket (512 rows) spans rank boundaries
     (1000, 200, 1, [250] * 4),                 # nothing a multiple of the tile
     (777, 96, 1, [300, 77, 400]),              # ragged shards
+    (1280, 256, 1, [640, 384, 256]),           # paired-CTA backward: 5 / 3 / 2 row blocks (phantom block pads the odd ones)
+    (900, 128, 1, [300, 600]),                 # paired-CTA backward at d = 128, row_offset not a multiple of the tile
 ])
 def test_row_sharded_loss_matches_unsharded_oracle(B, d, buckets, counts, precision):
     img, pro = _pairs(B, d, B + d)
