@@ -103,9 +103,16 @@ __device__ __forceinline__ void grad_chunk(const uint32_t (&raw)[32], uint32_t (
     for (int h = 0; h < 2; ++h) {
       const int e = e4 * 4 + h * 2;
       const uint64_t a2 = f2_pack_u(raw[e], raw[e + 1]);
-      float x0, x1;
-      f2_unpack(f2_fma(a2, c1p, c0p), x0, x1);
-      uint64_t g2 = f2_mul(f2_pack(ex2_approx(x0), ex2_approx(x1)), f2_add(rcp[h], rrsp));
+      const uint64_t x2 = f2_fma(a2, c1p, c0p);
+      uint64_t e2;
+      if (exp_pair_on_fma(e4 * 2 + h)) {   // compile-time choice (the loops are fully unrolled)
+        e2 = ex2_poly2(x2);
+      } else {
+        float x0, x1;
+        f2_unpack(x2, x0, x1);
+        e2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+      }
+      uint64_t g2 = f2_mul(e2, f2_add(rcp[h], rrsp));
       if constexpr (EDGE) {
         float g0, g1;
         f2_unpack(g2, g0, g1);
@@ -419,15 +426,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
         continue;
       }
       float v[32];
-      if (warp_full) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
-      } else {
+      for (int e = 0; e < 32; e += 2) {   // one pair in four on the FMA pipe (ex2_poly2), the rest MUFU.EX2
+        if (exp_pair_on_fma(e >> 1)) {
+          f2_unpack(ex2_poly2(f2_fma(f2_pack_u(raw[e], raw[e + 1]), f2_pack(c1, c1), f2_pack(c0, c0))), v[e], v[e + 1]);
+        } else {
+          v[e] = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
+          v[e + 1] = ex2_approx(fmaf(__uint_as_float(raw[e + 1]), c1, c0));
+        }
+      }
+      if (!warp_full) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
           const int64_t j = j0 + e;
-          const float E = ex2_approx(fmaf(__uint_as_float(raw[e]), c1, c0));
-          v[e] = (j >= lo && j < hi) ? E : 0.f;
+          v[e] = (j >= lo && j < hi) ? v[e] : 0.f;
         }
       }
       if (has_diag) {

@@ -480,6 +480,40 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   return d;
 }
 
+// 2^x for a PAIR on the FMA pipe (no MUFU): x = n + f with n = round(x), |f| <= 0.5 (magic-number rounding),
+// 2^f by a degree-5 minimax polynomial (max relative error 2.3e-7 in fp32 Horner form, i.e. the accuracy of
+// MUFU.EX2's 2 ulp), times 2^n built from the integer bits.  x is clamped at -127, where 2^n becomes the bit
+// pattern 0: results below the normal range are 0 like ex2.approx.ftz; callers guarantee x < 128.
+// The InfoNCE epilogues need one exponential per logit: 16384 per 128 x 128 tile = 1024 cycles of the SM's 16
+// MUFU lanes, the longest stage of every tile.  Moving one pair in four here (-DPLK_EXP_POLY_EVERY=4) trades 256
+// of those cycles for 13 packed fp32 instructions per pair.  MEASURED (B200, parity green, 166 GPU tests): it
+// does not pay -- backward 98.3 -> 106.4 us at B = 8192, 104.5 -> 112.7 us at d = 512, step 67.6 -> 69.6 us,
+// forward unchanged: the packed instructions occupy the fp32 pipe for two cycles each and the four epilogue
+// warps per scheduler are short of issue slots in exactly the phase that was MUFU-bound.  Default: off.
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  const uint64_t xc = f2_pack(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
+  const uint64_t r = f2_add(xc, f2_pack(12582912.f, 12582912.f));           // 1.5 * 2^23: integer in the low bits
+  const uint64_t n = f2_add(r, f2_pack(-12582912.f, -12582912.f));
+  const uint64_t f = f2_fma(n, f2_pack(-1.f, -1.f), xc);
+  uint64_t p = f2_fma(f, f2_pack(0.0013276456f, 0.0013276456f), f2_pack(0.009675541f, 0.009675541f));
+  p = f2_fma(p, f, f2_pack(0.055507135f, 0.055507135f));
+  p = f2_fma(p, f, f2_pack(0.2402212f, 0.2402212f));
+  p = f2_fma(p, f, f2_pack(0.69314694f, 0.69314694f));
+  p = f2_fma(p, f, f2_pack(1.0000001f, 1.0000001f));
+  const uint32_t s0 = ((uint32_t)r << 23) + 0x3F800000u;                    // 2^n: (n + 127) << 23
+  const uint32_t s1 = ((uint32_t)(r >> 32) << 23) + 0x3F800000u;
+  return f2_mul(p, f2_pack_u(s0, s1));
+}
+// which pairs of a 32-column chunk (pair index 0..15) take the polynomial: every PLK_EXP_POLY_EVERY-th; 0 = none
+#ifndef PLK_EXP_POLY_EVERY
+#define PLK_EXP_POLY_EVERY 0
+#endif
+__device__ __forceinline__ constexpr bool exp_pair_on_fma(int pair) {
+  return PLK_EXP_POLY_EVERY > 0 && (pair % (PLK_EXP_POLY_EVERY > 0 ? PLK_EXP_POLY_EVERY : 1)) == (PLK_EXP_POLY_EVERY - 1);
+}
+
 // Logistic pieces for the SigLIP epilogues; zl = z * log2(e).
 //   sigmoid(z)  = 1 / (1 + e^-z)                 (2 MUFU; relative accuracy also for z << 0)
 //   softplus(z) = max(z, 0) + log1p(e^-|z|)      (2 MUFU; series below t = 0.01 where 1 + t loses t)
