@@ -28,6 +28,11 @@ __device__ __forceinline__ void trace_stamp(int slot) {
   if (g_trace == nullptr) return;
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   g_trace[(size_t)cta * kTraceSlots + slot] = clock64();
+  if (slot == 0 || slot == 6) {   // wall-clock (ns) at CTA entry / exit: slots 120 / 121
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_trace[(size_t)cta * kTraceSlots + (slot == 0 ? 120 : 121)] = (long long)gt;
+  }
 }
 __device__ __forceinline__ void trace_value(int slot, long long v) {
   if (g_trace == nullptr) return;

@@ -52,7 +52,7 @@ template <int KD, int KC, int CS>
 __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
     const uint16_t* __restrict__ q_op, int64_t ldq, const __grid_constant__ CUtensorMap tmap_g,
     const __grid_constant__ CUtensorMap tmap_gp, const float* __restrict__ g_sqn, int64_t nq, int64_t ng, int64_t goff, int tiles_per_chunk,
-    int nchunks, int kc_out, int32_t* __restrict__ out_idx, float* __restrict__ out_key, int f16) {
+    int nchunks, int kc_out, int32_t* __restrict__ out_idx, float* __restrict__ out_key, int f16, int raster) {
   using Cfg = TopkCfg<KD>;
   constexpr int NST = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -69,8 +69,14 @@ __global__ void __launch_bounds__(kTkThreads, 1) topk_tc_kernel(
   float* gsq_s = reinterpret_cast<float*>(aux + 512);  // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t q0 = (int64_t)blockIdx.y * kTileRows;
-  const int chunk = blockIdx.x;
+  // Rasterisation: clusters become resident in launch order (x fastest).  Launch-linear cluster L sweeps gallery
+  // chunk L / pairs for query-block pair L % pairs, so the ~74 resident clusters read the SAME chunk in step
+  // and a gallery tile comes from DRAM once per wave, not once per query-block pair (3.9x the operand bytes
+  // at 8192 x 262144 with chunk-fastest order).
+  const int pairs = (int)(gridDim.y / CS);
+  const int64_t lin = (int64_t)blockIdx.x + (int64_t)gridDim.x * (blockIdx.y / CS);
+  const int64_t q0 = raster ? ((lin % pairs) * CS + blockIdx.y % CS) * kTileRows : (int64_t)blockIdx.y * kTileRows;
+  const int chunk = raster ? (int)(lin / pairs) : (int)blockIdx.x;   // PLK_TOPK_RASTER=0: the old order (A/B)
   const int total_tiles = (int)((ng + kTileRows - 1) / kTileRows);
   const int t_begin = chunk * tiles_per_chunk;
   int t_end = t_begin + tiles_per_chunk;
@@ -272,6 +278,11 @@ size_t topk_ws_tc16(int64_t nq, int64_t ng, int64_t d, int kc) {
   return (size_t)nq * c * 2 * kc * (sizeof(int32_t) + sizeof(float));  // two column-half lists per chunk
 }
 
+static int topk_raster() {
+  static const int v = [] { const char* e = getenv("PLK_TOPK_RASTER"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v;
+}
+
 template <int KD, int KC, int CS>
 static int launch_topk(const void* q, int64_t ldq, const CUtensorMap& tg, const CUtensorMap& tgp, dim3 grid,
                        const float* g_sqn, int64_t nq, int64_t ng, int64_t goff, int tpc, int nchunks,
@@ -283,7 +294,7 @@ static int launch_topk(const void* q, int64_t ldq, const CUtensorMap& tg, const 
     configured = true;
   }
   int rc = launch_kernel(kern, grid, dim3(kTkThreads), TopkCfg<KD>::kSmem, st, CS, (const uint16_t*)q, ldq, tg, tgp, g_sqn, nq, ng,
-                         goff, tpc, nchunks, kc, o_idx, o_key, f16);
+                         goff, tpc, nchunks, kc, o_idx, o_key, f16, topk_raster());
   if (rc) return rc;
   PLK_LAUNCHED(1);
   return PLK_OK;

@@ -10,6 +10,7 @@ import sys
 
 os.environ["PLK_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 import torch
 
 from multimodal_plankton_recognition_b200 import _lib, ops, synth
@@ -54,6 +55,17 @@ assert setter(buf.data_ptr()) == 0
 for it in range(3):
     run()
     torch.cuda.synchronize()
+# the same launch between CUDA events (what bench.py's kernel_ms sees) against the CTAs' own wall clocks
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+if kind == "fwd":
+    flush.zero_(); buf.zero_()
+    ev[0].record(); ops.infonce_fwd_local(u, v, mode, d, 0, B, ls); ev[1].record()
+else:
+    rs, cs, dg = ops.infonce_fwd_local(u, v, mode, d, 0, B, ls)
+    flush.zero_(); buf.zero_()
+    ev[0].record(); ops.infonce_grad_pair_local(u, v, v, u, mode, d, 0, B, ls, rs, cs, cs, rs, gs0); ev[1].record()
+torch.cuda.synchronize()
+print(f"CUDA events around the launch: {ev[0].elapsed_time(ev[1]) * 1e3:.1f} us")
 t = buf.view(-1, SLOTS).cpu().numpy()
 used = [i for i in range(t.shape[0]) if t[i, 0] != 0]
 print(f"{len(used)} CTAs traced")
@@ -63,8 +75,10 @@ def rel(row, k):
     return int(row[k] - row[0]) if row[k] else -1
 
 
-import numpy as np
 tot = np.array([rel(t[i], 6) for i in used])
+gt0 = np.array([t[i, 120] for i in used]); gt1 = np.array([t[i, 121] for i in used])
+print(f"wall clock: first entry -> last exit {(gt1.max() - gt0.min()) / 1e3:.1f} us; entry spread {(gt0.max() - gt0.min()) / 1e3:.1f} us; "
+      f"exit spread {(gt1.max() - gt1.min()) / 1e3:.1f} us; median lifetime {np.median(gt1 - gt0) / 1e3:.1f} us")
 print(f"CTA lifetime (entry -> exit): min {tot.min()} median {int(np.median(tot))} max {tot.max()} cycles")
 for i in used[:nprint] + used[-1:]:
     r = t[i]
