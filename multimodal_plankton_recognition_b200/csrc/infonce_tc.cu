@@ -28,10 +28,10 @@ __device__ __forceinline__ void trace_stamp(int slot) {
   if (g_trace == nullptr) return;
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   g_trace[(size_t)cta * kTraceSlots + slot] = clock64();
-  if (slot == 0 || slot == 6) {   // wall-clock (ns) at CTA entry / exit: slots 120 / 121
+  if (slot == 0 || slot == 6) {   // wall-clock (ns) at CTA entry / exit: slots 40 / 41
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    g_trace[(size_t)cta * kTraceSlots + (slot == 0 ? 120 : 121)] = (long long)gt;
+    g_trace[(size_t)cta * kTraceSlots + (slot == 0 ? 40 : 41)] = (long long)gt;
   }
 }
 __device__ __forceinline__ void trace_value(int slot, long long v) {
@@ -78,6 +78,14 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) 
   }
 }
 
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds_f4(const float* p) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
         uint32_t pk[32];
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4) {
-          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          const uint4 w = lds_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4));
           pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
         }
         tmem_st32(tmem_base + ((uint32_t)(q * 32) << 16) + 256 + c * 32, pk);
@@ -393,6 +401,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_sempty + buf);   // the accumulator buffer goes back to the MMA warp right away
+      if (threadIdx.x == 64 && t < 8) TR(8 + t);              // trace: first epilogue warp has its logits
+      if (threadIdx.x == 17 * 32 && t < 8) TR(24 + t);        // trace: last epilogue warp has its logits
       const bool full = (j0 >= lo) && (j0 + 32 <= hi);
       const bool warp_full = __all_sync(0xffffffffu, full);
       const bool has_diag = __any_sync(0xffffffffu, gi >= j0 && gi < j0 + 32 && i < n_rows);
@@ -468,6 +478,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       const int64_t j = j0 + lane;
       if (j < n_cols && v[0] != 0.f) atomicAdd(col_sumexp + j, v[0]);
       if (threadIdx.x == 64 && t < 16) TR(96 + t);
+      if (threadIdx.x == 17 * 32 && t < 8) TR(32 + t);        // trace: last epilogue warp done
     }
     if (siglip) {
 #pragma unroll
@@ -734,12 +745,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc(
                                want_gs, gs_local, siglip, gsum_local);
       mbar_wait(bar_gempty, (t & 1) ^ 1);  // MMA2 of the previous tile has read G
       // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
-      uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
+      const uint32_t grow = smem_u32(sm_g + (cc >> 1) * kChunkBytes + r * 128);
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {
+      for (int c16 = 0; c16 < 4; ++c16) {   // explicit st.shared: a generic store goes through the global path (stall_lg)
         const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
-        *reinterpret_cast<uint4*>(grow + chunk * 16) =
-            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+        sts_v4(grow + chunk * 16, packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
       }
       fence_proxy_async_smem();
       mbar_arrive(bar_gfull);
@@ -1025,8 +1035,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc2(
         uint8_t* rowp = stage + r * 128;
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4)
-          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
-              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+          sts_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4), raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
         fence_proxy_async_smem();
         named_barrier_sync(2 + cc, 128);
         if (q == 0 && lane == 0 && i0 < n_rows) {
@@ -1291,7 +1300,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc3(
         uint32_t pk[32];
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4) {
-          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          const uint4 w = lds_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4));
           pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
         }
         tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
@@ -1355,8 +1364,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc3(
         uint8_t* rowp = stage + r * 128;
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4)
-          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
-              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+          sts_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4), raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
         fence_proxy_async_smem();
         named_barrier_sync(3 + e, 128);
         if (q == 0 && lane == 0 && i0 < n_rows) {
@@ -1610,7 +1618,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
         uint32_t pk[32];
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4) {
-          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          const uint4 w = lds_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4));
           pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
         }
         tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
@@ -1654,12 +1662,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
       if (t >= 1) mbar_wait(bar_gempty, (t - 1) & 1);   // G.V of the previous tile has read the G buffer
       if (threadIdx.x == 64 && t == 4) TR(11);
       // G[r][cc*32 .. +32): sub-tile cc/2, logical 16-byte chunks (cc%2)*4 .. +4, 128B swizzle
-      uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
+      const uint32_t grow = smem_u32(sm_g + (cc >> 1) * kChunkBytes + r * 128);
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {
+      for (int c16 = 0; c16 < 4; ++c16) {   // explicit st.shared: a generic store goes through the global path (stall_lg)
         const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
-        *reinterpret_cast<uint4*>(grow + chunk * 16) =
-            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+        sts_v4(grow + chunk * 16, packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
       }
       if (threadIdx.x == 64 && t == 4) TR(12);
       fence_proxy_async_smem();
@@ -1683,8 +1690,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc4(
         uint8_t* rowp = stage + r * 128;
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4)
-          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
-              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+          sts_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4), raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
         fence_proxy_async_smem();
         named_barrier_sync(2 + cc, 128);
         if (q == 0 && lane == 0 && i0 < n_rows) {
@@ -1893,6 +1899,27 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
     mbar_init(bar_accfull, 1);
     fence_barrier_init();
   }
+  // One tile's operands: this CTA's 64 logits columns for every K chunk, then every tile row for its half of d.
+  auto load_tile = [&](int t, int b) {
+    const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+    uint8_t* buf = sm_y + b * Cfg::kTileBuf;
+    mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
+    for (int c = 0; c < KD; ++c)
+      tma_load_2d(buf + c * (kChunkBytes / 2), &g.tbp, bar_yfull + b, c * kChunkK, j0 + 64 * (int)rank);
+    for (int c = 0; c < KH; ++c)
+      tma_load_2d(buf + Cfg::kSBytes + c * kChunkBytes, &g.tb, bar_yfull + b, ((int)rank * KH + c) * kChunkK, j0);
+    if (t < 16) TR(48 + t);
+  };
+  // The owned rows and the first NB-1 tiles land in this CTA's own shared memory and complete on its own barriers:
+  // they are requested BEFORE the cluster rendezvous and the tensor-memory allocation (the operands were written
+  // two kernels earlier -- the loss reduction between waits for the forward before it lets this grid start), so
+  // ~1300 cycles of set-up run under the first loads' latency instead of in front of it.
+  const int kEarly = T < NB - 1 ? T : NB - 1;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_afull, KD * kChunkBytes);
+    for (int c = 0; c < KD; ++c) tma_load_2d(sm_astage + c * kChunkBytes, &g.ta, bar_afull, c * kChunkK, (int)i0);
+    for (int t = 0; t < kEarly; ++t) load_tile(t, t);
+  }
   if (warp == 1) tmem_alloc2<512>(tmem_slot);
   tc_fence_before();
   cluster_sync_exec();      // barriers of both CTAs initialised before any remote arrive / multicast commit
@@ -1903,20 +1930,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_afull, KD * kChunkBytes);
-      for (int c = 0; c < KD; ++c) tma_load_2d(sm_astage + c * kChunkBytes, &g.ta, bar_afull, c * kChunkK, (int)i0);
-      int b = 0; uint32_t ph = 0;
-      for (int t = 0; t < T; ++t) {
-        const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+      int b = kEarly; uint32_t ph = 0;
+      if (b == NB) { b = 0; ph ^= 1; }
+      for (int t = kEarly; t < T; ++t) {
         if (t == NB - 1) mbar_wait(bar_aloc, 0);   // the staged rows have left the last buffer
         mbar_wait(bar_yempty + b, ph ^ 1);
-        uint8_t* buf = sm_y + b * Cfg::kTileBuf;
-        mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
-        for (int c = 0; c < KD; ++c)    // this CTA's 64 logits columns, every K chunk
-          tma_load_2d(buf + c * (kChunkBytes / 2), &g.tbp, bar_yfull + b, c * kChunkK, j0 + 64 * (int)rank);
-        for (int c = 0; c < KH; ++c)    // every tile row, this CTA's half of d
-          tma_load_2d(buf + Cfg::kSBytes + c * kChunkBytes, &g.tb, bar_yfull + b, ((int)rank * KH + c) * kChunkK, j0);
-        if (t < 16) TR(48 + t);
+        load_tile(t, b);
         if (++b == NB) { b = 0; ph ^= 1; }
       }
     }
@@ -2021,7 +2040,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
         uint32_t pk[32];
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4) {
-          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          const uint4 w = lds_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4));
           pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
         }
         tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
@@ -2034,10 +2053,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
         mbar_arrive_remote(bar_aall, 0);
       }
     }
+    // 1 / (column sum) of the tile's columns, double buffered.  The four warps that share a 32-column chunk all
+    // write the SAME 32 values (identical stores) and each reads only behind its own write + __syncwarp, so no
+    // CTA-wide barrier per tile is needed (it made every warp wait for the slowest one: 10 % of the epilogue's
+    // stall samples).  A warp cannot overwrite a buffer a slower warp still reads: it stores after the gempty(t-1)
+    // wait, i.e. after every warp has arrived on gfull(t-1), which follows that warp's last read of tile t-1.
     float rc_next = 0.f;
-    if (cc == 0 && !siglip) {
-      const int64_t jc = jlo + (int64_t)t_begin * kTileRows + r;
-      rcs_s[r] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+    if (!siglip) {
+      const int64_t jc = jlo + (int64_t)t_begin * kTileRows + cc * 32 + lane;
+      rcs_s[cc * 32 + lane] = (jc < n_cols) ? 1.0f / g.cs[jc] : 0.f;
+      __syncwarp();
     }
     // (Tried: software-pipelining this loop by one tile -- tcgen05.ld of tile t+1 issued before the fence and
     // the gfull arrive of tile t.  It delays gfull(t) until S(t+1) has completed, which opens a ~900-cycle
@@ -2045,9 +2070,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
     for (int t = 0; t < T; ++t) {
       const int buf = t & 1;
       const int64_t j0 = jlo + (int64_t)(t_begin + t) * kTileRows;
-      named_barrier_sync(1, kEpiThreads);
-      if (cc == 0 && t + 1 < T && !siglip) {
-        const int64_t jc = j0 + kTileRows + r;
+      if (t + 1 < T && !siglip) {
+        const int64_t jc = j0 + kTileRows + cc * 32 + lane;
         rc_next = (jc < n_cols) ? g.cs[jc] : 0.f;
       }
       mbar_wait(bar_sfull, t & 1);
@@ -2063,18 +2087,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
       grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
                                want_gs, gs_local, siglip, gsum_local);
       if (t >= 1) mbar_wait(bar_gempty, (t - 1) & 1);
-      uint8_t* grow = sm_g + (cc >> 1) * kChunkBytes + r * 128;
+      const uint32_t grow = smem_u32(sm_g + (cc >> 1) * kChunkBytes + r * 128);
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {
+      for (int c16 = 0; c16 < 4; ++c16) {   // explicit st.shared: a generic store goes through the global path (stall_lg)
         const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
-        *reinterpret_cast<uint4*>(grow + chunk * 16) =
-            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+        sts_v4(grow + chunk * 16, packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(bar_gfull, 0);
       if (threadIdx.x == 64 && t < 16) TR(96 + t);
-      if (cc == 0 && t + 1 < T) rcs_s[(buf ^ 1) * 128 + r] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+      if (t + 1 < T && !siglip) {
+        rcs_s[(buf ^ 1) * 128 + cc * 32 + lane] = (rc_next != 0.f) ? 1.0f / rc_next : 0.f;
+        __syncwarp();
+      }
     }
     mbar_wait(bar_accfull, 0);
     tc_fence_after();
@@ -2090,8 +2116,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
         uint8_t* rowp = stage + r * 128;
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4)
-          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
-              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+          sts_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4), raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
         fence_proxy_async_smem();
         named_barrier_sync(2 + cc, 128);
         if (q == 0 && lane == 0 && i0 < n_rows) {
@@ -2353,7 +2378,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc8(
         uint32_t pk[32];
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4) {
-          const uint4 w = *reinterpret_cast<const uint4*>(rowp + ((v4 ^ (r & 7)) << 4));
+          const uint4 w = lds_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4));
           pk[v4 * 4 + 0] = w.x; pk[v4 * 4 + 1] = w.y; pk[v4 * 4 + 2] = w.z; pk[v4 * 4 + 3] = w.w;
         }
         tmem_st32(tmem_base + lane_addr + kACol + c * 32, pk);
@@ -2387,12 +2412,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc8(
       grad_chunk_dispatch<F16>(raw, packed, rcs_s + buf * 128 + cc * 32, rrs, c1, c0, lo, hi, gi, j0 + cc * 32,
                                want_gs, gs_local, siglip, gsum_local);
       // G buffer t&1 was last read by G.V(t-2), which the in-order tensor pipe ran before S(t) completed
-      uint8_t* grow = sm_g + buf * Cfg::kGBuf + (cc >> 1) * kChunkBytes + r * 128;
+      const uint32_t grow = smem_u32(sm_g + buf * Cfg::kGBuf + (cc >> 1) * kChunkBytes + r * 128);
 #pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {
+      for (int c16 = 0; c16 < 4; ++c16) {   // explicit st.shared: a generic store goes through the global path (stall_lg)
         const int chunk = ((cc & 1) * 4 + c16) ^ (r & 7);
-        *reinterpret_cast<uint4*>(grow + chunk * 16) =
-            make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+        sts_v4(grow + chunk * 16, packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -2412,8 +2436,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc8(
         uint8_t* rowp = stage + r * 128;
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4)
-          *reinterpret_cast<uint4*>(rowp + ((v4 ^ (r & 7)) << 4)) =
-              make_uint4(raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
+          sts_v4(smem_u32(rowp) + ((v4 ^ (r & 7)) << 4), raw[v4 * 4], raw[v4 * 4 + 1], raw[v4 * 4 + 2], raw[v4 * 4 + 3]);
         fence_proxy_async_smem();
         named_barrier_sync(2 + cc, 128);
         if (q == 0 && lane == 0 && i0 < n_rows) {

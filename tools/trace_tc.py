@@ -48,6 +48,7 @@ def run():
     if not WARM:
         flush.zero_()
     buf.zero_()
+    torch.cuda.synchronize()
     ops.infonce_grad_pair_local(u, v, v, u, mode, d, 0, B, ls, rs, cs, cs, rs, gs0)
 
 
@@ -63,6 +64,7 @@ if kind == "fwd":
 else:
     rs, cs, dg = ops.infonce_fwd_local(u, v, mode, d, 0, B, ls)
     flush.zero_(); buf.zero_()
+    torch.cuda.synchronize()   # the backward launches with programmatic stream serialisation: it may start under buf.zero_()
     ev[0].record(); ops.infonce_grad_pair_local(u, v, v, u, mode, d, 0, B, ls, rs, cs, cs, rs, gs0); ev[1].record()
 torch.cuda.synchronize()
 print(f"CUDA events around the launch: {ev[0].elapsed_time(ev[1]) * 1e3:.1f} us")
@@ -76,7 +78,7 @@ def rel(row, k):
 
 
 tot = np.array([rel(t[i], 6) for i in used])
-gt0 = np.array([t[i, 120] for i in used]); gt1 = np.array([t[i, 121] for i in used])
+gt0 = np.array([t[i, 40] for i in used]); gt1 = np.array([t[i, 41] for i in used])
 print(f"wall clock: first entry -> last exit {(gt1.max() - gt0.min()) / 1e3:.1f} us; entry spread {(gt0.max() - gt0.min()) / 1e3:.1f} us; "
       f"exit spread {(gt1.max() - gt1.min()) / 1e3:.1f} us; median lifetime {np.median(gt1 - gt0) / 1e3:.1f} us")
 print(f"CTA lifetime (entry -> exit): min {tot.min()} median {int(np.median(tot))} max {tot.max()} cycles")
@@ -89,8 +91,12 @@ for i in used[:nprint] + used[-1:]:
         print("   epilogue tile 4: at barrier", rel(r, 14), "passed", rel(r, 15), "got S", rel(r, 84),
               " ".join(f"{n} +{int(r[8 + i] - r[84])}" for i, n in enumerate(names)))
     for name, base in (("S exec (probe)", 24), ("GV exec (probe)", 32)):
-        vals = [int(r[base + k]) for k in range(16) if r[base + k]]
+        vals = [int(r[base + k]) for k in range(16) if r[base + k]] if kind != "fwd" else []
         if vals:
+            print(f"   {name}", " ".join(f"{x:6d}" for x in vals))
+    if kind == "fwd":
+        for name, base in (("w2 ld done   ", 8), ("w17 ld done  ", 24), ("w17 epi done ", 32)):
+            vals = [rel(r, base + k) for k in range(8) if r[base + k]]
             print(f"   {name}", " ".join(f"{x:6d}" for x in vals))
     for name, base in (("tma issued   ", 48), ("S committed  ", 64), ("epi got S    ", 80), ("epi done     ", 96),
                        ("GV issued    ", 112)):
