@@ -1822,11 +1822,17 @@ struct Grad5Cfg {
   static constexpr int KH = KD / 2;
   static constexpr int kSBytes = KD * (kChunkBytes / 2);   // [KD][64 x 64]
   static constexpr int kVBytes = KH * kChunkBytes;         // [KH][128 x 64]
-  static constexpr int kTileBuf = kSBytes + kVBytes;       // = KD * kChunkBytes
-  static constexpr int kNBuf = 3;
+  // Two rings instead of three whole-tile buffers (same 3 * KD * 16 KiB): the logits half of a tile is dead as soon
+  // as S(t) has retired, the G.V half lives until G.V(t) has -- a whole-tile buffer was held for both, and every
+  // third tile waited ~500 cycles for its operands (G.V(t) done -> load of tile t+3 -> ~1450 cycles to arrive).
+  static constexpr int kNS = 2;                            // logits operands: S(t) .. S(t+1)
+  static constexpr int kNV = 4;                            // G.V operands: held from arrival to the end of G.V(t)
+  static constexpr int kRingBytes = kNS * kSBytes + kNV * kVBytes;
   static constexpr int kGBuf = 2 * kChunkBytes;
-  static constexpr int kSmem = 1024 + kNBuf * kTileBuf + kGBuf + kG4Aux;
+  static constexpr int kSmem = 1024 + kRingBytes + kGBuf + kG4Aux;
   static_assert(kSmem <= kMaxSmem, "tc5 needs d <= 256");
+  static_assert(2 * kVBytes == KD * kChunkBytes, "the owned rows are staged in the last two G.V slots");
+  static_assert(kRingBytes >= 2 * KD * kChunkBytes, "accumulator drain staging");
 };
 
 template <int KD, bool F16, bool SIG>
@@ -1835,27 +1841,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
     int64_t d, int64_t bs, int tiles_per_seg, const float* __restrict__ ls) {
   const GradDir& g = ga.dir[blockIdx.z % ga.ndir];
   using Cfg = Grad5Cfg<KD>;
-  constexpr int NB = Cfg::kNBuf, KH = Cfg::KH;
+  constexpr int NS = Cfg::kNS, NV = Cfg::kNV, KH = Cfg::KH;
   constexpr int DN = KD * 64;  // accumulator columns = padded d
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sm_y = smem;                                    // [NB] { S part [KD][64 x 64] | V part [KH][128 x 64] }
-  uint8_t* sm_g = smem + NB * Cfg::kTileBuf;               // [2 sub-tiles]
+  uint8_t* sm_y = smem;                                    // (also the accumulator drain's staging area)
+  uint8_t* sm_s = smem;                                    // [NS] logits operands   [KD][64 x 64]
+  uint8_t* sm_v = smem + NS * Cfg::kSBytes;                // [NV] G.V operands      [KH][128 x 64]
+  uint8_t* sm_g = smem + Cfg::kRingBytes;                  // [2 sub-tiles]
   uint8_t* aux = sm_g + Cfg::kGBuf;
   uint64_t* bar_afull = reinterpret_cast<uint64_t*>(aux);  // [1] own rows landed in the last tile buffer
   uint64_t* bar_aloc = bar_afull + 1;                      // [1] own rows parked in TMEM (this CTA's warps)
   uint64_t* bar_aall = bar_aloc + 1;                       // [1] leader: both CTAs' rows parked
-  uint64_t* bar_yfull = bar_aall + 1;                      // [NB] own tile operands landed
-  uint64_t* bar_pfull = bar_yfull + NB;                    // [NB] leader: the peer's tile operands landed
-  uint64_t* bar_yempty = bar_pfull + NB;                   // [NB] tile consumed (multicast commit)
-  uint64_t* bar_sfull = bar_yempty + NB;                   // [1] logits complete (multicast commit)
+  uint64_t* bar_yfull = bar_aall + 1;                      // [NS] own logits operands landed
+  uint64_t* bar_pfull = bar_yfull + NS;                    // [NS] leader: the peer's logits operands landed
+  uint64_t* bar_yempty = bar_pfull + NS;                   // [NS] logits operands consumed (multicast commit)
+  uint64_t* bar_vfull = bar_yempty + NS;                   // [NV] own G.V operands landed
+  uint64_t* bar_pvfull = bar_vfull + NV;                   // [NV] leader: the peer's G.V operands landed
+  uint64_t* bar_vempty = bar_pvfull + NV;                  // [NV] G.V operands consumed (multicast commit)
+  uint64_t* bar_sfull = bar_vempty + NV;                   // [1] logits complete (multicast commit)
   uint64_t* bar_sempty = bar_sfull + 1;                    // [1] leader: logits read by both epilogues
   uint64_t* bar_gfull = bar_sempty + 1;                    // [1] leader: both G buffers written
   uint64_t* bar_gempty = bar_gfull + 1;                    // [1] G consumed (multicast commit)
   uint64_t* bar_accfull = bar_gempty + 1;                  // [1] (multicast commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_accfull + 1);
   float* rcs_s = reinterpret_cast<float*>(aux + 512);      // [2][128]
-  uint8_t* sm_astage = sm_y + (NB - 1) * Cfg::kTileBuf;    // own rows arrive here (first used by tile NB-1)
+  uint8_t* sm_astage = sm_v + (NV - 2) * Cfg::kVBytes;     // own rows arrive here (first used by tile NV-2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                 // 0 = leader; grid = (row blocks, segments, z),
@@ -1887,10 +1898,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
     mbar_init(bar_afull, 1);
     mbar_init(bar_aloc, kEpiWarps);
     mbar_init(bar_aall, 2 * kEpiWarps);
-    for (int b = 0; b < NB; ++b) {
+    for (int b = 0; b < NS; ++b) {
       mbar_init(bar_yfull + b, 1);
       mbar_init(bar_pfull + b, 1);
       mbar_init(bar_yempty + b, 1);
+    }
+    for (int b = 0; b < NV; ++b) {
+      mbar_init(bar_vfull + b, 1);
+      mbar_init(bar_pvfull + b, 1);
+      mbar_init(bar_vempty + b, 1);
     }
     mbar_init(bar_sfull, 1);
     mbar_init(bar_sempty, 2 * kEpiWarps);
@@ -1900,25 +1916,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
     fence_barrier_init();
   }
   // One tile's operands: this CTA's 64 logits columns for every K chunk, then every tile row for its half of d.
-  auto load_tile = [&](int t, int b) {
+  auto load_s = [&](int t) {
+    const int b = t % NS;
     const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
-    uint8_t* buf = sm_y + b * Cfg::kTileBuf;
-    mbar_expect_tx(bar_yfull + b, Cfg::kTileBuf);
+    uint8_t* buf = sm_s + b * Cfg::kSBytes;
+    mbar_expect_tx(bar_yfull + b, Cfg::kSBytes);
     for (int c = 0; c < KD; ++c)
       tma_load_2d(buf + c * (kChunkBytes / 2), &g.tbp, bar_yfull + b, c * kChunkK, j0 + 64 * (int)rank);
-    for (int c = 0; c < KH; ++c)
-      tma_load_2d(buf + Cfg::kSBytes + c * kChunkBytes, &g.tb, bar_yfull + b, ((int)rank * KH + c) * kChunkK, j0);
     if (t < 16) TR(48 + t);
   };
-  // The owned rows and the first NB-1 tiles land in this CTA's own shared memory and complete on its own barriers:
+  auto load_v = [&](int t) {
+    const int b = t % NV;
+    const int j0 = (int)(jlo + (int64_t)(t_begin + t) * kTileRows);
+    uint8_t* buf = sm_v + b * Cfg::kVBytes;
+    mbar_expect_tx(bar_vfull + b, Cfg::kVBytes);
+    for (int c = 0; c < KH; ++c)
+      tma_load_2d(buf + c * kChunkBytes, &g.tb, bar_vfull + b, ((int)rank * KH + c) * kChunkK, j0);
+  };
+  // The owned rows and the first tiles land in this CTA's own shared memory and complete on its own barriers:
   // they are requested BEFORE the cluster rendezvous and the tensor-memory allocation (the operands were written
   // two kernels earlier -- the loss reduction between waits for the forward before it lets this grid start), so
   // ~1300 cycles of set-up run under the first loads' latency instead of in front of it.
-  const int kEarly = T < NB - 1 ? T : NB - 1;
+  constexpr int kEarlyMax = NS < NV - 2 ? NS : NV - 2;    // slots that are free before anything has been consumed
+  const int kEarly = T < kEarlyMax ? T : kEarlyMax;
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_afull, KD * kChunkBytes);
     for (int c = 0; c < KD; ++c) tma_load_2d(sm_astage + c * kChunkBytes, &g.ta, bar_afull, c * kChunkK, (int)i0);
-    for (int t = 0; t < kEarly; ++t) load_tile(t, t);
+    for (int t = 0; t < kEarly; ++t) { load_s(t); load_v(t); }
   }
   if (warp == 1) tmem_alloc2<512>(tmem_slot);
   tc_fence_before();
@@ -1930,24 +1954,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
 
   if (warp == 0) {
     if (lane == 0) {
-      int b = kEarly; uint32_t ph = 0;
-      if (b == NB) { b = 0; ph ^= 1; }
-      for (int t = kEarly; t < T; ++t) {
-        if (t == NB - 1) mbar_wait(bar_aloc, 0);   // the staged rows have left the last buffer
-        mbar_wait(bar_yempty + b, ph ^ 1);
-        load_tile(t, b);
-        if (++b == NB) { b = 0; ph ^= 1; }
+      for (int t = kEarly; t < T; ++t) {   // use n of a slot waits for the slot's (n-1)-th release: parity (n-1) & 1
+        mbar_wait(bar_yempty + t % NS, ((t / NS) & 1) ^ 1);
+        load_s(t);
+        if (t == NV - 2) mbar_wait(bar_aloc, 0);   // the staged rows have left the last two G.V slots
+        mbar_wait(bar_vempty + t % NV, ((t / NV) & 1) ^ 1);
+        load_v(t);
       }
     }
     __syncwarp();
   } else if (warp == 1 && rank != 0) {
     // peer: tell the leader when this CTA's operands of tile t are in shared memory
-    int b = 0; uint32_t ph = 0;
     for (int t = 0; t < T; ++t) {
-      mbar_wait(bar_yfull + b, ph);
-      if (lane == 0) mbar_arrive_remote(bar_pfull + b, 0);
+      mbar_wait(bar_yfull + t % NS, (t / NS) & 1);
+      if (lane == 0) mbar_arrive_remote(bar_pfull + t % NS, 0);
       __syncwarp();
-      if (++b == NB) { b = 0; ph ^= 1; }
+      mbar_wait(bar_vfull + t % NV, (t / NV) & 1);
+      if (lane == 0) mbar_arrive_remote(bar_pvfull + t % NV, 0);
+      __syncwarp();
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc_s = umma_idesc_16(256, 128, 0, 0, F16);
@@ -1956,18 +1980,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
     tc_fence_after();
     if (lane == 0) TR(3);
     const uint32_t s_tmem = tmem_base + kSCol, a_tmem0 = tmem_base + kACol, acc_tmem = tmem_base + kAccCol;
-    const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_y), 16);                              // K-major view (S)
-    const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_y + Cfg::kSBytes), kChunkBytes);     // MN-major view (G.V)
+    const uint32_t y_lo0 = umma_desc_lo(smem_u32(sm_s), 16);                              // K-major view (S)
+    const uint32_t y2_lo0 = umma_desc_lo(smem_u32(sm_v), kChunkBytes);                    // MN-major view (G.V)
     const uint32_t g_lo0 = umma_desc_lo(smem_u32(sm_g), 16);
-    int b = 0; uint32_t ph = 0;
-    int bg = 0;
     for (int t = 0; t <= T; ++t) {
       if (t < T) {
+        const int b = t % NS;
+        const uint32_t ph = (t / NS) & 1;
         mbar_wait(bar_yfull + b, ph);
         mbar_wait(bar_pfull + b, ph);
         if (t >= 1) mbar_wait(bar_sempty, (t - 1) & 1);
         tc_fence_after();
-        const uint32_t b_lo = y_lo0 + b * (Cfg::kTileBuf >> 4);
+        const uint32_t b_lo = y_lo0 + b * (Cfg::kSBytes >> 4);
 #ifdef PLK_TRACE_PROBE
         const long long ts0 = clock64();
 #endif
@@ -1979,6 +2003,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
               umma2_bf16_ts(s_tmem, a_tmem0 + c * 32 + k * 8, b_lo + c * (kChunkBytes >> 5) + 2 * k, idesc_s,
                             (c | k) != 0);
           umma2_commit(bar_sfull);
+          umma2_commit(bar_yempty + b);   // the logits operands are free as soon as S(t) has retired
         }
         __syncwarp();
         if (lane == 0 && t < 16) TR(64 + t);
@@ -1986,13 +2011,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
         mbar_wait(bar_sfull, t & 1);     // probe: serialise, measure issue -> completion of the 16 S MMAs
         if (lane == 0 && t < 16) TRV(24 + (t & 7), clock64() - ts0);
 #endif
-        if (++b == NB) { b = 0; ph ^= 1; }
       }
       if (t >= 1) {
         const int u = t - 1;
+        const int bg = u % NV;
+        mbar_wait(bar_vfull + bg, (u / NV) & 1);
+        mbar_wait(bar_pvfull + bg, (u / NV) & 1);
         mbar_wait(bar_gfull, u & 1);
         tc_fence_after();
-        const uint32_t b_lo = y2_lo0 + bg * (Cfg::kTileBuf >> 4);
+        const uint32_t b_lo = y2_lo0 + bg * (Cfg::kVBytes >> 4);
 #ifdef PLK_TRACE_PROBE
         const long long tg0 = clock64();
 #endif
@@ -2001,7 +2028,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
           for (int k = 0; k < kTileRows / kUmmaK; ++k)
             umma2_bf16_lo(acc_tmem, g_lo0 + (k >> 2) * (kChunkBytes >> 4) + (k & 3) * 2, b_lo + k * (2048 >> 4),
                           idesc_g, (u | k) != 0);
-          umma2_commit(bar_yempty + bg);
+          umma2_commit(bar_vempty + bg);
           umma2_commit(bar_gempty);
         }
         __syncwarp();
@@ -2010,7 +2037,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
         mbar_wait(bar_gempty, u & 1);    // probe: issue -> completion of the 8 G.V MMAs
         if (lane == 0 && u < 16) TRV(32 + (u & 7), clock64() - tg0);
 #endif
-        if (++bg == NB) bg = 0;
       }
     }
     if (elect_one()) umma2_commit(bar_accfull);
