@@ -16,12 +16,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # PLK_TRACE=1 (development only): a second library with in-kernel clock stamps (tools/trace_tc.py)
 _TRACE = os.environ.get("PLK_TRACE", "0") == "1"
-LIB_PATH = os.path.join(HERE, "libplk_trace.so" if _TRACE else "libplk.so")
-OBJ_DIR = os.path.join(HERE, "build_trace" if _TRACE else "build")
+# PLK_VARIANT_FLAGS="-DX=1 ..." (development only): a third library built with extra nvcc flags (kernel A/B runs)
+_VARIANT = os.environ.get("PLK_VARIANT_FLAGS", "").split()
+LIB_PATH = os.path.join(HERE, "libplk_trace.so" if _TRACE else ("libplk_variant.so" if _VARIANT else "libplk.so"))
+OBJ_DIR = os.path.join(HERE, "build_trace" if _TRACE else ("build_variant" if _VARIANT else "build"))
 SOURCES = ["api.cu", "elementwise.cu", "infonce_simt.cu", "topk_simt.cu", "tc_host.cu", "stager.cu",
            "infonce_tc.cu", "topk_tc.cu", "proj_tc.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC"] + (["-DPLK_TRACE"] if _TRACE else [])
+              "-Xcompiler", "-fPIC"] + (["-DPLK_TRACE"] if _TRACE else []) + _VARIANT
 
 PLK_F32, PLK_BF16, PLK_F16 = 0, 1, 2
 
