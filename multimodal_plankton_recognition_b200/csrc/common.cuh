@@ -65,23 +65,32 @@ __device__ __forceinline__ void tail_terms(const float* bias, float diag_i, cons
 //   acc_i = sum of the `parts` partial slabs;  dU = coef (acc_i + dterm p / den_p);
 //   dx = (dU - u (u . dU)) / den   (no projection term below the eps clamp of F.normalize)
 // Shared by the stand-alone tail kernels (elementwise.cu) and the tail fused into infonce_grad_tc4.
+// The row's own and partner raw rows (inputs of the step, never written by it): loaded first -- in the stand-alone
+// tail even before griddepcontrol.wait, under the last thread blocks of the backward.
 template <int NV>
-__device__ __forceinline__ void finish_row_vec(const float* __restrict__ acc_row, int parts, int64_t slab4,
-                                               const float* __restrict__ x_row, const float* __restrict__ p_row,
-                                               float coef, float dterm, float idx_, float idp, bool clamped,
-                                               float* __restrict__ dx_row, int lane) {
-  const float4* ar = reinterpret_cast<const float4*>(acc_row);
+__device__ __forceinline__ void finish_row_load_inputs(const float* __restrict__ x_row, const float* __restrict__ p_row,
+                                                       float4 (&xv)[NV], float4 (&pv)[NV], int lane) {
   const float4* xr = reinterpret_cast<const float4*>(x_row);
   const float4* pr = reinterpret_cast<const float4*>(p_row);
-  // every load of the row (first two partial slabs, own row, partner row) is issued before the first use
-  float4 acc[NV], acc1[NV], xv[NV], pv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    xv[i] = xr[lane + 32 * i];
+    pv[i] = pr[lane + 32 * i];
+  }
+}
+template <int NV>
+__device__ __forceinline__ void finish_row_vec_loaded(const float* __restrict__ acc_row, int parts, int64_t slab4,
+                                                      float4 (&xv)[NV], float4 (&pv)[NV], float coef, float dterm,
+                                                      float idx_, float idp, bool clamped, float* __restrict__ dx_row,
+                                                      int lane) {
+  const float4* ar = reinterpret_cast<const float4*>(acc_row);
+  // every load of the row's partial slabs is issued before the first use
+  float4 acc[NV], acc1[NV];
   const bool two = parts > 1;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     acc[i] = ar[lane + 32 * i];
     acc1[i] = two ? ar[lane + 32 * i + slab4] : make_float4(0.f, 0.f, 0.f, 0.f);
-    xv[i] = xr[lane + 32 * i];
-    pv[i] = pr[lane + 32 * i];
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -112,6 +121,15 @@ __device__ __forceinline__ void finish_row_vec(const float* __restrict__ acc_row
   for (int i = 0; i < NV; ++i)
     dr[lane + 32 * i] = make_float4((acc[i].x - xv[i].x * dot) * idx_, (acc[i].y - xv[i].y * dot) * idx_,
                                     (acc[i].z - xv[i].z * dot) * idx_, (acc[i].w - xv[i].w * dot) * idx_);
+}
+template <int NV>
+__device__ __forceinline__ void finish_row_vec(const float* __restrict__ acc_row, int parts, int64_t slab4,
+                                               const float* __restrict__ x_row, const float* __restrict__ p_row,
+                                               float coef, float dterm, float idx_, float idp, bool clamped,
+                                               float* __restrict__ dx_row, int lane) {
+  float4 xv[NV], pv[NV];
+  finish_row_load_inputs<NV>(x_row, p_row, xv, pv, lane);
+  finish_row_vec_loaded<NV>(acc_row, parts, slab4, xv, pv, coef, dterm, idx_, idp, clamped, dx_row, lane);
 }
 #endif
 

@@ -526,7 +526,23 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     float* __restrict__ gs, const float* __restrict__ diag_sum, float* __restrict__ dls_out, XGpuArgs xg) {
   constexpr int64_t d = NV * 128;
   const int m = blockIdx.y;
-  pdl_wait();   // launched under the tail of the recompute backward
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // Launched under the tail of the recompute backward.  Everything that kernel does not write -- the raw rows, the
+  // statistics of the normalisation and of the forward (both complete before the backward could start), the
+  // upstream gradient -- is fetched BEFORE griddepcontrol.wait; only the partial slabs and sum G*S come after it.
+  float4 xv[NV], pv[NV];
+  float coef = 0.f, dterm = 0.f, idx_ = 0.f, idp = 0.f;
+  bool clamped = false;
+  if (row < n) {
+    finish_row_load_inputs<NV>(a.x[m] + row * ldx, a.x[1 - m] + row * ldx, xv, pv, lane);
+    const float s = expf(*ls);
+    tail_terms(a.bias, diag[row], rs, cs, row, s, (*grad_out) * a.emb_scale, batch, coef, dterm);
+    idx_ = a.inv_den[m][row];
+    idp = a.inv_den[1 - m][row];
+    clamped = !(a.nrm[m][row] > kNormEps);
+  }
+  pdl_wait();
   if (blockIdx.x == 0 && m == 0 && threadIdx.x < 32 && dls_out != nullptr) {
     float dls_local = 0.f;
     if (threadIdx.x == 0) {
@@ -546,14 +562,9 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
   if (xg.peer != nullptr && blockIdx.x == gridDim.x - 1 && m == (int)gridDim.y - 1 && threadIdx.x < 32 &&
       dls_out != nullptr)
     xgpu_collect(xg);
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
-  const float s = expf(*ls);
-  float coef, dterm;
-  tail_terms(a.bias, diag[row], rs, cs, row, s, (*grad_out) * a.emb_scale, batch, coef, dterm);
-  finish_row_vec<NV>(a.acc[m] + row * d, parts, n * d / 4, a.x[m] + row * ldx, a.x[1 - m] + row * ldx, coef, dterm,
-                     a.inv_den[m][row], a.inv_den[1 - m][row], !(a.nrm[m][row] > kNormEps), a.dx[m] + row * d, lane);
+  finish_row_vec_loaded<NV>(a.acc[m] + row * d, parts, n * d / 4, xv, pv, coef, dterm, idx_, idp, clamped,
+                            a.dx[m] + row * d, lane);
 }
 
 template <typename TI>
