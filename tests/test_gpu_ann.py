@@ -59,6 +59,25 @@ def test_against_oracle(ng, nq, d, k, precision):
     np.testing.assert_array_equal(clf.predict(q, k=k, epsilon=.3), want.predict(q, k=k))
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sliced_upload_equals_one_upload(precision):
+    """Large host query matrices are uploaded in slices under the search of the previous slice
+    (GpuExactIndex.search_host): same neighbours, distances and labels as one upload, ragged last slice included."""
+    from multimodal_plankton_recognition_b200 import ANNClassifier
+    gal, yg = _clustered(3000, 128, 27, 1)
+    q, _ = _clustered(1111, 128, 27, 2, noise=1.1)
+    clf = ANNClassifier(gal, yg, plk_precision=precision, **KW)
+    wi, wd = clf.kneighbors(q, k=10)[0]
+    wl = clf.predict(q, k=10)
+    clf.index.PIPELINE_MIN_BYTES = 0
+    clf.index.PIPELINE_SLICE_BYTES = 256 * 128 * 4 + 7       # 5 slices of 256 queries, the last one ragged (87)
+    gi, gd = clf.kneighbors(q, k=10)[0]
+    np.testing.assert_array_equal(gi, wi)
+    np.testing.assert_array_equal(gd, wd)
+    np.testing.assert_array_equal(clf.predict(q, k=10), wl)
+    np.testing.assert_array_equal(clf.predict_multi_k(q, ks=(1, 5, 10))[10], wl)
+
+
 def test_two_modalities_and_fold_setups():
     """The 8 set-ups of reference scripts/benchmark_cross.py:57-86 on a synthetic fold: labels identical to
     the oracle for k in (1,3,5,7,9) and the BASELINE k=10."""
