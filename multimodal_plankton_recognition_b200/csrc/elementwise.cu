@@ -518,14 +518,17 @@ struct FinishPairArgs {
   const double* sig_sums;
   float* dbias_out;
 };
-template <int NV>
+// BOTH = true (d <= 512): one warp finishes row i of BOTH modalities -- the two raw rows are each other's partner, so
+// they are loaded once instead of twice (32 MB instead of 40 MB through L2 per step at B = 4096, d = 256; the tail is
+// bound by exactly that traffic).  BOTH = false: blockIdx.y selects the modality (wide rows: register budget).
+template <int NV, bool BOTH>
 __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     FinishPairArgs a, int parts, int64_t n, int64_t ldx, const float* __restrict__ diag,
     const float* __restrict__ rs, const float* __restrict__ cs, const float* __restrict__ ls,
     const float* __restrict__ grad_out, const float* __restrict__ grad_out_dls, int64_t batch,
     float* __restrict__ gs, const float* __restrict__ diag_sum, float* __restrict__ dls_out, XGpuArgs xg) {
   constexpr int64_t d = NV * 128;
-  const int m = blockIdx.y;
+  const int m = BOTH ? 0 : blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   // Launched under the tail of the recompute backward.  Everything that kernel does not write -- the raw rows, the
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
   // upstream gradient -- is fetched BEFORE griddepcontrol.wait; only the partial slabs and sum G*S come after it.
   float4 xv[NV], pv[NV];
   float coef = 0.f, dterm = 0.f, idx_ = 0.f, idp = 0.f;
-  bool clamped = false;
+  bool clamped = false, clamped_p = false;
   if (row < n) {
     finish_row_load_inputs<NV>(a.x[m] + row * ldx, a.x[1 - m] + row * ldx, xv, pv, lane);
     const float s = expf(*ls);
@@ -541,6 +544,7 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     idx_ = a.inv_den[m][row];
     idp = a.inv_den[1 - m][row];
     clamped = !(a.nrm[m][row] > kNormEps);
+    if constexpr (BOTH) clamped_p = !(a.nrm[1 - m][row] > kNormEps);
   }
   pdl_wait();
   if (blockIdx.x == 0 && m == 0 && threadIdx.x < 32 && dls_out != nullptr) {
@@ -559,12 +563,22 @@ __global__ void __launch_bounds__(256) grad_finish_pair_vec_kernel(
     }
     if (xg.peer != nullptr) xgpu_publish(xg, threadIdx.x == 0 ? *xg.loss_partial : 0.f, dls_local);
   }
-  if (xg.peer != nullptr && blockIdx.x == gridDim.x - 1 && m == (int)gridDim.y - 1 && threadIdx.x < 32 &&
+  if (xg.peer != nullptr && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && threadIdx.x < 32 &&
       dls_out != nullptr)
     xgpu_collect(xg);
   if (row >= n) return;
-  finish_row_vec_loaded<NV>(a.acc[m] + row * d, parts, n * d / 4, xv, pv, coef, dterm, idx_, idp, clamped,
-                            a.dx[m] + row * d, lane);
+  if constexpr (BOTH) {
+    float4 xo[NV], po[NV];   // finish_row_vec_loaded scales its own row in place: the partner's tail needs the raw rows
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { xo[i] = pv[i]; po[i] = xv[i]; }
+    finish_row_vec_loaded<NV>(a.acc[0] + row * d, parts, n * d / 4, xv, pv, coef, dterm, idx_, idp, clamped,
+                              a.dx[0] + row * d, lane);
+    finish_row_vec_loaded<NV>(a.acc[1] + row * d, parts, n * d / 4, xo, po, coef, dterm, idp, idx_, clamped_p,
+                              a.dx[1] + row * d, lane);
+  } else {
+    finish_row_vec_loaded<NV>(a.acc[m] + row * d, parts, n * d / 4, xv, pv, coef, dterm, idx_, idp, clamped,
+                              a.dx[m] + row * d, lane);
+  }
 }
 
 template <typename TI>
@@ -865,10 +879,12 @@ static int finish_pair_impl(const float* acc_x, const float* acc_y, int parts, c
     a.dx[0] = dx; a.dx[1] = dy;
     a.emb_scale = emb_scale;
     a.bias = bias; a.sig_sums = sig_sums; a.dbias_out = dbias_out;
-    dim3 block(256), grid((unsigned)ceil_div(n, 8), 2);
+    const bool both = d <= 512;   // one warp per row PAIR (see grad_finish_pair_vec_kernel)
+    dim3 block(256), grid((unsigned)ceil_div(n, 8), both ? 1 : 2);
     switch (d / 128) {
-#define PLK_CASE(NV) case NV: PLK_CUDA(launch_overlapped(grad_finish_pair_vec_kernel<NV>, grid, block, st, a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out, xg)); break;
-      PLK_CASE(1) PLK_CASE(2) PLK_CASE(3) PLK_CASE(4) PLK_CASE(5) PLK_CASE(6) PLK_CASE(7) PLK_CASE(8)
+#define PLK_CASE(NV, BOTH) case NV: PLK_CUDA(launch_overlapped(grad_finish_pair_vec_kernel<NV, BOTH>, grid, block, st, a, parts, n, ldx, diag, rs, cs, logit_scale, grad_out_emb, grad_out, batch_global, gs, diag_sum, dls_out, xg)); break;
+      PLK_CASE(1, true) PLK_CASE(2, true) PLK_CASE(3, true) PLK_CASE(4, true)
+      PLK_CASE(5, false) PLK_CASE(6, false) PLK_CASE(7, false) PLK_CASE(8, false)
 #undef PLK_CASE
     }
     PLK_LAUNCHED(1);
