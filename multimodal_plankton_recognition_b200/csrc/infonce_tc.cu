@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
     // ring slots as well, including the tail slots the owned rows are staged in
     mbar_init(bar_a, CS * (kEpiThreads / 32));
     mbar_init(bar_afull, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_sfull + b, 1); mbar_init(bar_sempty + b, kEpiThreads / 32); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -400,7 +400,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cc * 32, raw);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar_sempty + buf);   // the accumulator buffer goes back to the MMA warp right away
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sempty + buf);   // the accumulator buffer goes back to the MMA warp right away
+                                                      // (one arrive per warp: 512 arrives on one word cost MIO slots)
       if (threadIdx.x == 64 && t < 8) TR(8 + t);              // trace: first epilogue warp has its logits
       if (threadIdx.x == 17 * 32 && t < 8) TR(24 + t);        // trace: last epilogue warp has its logits
       const bool full = (j0 >= lo) && (j0 + 32 <= hi);

@@ -43,7 +43,8 @@ def timed(fn, n=50):
         b.record()
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in evs)
-    return ts[len(ts) // 2] * 1e3, ts[0] * 1e3      # median, best (us)
+    # CUDA event stamps tick every 2.048 us on these boxes: medians land on multiples of it, the MEAN resolves finer
+    return sum(ts) / len(ts) * 1e3, ts[0] * 1e3      # mean, best (us)
 
 
 shapes = [(4096, 256, 1), (4096, 128, 1), (8192, 256, 1), (16384, 256, 1), (4096, 256, 8), (4096, 512, 1)]
