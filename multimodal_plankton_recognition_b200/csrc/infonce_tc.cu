@@ -1891,6 +1891,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
   }
   if (threadIdx.x == 0) TR(0);
   pdl_trigger();
+  // Scalars of the epilogue (temperature, bias, this thread's row sum): requested at entry, first used after the
+  // owned rows are parked -- the two dependent global round trips used to sit between the set-up and the parking
+  // (~2000 cycles of the prologue; inputs of this kernel were written before the loss reduction let it start).
+  float pre_ls = 0.f, pre_bias = 0.f, pre_rs = 1.f;
+  if (warp >= 2) {
+    pre_ls = *ls;
+    if (SIG) pre_bias = *ga.bias;
+    const int64_t ip = i0 + (warp & 3) * 32 + lane;
+    if (!SIG && ip < n_rows) pre_rs = g.rs[ip];
+  }
 
   constexpr int kEpiWarps = kEpiThreads / 32;
   if (threadIdx.x == 0) {
@@ -2052,12 +2062,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
     int64_t lo = 0, hi = 0;
     float rrs = 0.f;
     constexpr bool siglip = SIG;
-    if (i < n_rows) {
-      bucket_range(gi, bs, n_cols, lo, hi);
-      if (!siglip) rrs = 1.0f / g.rs[i];
-    }
-    const float s = expf(*ls);
-    const float c1 = s * kLog2e, c0 = siglip ? *ga.bias * kLog2e : (kShiftK - s) * kLog2e;
+    if (i < n_rows) bucket_range(gi, bs, n_cols, lo, hi);
     const bool want_gs = g.gs != nullptr;
     float gs_local = 0.f, gsum_local = 0.f;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -2081,6 +2086,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_grad_tc5(
         mbar_arrive_remote(bar_aall, 0);
       }
     }
+    if (i < n_rows && !siglip) rrs = 1.0f / pre_rs;
+    const float s = expf(pre_ls);
+    const float c1 = s * kLog2e, c0 = siglip ? pre_bias * kLog2e : (kShiftK - s) * kLog2e;
     // 1 / (column sum) of the tile's columns, double buffered.  The four warps that share a 32-column chunk all
     // write the SAME 32 values (identical stores) and each reads only behind its own write + __syncwarp, so no
     // CTA-wide barrier per tile is needed (it made every warp wait for the slowest one: 10 % of the epilogue's
