@@ -63,6 +63,10 @@ __device__ __forceinline__ void row_block_cols(int64_t i0, int64_t n_rows, int64
   jhi = hi2;
 }
 
+#ifndef PLK_FWD_TT
+#define PLK_FWD_TT 1   // forward column sums through a tensor-memory transposition (see infonce_fwd_tc); 0: 31-shuffle transpose-reduce
+#endif
+
 // column sums over the 32 lanes of a warp for 32 columns held one-row-per-lane:
 // on return v[0] of lane l is the sum of column l.
 __device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane) {
@@ -401,8 +405,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sempty + buf);   // the accumulator buffer goes back to the MMA warp right away
-                                                      // (one arrive per warp: 512 arrives on one word cost MIO slots)
+      // the accumulator buffer goes back to the MMA warp right away (one arrive per warp: 512 arrives on one word cost
+      // MIO slots) -- except for InfoNCE under PLK_FWD_TT, where the chunk is reused for the column-sum transposition
+      if (lane == 0 && (!PLK_FWD_TT || siglip)) mbar_arrive(bar_sempty + buf);
       if (threadIdx.x == 64 && t < 8) TR(8 + t);              // trace: first epilogue warp has its logits
       if (threadIdx.x == 17 * 32 && t < 8) TR(24 + t);        // trace: last epilogue warp has its logits
       const bool full = (j0 >= lo) && (j0 + 32 <= hi);
@@ -475,10 +480,54 @@ __global__ void __launch_bounds__(kNumThreads, 1) infonce_fwd_tc(
 #pragma unroll
       for (int e = 0; e < 32; e += 4) { p0 += v[e]; p1 += v[e + 1]; p2 += v[e + 2]; p3 += v[e + 3]; }
       rsum += (p0 + p1) + (p2 + p3);
+#if PLK_FWD_TT
+      {
+        // Column sums through tensor memory: E goes back into the chunk it came from (32x32b: thread = row) and is
+        // read as two 16x256b fragments (thread = 4 rows x 8 columns), so 24 of the 31 cross-lane steps become
+        // in-thread adds: 7 shuffles per 32 x 32 block instead of 31 (the MIO queue is shared with the 32 MUFU.EX2).
+        const uint32_t chunk_addr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128 + cc * 32;
+        uint32_t eb[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) eb[e] = __float_as_uint(v[e]);
+        tmem_st32(chunk_addr, eb);
+        tmem_st_wait();
+        uint32_t f0[16], f1[16];
+        tmem_ld_16x256b_x4(chunk_addr, f0);                      // lanes q*32 + 0..15
+        tmem_ld_16x256b_x4(chunk_addr + (16u << 16), f1);        // lanes q*32 + 16..31
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sempty + buf);
+        // r[4n + 2h + b] = (row t/4 + 8h, column 8n + 2(t%4) + b): add the thread's four rows
+        float c8[8];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+            c8[n * 2 + b] = (__uint_as_float(f0[4 * n + b]) + __uint_as_float(f0[4 * n + 2 + b])) +
+                            (__uint_as_float(f1[4 * n + b]) + __uint_as_float(f1[4 * n + 2 + b]));
+        // the 8 lanes t%4 + 4k share these 8 columns: transpose-reduce over lane bits 4, 3, 2
+#pragma unroll
+        for (int h = 4; h >= 1; h >>= 1) {
+          const bool up = (lane & (h * 4)) != 0;
+#pragma unroll
+          for (int x = 0; x < h; ++x) {
+            const float keep = up ? c8[x + h] : c8[x];
+            const float send = up ? c8[x] : c8[x + h];
+            c8[x] = keep + __shfl_xor_sync(0xffffffffu, send, h * 4);
+          }
+        }
+        // lane bits 4, 3 picked n, bit 2 picked b
+        const int col = 8 * (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)) + 2 * (lane & 3) + ((lane >> 2) & 1);
+        const int64_t j = j0 + col;
+        if (j < n_cols && c8[0] != 0.f) atomicAdd(col_sumexp + j, c8[0]);
+      }
+#else
       // column sums over this warp's 32 rows, then one 128-byte reduction per warp
       warp_transpose_reduce(v, lane);
       const int64_t j = j0 + lane;
       if (j < n_cols && v[0] != 0.f) atomicAdd(col_sumexp + j, v[0]);
+#endif
       if (threadIdx.x == 64 && t < 16) TR(96 + t);
       if (threadIdx.x == 17 * 32 && t < 8) TR(32 + t);        // trace: last epilogue warp done
     }
