@@ -9,8 +9,9 @@
 // streams [128 x 64] chunks of the "b" operand.  The B x B logits only ever exist as 128x128 fp32
 // tiles in TMEM (double buffered so the epilogue of tile t overlaps the MMAs of tile t+1).
 //
-// Forward epilogue  : E = exp2(acc*s*log2e - s*log2e); row sums in registers, column sums by a
-//                     31-shuffle transpose-reduce per 32 columns, diagonal pick.
+// Forward epilogue  : E = exp2(acc*s*log2e - (s - 64)*log2e); row sums in registers, diagonal pick; column sums by
+//                     storing E back into its tensor-memory chunk and re-reading it as 16x256b fragments (four rows
+//                     per thread), then 7 shuffles per 32 columns (PLK_FWD_TT=0: the 31-shuffle transpose-reduce).
 // Backward epilogue : G = E*(1/rs_i + 1/cs_j) -> bf16 -> shared memory (swizzled K-major A operand),
 //                     then a second tcgen05.mma  acc[128 x 64*c] += G . b_chunk  with the streamed
 //                     chunk reused as an MN-major B operand; acc (<= 256 fp32 columns) stays in TMEM

@@ -120,6 +120,19 @@ def test_against_oracle(B, d, buckets, ls, precision):
            floor=_floor(img, pro, ls, buckets, precision))
 
 
+@pytest.mark.parametrize("B,d", [(256, 640), (130, 1024)])
+def test_wide_rows_fp32(B, d):
+    """d > 512 is served by the fp32 kernels; the gradient tail then runs one warp per row and modality
+    (grad_finish_pair_vec_kernel<NV, false>), not one warp per row pair as for d <= 512."""
+    r = np.random.default_rng(B + d)
+    z = r.standard_normal((B, d))
+    img = (z + 0.4 * r.standard_normal((B, d))).astype(np.float32)
+    pro = (z + 0.4 * r.standard_normal((B, d))).astype(np.float32)
+    ref = oinf.clip_loss_closed_form(img, pro, 1.0, 1)
+    _check(_run(img, pro, 1.0, 1, "fp32"), ref, TOL["fp32"], ls=1.0, precision="fp32",
+           floor=_floor(img, pro, 1.0, 1, "fp32"))
+
+
 @pytest.mark.parametrize("precision", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("ls", [3.7, 4.6])
 def test_large_temperature(ls, precision):
