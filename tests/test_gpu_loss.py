@@ -120,6 +120,25 @@ def test_against_oracle(B, d, buckets, ls, precision):
            floor=_floor(img, pro, ls, buckets, precision))
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("d", [128, 256])
+def test_zero_norm_rows_in_the_row_pair_tail(d, precision):
+    """Zero rows (below F.normalize's eps clamp: dx = dU / eps, no projection term) in EITHER modality at a width
+    the vectorised gradient tail serves -- one warp finishes row i of both modalities there, each with its own
+    clamp flag.  (The reference-generated edge golden has d = 64, which takes the scalar tail.)"""
+    r = np.random.default_rng(d)
+    B = 256
+    z = r.standard_normal((B, d))
+    img = (z + 0.4 * r.standard_normal((B, d))).astype(np.float32)
+    pro = (z + 0.4 * r.standard_normal((B, d))).astype(np.float32)
+    img[3] = 0.0      # image row 3 and profile row 5 are zero; row 7 is zero in both
+    pro[5] = 0.0
+    img[7] = 0.0
+    pro[7] = 0.0
+    ref = oinf.clip_loss_closed_form(img, pro, 1.0, 1)
+    _check(_run(img, pro, 1.0, 1, precision), ref, TOL[precision], [3, 5, 7], 1.0, precision)
+
+
 @pytest.mark.parametrize("B,d", [(256, 640), (130, 1024)])
 def test_wide_rows_fp32(B, d):
     """d > 512 is served by the fp32 kernels; the gradient tail then runs one warp per row and modality
