@@ -25,6 +25,14 @@ from . import _lib, ops
 from ._lib import PLK_F32
 
 
+def upload_slice_rows(nq: int, nbytes: int, slice_bytes: int) -> int:
+    """Rows per slice when a host query matrix of `nq` rows / `nbytes` bytes is uploaded in slices of about
+    `slice_bytes`: equal slices, rounded up to whole pairs of 128-query blocks (the search kernel's cluster unit)."""
+    n_slices = max(1, -(-nbytes // max(1, slice_bytes)))
+    rows = -(-nq // n_slices)
+    return -(-rows // 256) * 256
+
+
 class GpuExactIndex:
     """Gallery resident in HBM: fp32 rows (exact re-score) + operand copy (bf16 padded or fp32)
     + squared norms.  ``gallery_offset`` makes returned indices global when the gallery is a shard."""
@@ -123,9 +131,7 @@ class GpuExactIndex:
         nq = x.shape[0]
         if x.nbytes < self.PIPELINE_MIN_BYTES:
             return self.search_device(torch.from_numpy(x).to(self.device), k)
-        n_slices = -(-x.nbytes // self.PIPELINE_SLICE_BYTES)
-        rows = -(-nq // n_slices)
-        rows = -(-rows // 256) * 256          # whole pairs of 128-query blocks (the kernel's cluster unit)
+        rows = upload_slice_rows(nq, x.nbytes, self.PIPELINE_SLICE_BYTES)
         main = torch.cuda.current_stream(self.device)
         copy = torch.cuda.Stream(self.device)
         parts = []

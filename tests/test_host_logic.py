@@ -82,3 +82,17 @@ def test_sharded_module_keeps_nccl_path_without_cuda():
     from multimodal_plankton_recognition_b200 import CLIPLoss
     mod = CLIPLoss(sharded=True)
     assert mod._peer_scalars(torch.randn(8, 4), 2) is None and mod._xgpu is None and not mod._xgpu_tried
+
+
+def test_upload_slices_cover_every_query_once():
+    """GpuExactIndex.search_host: equal slices of whole 256-query units, the last one ragged."""
+    from multimodal_plankton_recognition_b200.ann import upload_slice_rows
+    for nq, d, sb in ((100000, 512, 32 << 20), (1111, 128, 256 * 128 * 4 + 7), (256, 64, 1), (5, 8, 1 << 30),
+                      (70000, 200, 10 << 20)):
+        rows = upload_slice_rows(nq, nq * d * 4, sb)
+        assert rows > 0 and rows % 256 == 0
+        starts = list(range(0, nq, rows))
+        assert sum(min(rows, nq - s) for s in starts) == nq
+        # no more slices than asked for (rounding up to 256 rows only ever makes slices larger)
+        assert len(starts) <= max(1, -(-(nq * d * 4) // sb))
+    assert upload_slice_rows(100000, 100000 * 512 * 4, 32 << 20) == 14336   # the C4 query matrix: 7 slices
